@@ -1,0 +1,151 @@
+/*
+ * vwb200.h -- C ABI of the B200-native stereo-correlation engine.
+ *
+ * This is the drop-in boundary for Vision Workbench's dense block-matching path.  VW has no
+ * FFI: its "operator API" is the compile-time ImageViewBase<> concept
+ * (src/vw/Image/ImageViewBase.h:57-122).  The C++ shim include/vwb200/PyramidCorrelationView.h
+ * keeps that concept (prerasterize()/rasterize()) and calls the functions below; no C++ or
+ * torch types cross this boundary -- plain pointers, sizes and POD structs only.
+ *
+ * Conventions
+ *  - images are row-major, one plane, pitch in ELEMENTS (vw::ImageView, Image/ImageView.h:226-227)
+ *  - boxes are half-open [x0,x1) x [y0,y1) (vw::BBox2i, Math/BBox.tcc)
+ *  - integer disparity pixel = {int32 dx, int32 dy, int32 valid(0/1)}   (PixelMask<Vector2i>)
+ *  - float   disparity pixel = {float dx, float dy, float valid(0/1)}   (PixelMask<Vector2f>,
+ *    Image/PixelMask.h:52-54: 12 bytes)
+ *  - every function returns 0 on success or a negative VWB200_E* code; vwb200_last_error()
+ *    gives the message of the calling thread's last failure.  The shim maps codes to
+ *    vw::ArgumentErr / MathErr / LogicErr (Core/Exception.h:225-253).
+ *  - "on_device" != 0 means the pointers are CUDA device pointers on the current device;
+ *    otherwise they are host pointers and the call stages them through HBM itself.
+ *  - `stream` is a cudaStream_t (or NULL for the library's own per-call stream).  All calls
+ *    block until their result is complete unless stated otherwise.
+ *  - all entry points are thread-safe (VW calls prerasterize() concurrently from its tile
+ *    thread pool, Image/ImageIO.h:228-235).
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *    VWB200_ENODEVICE.
+ */
+#ifndef VWB200_H
+#define VWB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VWB200_OK          0
+#define VWB200_EARG       -1   /* -> vw::ArgumentErr */
+#define VWB200_EMATH      -2   /* -> vw::MathErr     */
+#define VWB200_ELOGIC     -3   /* -> vw::LogicErr    */
+#define VWB200_ENOIMPL    -4   /* -> vw::NoImplErr   */
+#define VWB200_ECUDA      -5   /* CUDA runtime failure */
+#define VWB200_ENODEVICE  -6   /* no CUDA device: the engine has no CPU path */
+#define VWB200_ENOMEM     -7
+
+/* vw::stereo::CostFunctionType, src/vw/Stereo/CostFunctions.h:143-149 */
+enum { VWB200_ABSOLUTE_DIFFERENCE = 0, VWB200_SQUARED_DIFFERENCE = 1, VWB200_CROSS_CORRELATION = 2 };
+/* vw::stereo::PrefilterModeType, src/vw/Stereo/PrefilterEnum.h:24-28 */
+enum { VWB200_PREFILTER_NONE = 0, VWB200_PREFILTER_LOG = 1, VWB200_PREFILTER_MEANSUB = 2 };
+
+typedef struct { int32_t dx, dy, valid; } vwb200_dispi;
+
+const char* vwb200_last_error(void);
+int vwb200_device_count(void);          /* number of visible CUDA devices (0 if none) */
+const char* vwb200_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1: vw::stereo::calc_disparity (src/vw/Stereo/Correlation.h:50-57, Correlation.cc:330-375)
+ * -> best_of_search_convolution (Correlation.cc:33-137).
+ * left  : (W+kx-1) x (H+ky-1) float; right: at least (W+kx-1+sx-1) x (H+ky-1+sy-1) float.
+ * out   : W x H vwb200_dispi, disparities in [0,sx) x [0,sy), first-in-raster-order wins ties,
+ *         pixel invalid iff every disparity gave the same cost (Correlation.cc:121-133).
+ * ------------------------------------------------------------------------------------------- */
+int vwb200_calc_disparity(int cost_type,
+                          const float* left,  int lw, int lh, ptrdiff_t lpitch,
+                          const float* right, int rw, int rh, ptrdiff_t rpitch,
+                          int sx, int sy, int kx, int ky,
+                          vwb200_dispi* out, ptrdiff_t opitch,
+                          int on_device, void* stream);
+
+/* Statistics of the last vwb200_calc_disparity on this thread: which kernel path ran
+ * (0 = exact-integer fast path, 1 = general fp64 path), kernel launches issued. */
+typedef struct { int32_t path; int32_t launches; int32_t flagged_pixels; int32_t reserved; } vwb200_k1_stats;
+int vwb200_last_k1_stats(vwb200_k1_stats* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2: one Gaussian-pyramid level = subsample(separable_convolution_filter(in,{1,4,6,4,1}/16),2)
+ * (src/vw/Stereo/CorrelationView.cc:210-214; Image/Convolution.h:275-328; Image/Filter.h:89-99;
+ *  Image/Manipulation.h:238-251).  out is (1+(w-1)/2) x (1+(h-1)/2).  Bit-exact in float.
+ * ------------------------------------------------------------------------------------------- */
+int vwb200_pyramid_down(const float* in, int w, int h, ptrdiff_t pitch,
+                        float* out, ptrdiff_t opitch, int on_device, void* stream);
+/* SubsampleMaskByTwoFunc, src/vw/Stereo/CorrelationView.cc:38-63 */
+int vwb200_subsample_mask_by_two(const uint8_t* in, int w, int h, ptrdiff_t pitch,
+                                 uint8_t* out, ptrdiff_t opitch, int on_device, void* stream);
+
+/* K3: vw::stereo::cross_corr_consistency_check (src/vw/Stereo/Correlate.cc:1441-1502), in place */
+int vwb200_cross_corr_consistency_check(vwb200_dispi* l2r, int lw, int lh, ptrdiff_t lpitch,
+                                        const vwb200_dispi* r2l, int rw, int rh, ptrdiff_t rpitch,
+                                        float threshold, int on_device, void* stream);
+
+/* K4: rm_outliers_using_thresh / disparity_cleanup_using_thresh / disparity_mask
+ * (src/vw/Stereo/DisparityMap.h:318-442, :97-253).  in/out are w x h, dense pitch. */
+int vwb200_rm_outliers_using_thresh(const vwb200_dispi* in, int w, int h, int half_h, int half_v,
+                                    double pixel_threshold, double rejection_threshold,
+                                    vwb200_dispi* out, int on_device, void* stream);
+int vwb200_disparity_cleanup_using_thresh(const vwb200_dispi* in, int w, int h, int half_h, int half_v,
+                                          double pixel_threshold, double rejection_threshold,
+                                          vwb200_dispi* out, int on_device, void* stream);
+int vwb200_disparity_mask(const vwb200_dispi* in, int w, int h,
+                          const uint8_t* left_mask, const uint8_t* right_mask, int rmw, int rmh,
+                          vwb200_dispi* out, int on_device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The lazy view: vw::stereo::PyramidCorrelationView (src/vw/Stereo/CorrelationView.h:35-193,
+ * CorrelationView.cc:273-886) behind a handle.  vwb200_corr_params mirrors the constructor
+ * arguments (CorrelationView.h:48-69) that the block-matching algorithm uses.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t search_x0, search_y0, search_x1, search_y1;   /* BBox2i search_region */
+  int32_t kernel_x, kernel_y;                           /* Vector2i kernel_size (odd) */
+  int32_t cost_type;                                    /* CostFunctionType */
+  int32_t prefilter_mode; float prefilter_width;
+  float   consistency_threshold;                        /* < 0: no L/R check */
+  int32_t min_consistency_level;
+  int32_t filter_half_kernel;
+  int32_t max_pyramid_levels;
+  int32_t collar_size;
+  int32_t corr_timeout; double seconds_per_op;          /* accepted; timeouts never trigger on the GPU */
+  int32_t algorithm;                                    /* 0 = VW_CORRELATION_BM (only one implemented) */
+  int32_t blob_filter_area;                             /* must be 0 (CorrelationView.cc:249-250) */
+} vwb200_corr_params;
+
+typedef struct vwb200_corr vwb200_corr;
+
+int  vwb200_corr_create(const vwb200_corr_params* p, vwb200_corr** out);
+/* Inputs are copied to (or, if on_device, referenced in) HBM once; they must outlive the handle
+ * when on_device != 0.  Masks are uint8, nonzero = valid, same size as their image. */
+int  vwb200_corr_set_inputs(vwb200_corr* h,
+                            const float* left,  int lcols, int lrows, ptrdiff_t lpitch,
+                            const float* right, int rcols, int rrows, ptrdiff_t rpitch,
+                            const uint8_t* lmask, ptrdiff_t lmpitch,
+                            const uint8_t* rmask, ptrdiff_t rmpitch, int on_device);
+int  vwb200_corr_cols(const vwb200_corr* h);
+int  vwb200_corr_rows(const vwb200_corr* h);
+/* rasterize(dest, bbox): dest receives (x1-x0) x (y1-y0) float disparity pixels (3 floats each),
+ * row pitch dest_pitch in PIXELS.  Collar handling as in CorrelationView.h:123-133. */
+int  vwb200_corr_rasterize(vwb200_corr* h, int x0, int y0, int x1, int y1,
+                           float* dest, ptrdiff_t dest_pitch, int dest_on_device, void* stream);
+/* levels prerasterize() would use for a bbox of this size (CorrelationView.cc:301-310) */
+int  vwb200_corr_num_levels(const vwb200_corr* h, int bw, int bh);
+void vwb200_corr_destroy(vwb200_corr* h);
+
+/* total number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+long long vwb200_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VWB200_H */

@@ -1,0 +1,97 @@
+"""CPU-side checks of the product boundary (no compute without a GPU):
+  * libvwb200.so loads and exports every symbol include/vwb200.h declares
+  * argument validation mirrors the reference's asserts
+  * with no CUDA device every compute call fails loudly (no CPU fallback exists)
+  * the product package never imports the oracle
+"""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def vwb():
+    sys.path.insert(0, ROOT)
+    from visionworkbench_b200 import build
+    build.build()
+    import visionworkbench_b200 as v
+    return v
+
+
+def test_every_declared_symbol_is_exported(vwb):
+    hdr = open(os.path.join(ROOT, "include", "vwb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(vwb200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 19
+    so = os.path.join(ROOT, "visionworkbench_b200", "libvwb200.so")
+    out = subprocess.check_output(["nm", "-D", "--defined-only", so], text=True)
+    exported = set(re.findall(r" T (vwb200_[a-z0-9_]+)", out))
+    missing = names - exported
+    assert not missing, f"declared but not exported: {sorted(missing)}"
+    L = vwb.lib()
+    for n in names:
+        assert getattr(L, n) is not None
+
+
+def test_sass_is_sm100a(vwb):
+    so = os.path.join(ROOT, "visionworkbench_b200", "libvwb200.so")
+    out = subprocess.run(["cuobjdump", "--list-elf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_argument_validation(vwb):
+    l = np.zeros((11, 11), np.float32)
+    r = np.zeros((14, 14), np.float32)
+    with pytest.raises(vwb.ArgumentErr):       # even kernel (Correlation.cc:340-341)
+        vwb.calc_disparity(0, l, r, (4, 4), (4, 5))
+    with pytest.raises(vwb.ArgumentErr):       # zero search volume (:345-346)
+        vwb.calc_disparity(0, l, r, (0, 4), (5, 5))
+    with pytest.raises(vwb.ArgumentErr):       # right raster too small
+        vwb.calc_disparity(0, l, r, (9, 9), (5, 5))
+    with pytest.raises(vwb.ArgumentErr):       # kernel larger than the region (:342-344)
+        vwb.calc_disparity(0, l, r, (2, 2), (13, 13))
+    m = np.full((11, 11), 255, np.uint8)
+    with pytest.raises(vwb.ArgumentErr):       # even kernel in the view
+        vwb.PyramidCorrelationView(l, l, m, m, 0, 0, (0, 0, 4, 4), (4, 4), 0, 0, 0.0, -1, 0, 0, 0)
+    with pytest.raises(vwb.NoImplErr):         # SGM is not this engine's algorithm
+        vwb.PyramidCorrelationView(l, l, m, m, 0, 0, (0, 0, 4, 4), (5, 5), 0, 0, 0.0, -1, 0, 0, 0, algorithm=1)
+
+
+def test_no_device_means_loud_failure(vwb):
+    if vwb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    l = np.zeros((11, 11), np.float32)
+    r = np.zeros((14, 14), np.float32)
+    with pytest.raises(vwb.NoDeviceErr):
+        vwb.calc_disparity(0, l, r, (4, 4), (5, 5))
+    with pytest.raises(vwb.NoDeviceErr):
+        vwb.pyramid_down(l)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "visionworkbench_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "vw_oracle" not in txt and "vwo_" not in txt, f
+    for f in os.listdir(os.path.join(ROOT, "include")):
+        p = os.path.join(ROOT, "include", f)
+        if os.path.isfile(p):
+            assert "vwo_" not in open(p).read()
+
+
+def test_view_is_lazy_and_operator_call_throws(vwb):
+    if vwb.device_count() > 0:
+        pytest.skip("needs the no-device behaviour")
+    l = np.zeros((32, 32), np.float32)
+    m = np.full((32, 32), 255, np.uint8)
+    # construction places inputs in HBM -> fails loudly without a device
+    with pytest.raises(vwb.NoDeviceErr):
+        vwb.PyramidCorrelationView(l, l, m, m, 0, 0, (0, 0, 4, 4), (5, 5), 0, 0, 0.0, -1, 0, 0, 0)

@@ -1,0 +1,224 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Bit-exact for integer disparities / validity / pyramid floats (float ops are issued in the
+reference's order with no FMA contraction)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vwb():
+    import visionworkbench_b200 as v
+    assert v.device_count() > 0, "GPU tests need a CUDA device"
+    return v
+
+
+def _assert_disp_equal(got, ref, what=""):
+    got = np.asarray(got)
+    ref = np.asarray(ref)
+    assert got.shape == ref.shape, what
+    gv, rv = got[..., 2] != 0, ref[..., 2] != 0
+    nbad_valid = int((gv != rv).sum())
+    both = gv & rv
+    nbad_d = int(((got[..., 0] != ref[..., 0]) | (got[..., 1] != ref[..., 1]))[both].sum())
+    assert nbad_valid == 0 and nbad_d == 0, f"{what}: {nbad_valid} validity mismatches, {nbad_d} disparity mismatches of {gv.size}"
+    # children of invalid pixels are observable through PixelMask::child(): keep them equal too
+    assert np.array_equal(got[..., :2], ref[..., :2]), f"{what}: children of invalid pixels differ"
+
+
+def _known_shift(rng, scale):
+    left = np.floor(rng.random((25, 25)) * scale).astype(np.float32) if scale > 1 else rng.random((25, 25)).astype(np.float32)
+    ys = np.clip(np.arange(46) - 8, 0, 24)
+    xs = np.clip(np.arange(31) - 3, 0, 24)
+    return left, left[np.ix_(ys, xs)]
+
+
+@pytest.mark.parametrize("cost", [0, 1, 2])
+@pytest.mark.parametrize("scale", [255.0, 32767.0, 1.0])
+def test_calc_disparity_reference_kat(vwb, oracle, cost, scale):
+    """Stereo/tests/TestCorrelation.cxx:45-65: shift (3,8), kernel 7x5, search 7x12."""
+    left, right = _known_shift(np.random.default_rng(10), scale)
+    d = vwb.calc_disparity(cost, left, right, (7, 12), (7, 5))
+    assert d.shape == (21, 19, 3)
+    assert (d[..., 2] == 1).all() and (d[..., 0] == 3).all() and (d[..., 1] == 8).all()
+    _assert_disp_equal(d, oracle.calc_disparity(cost, left, right, (7, 12), (7, 5)))
+
+
+@pytest.mark.parametrize("cost", [0, 1, 2])
+@pytest.mark.parametrize("shape", [((96, 70), (9, 7), (7, 7)), ((200, 130), (33, 33), (15, 15)), ((64, 64), (1, 1), (5, 5)),
+                                   ((37, 41), (5, 1), (3, 9)), ((130, 90), (16, 20), (21, 21))])
+def test_calc_disparity_matches_oracle(vwb, oracle, cost, shape):
+    from visionworkbench_b200.synth import make_rasters
+    (W, H), search, kernel = shape
+    left, right = make_rasters(W, H, search, kernel, seed=101 + cost)
+    got = vwb.calc_disparity(cost, left, right, search, kernel)
+    ref = oracle.calc_disparity(cost, left, right, search, kernel)
+    _assert_disp_equal(got, ref, f"cost {cost} {shape}")
+
+
+@pytest.mark.parametrize("cost", [0, 1, 2])
+def test_calc_disparity_general_float_inputs(vwb, oracle, cost):
+    """Non-integer imagery (what pyramid levels look like): fp64 path; values are multiples of 2^-8."""
+    rng = np.random.default_rng(5)
+    W, H, search, kernel = 80, 60, (9, 9), (9, 9)
+    right = (np.floor(rng.random((H + 16, W + 16)) * 4096 * 256) / 256).astype(np.float32)
+    left = np.ascontiguousarray(right[3:3 + H + 8, 5:5 + W + 8]) + (np.floor(rng.random((H + 8, W + 8)) * 512) / 256).astype(np.float32)
+    got = vwb.calc_disparity(cost, left, right, search, kernel)
+    ref = oracle.calc_disparity(cost, left, right, search, kernel)
+    _assert_disp_equal(got, ref)
+
+
+def test_calc_disparity_constant_image_is_invalid(vwb, oracle):
+    """Correlation.cc:121-133: every disparity gives the same cost -> invalid."""
+    left = np.full((30, 30), 7.0, np.float32)
+    right = np.full((34, 34), 7.0, np.float32)
+    for cost in (0, 1, 2):
+        got = vwb.calc_disparity(cost, left, right, (5, 5), (5, 5))
+        ref = oracle.calc_disparity(cost, left, right, (5, 5), (5, 5))
+        _assert_disp_equal(got, ref)
+    assert not vwb.calc_disparity(0, left, right, (5, 5), (5, 5))[..., 2].any()
+
+
+def test_calc_disparity_ncc_zero_windows(vwb, oracle):
+    """NCC with zero-energy windows: 1/0 = inf, inf*0 = NaN; the reference's best/worst state machine is
+    order dependent (Correlation.cc:97-117).  The GPU replays it for flagged pixels."""
+    rng = np.random.default_rng(3)
+    right = np.floor(rng.random((50, 50)) * 255).astype(np.float32)
+    right[:, :18] = 0
+    right[20:40, 25:45] = 0
+    left = np.ascontiguousarray(right[2:2 + 40, 3:3 + 40])
+    left[5:25, 5:30] = 0
+    got = vwb.calc_disparity(2, left, right, (8, 8), (7, 7))
+    ref = oracle.calc_disparity(2, left, right, (8, 8), (7, 7))
+    _assert_disp_equal(got, ref)
+
+
+def test_pyramid_down_bit_exact(vwb, oracle):
+    rng = np.random.default_rng(11)
+    for shape in [(64, 64), (65, 97), (3, 5), (1, 1), (2, 7), (300, 211)]:
+        img = (rng.random(shape) * 4096).astype(np.float32)     # arbitrary floats: rounding on every op
+        a = vwb.pyramid_down(img)
+        b = oracle.pyramid_down(img)
+        assert a.shape == b.shape
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), shape
+    # three levels deep
+    img = np.floor(rng.random((257, 301)) * 4096).astype(np.float32)
+    a, b = img, img
+    for _ in range(3):
+        a, b = vwb.pyramid_down(a), oracle.pyramid_down(b)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_subsample_mask(vwb, oracle):
+    rng = np.random.default_rng(12)
+    for shape in [(64, 64), (65, 97), (1, 1), (2, 7)]:
+        m = (rng.random(shape) > 0.5).astype(np.uint8) * 255
+        assert np.array_equal(vwb.subsample_mask_by_two(m), oracle.subsample_mask_by_two(m))
+
+
+def _random_disp(rng, h, w, invalid_frac=0.2, spread=6):
+    d = np.zeros((h, w, 3), np.int32)
+    d[..., 0] = rng.integers(-spread, spread + 1, (h, w))
+    d[..., 1] = rng.integers(-spread, spread + 1, (h, w))
+    d[..., 2] = rng.random((h, w)) > invalid_frac
+    return d
+
+
+def test_consistency_check(vwb, oracle):
+    rng = np.random.default_rng(13)
+    l2r = _random_disp(rng, 40, 50)
+    r2l = _random_disp(rng, 46, 58)
+    for thr in (0, 1, 2):
+        _assert_disp_equal(vwb.cross_corr_consistency_check(l2r, r2l, thr), oracle.cross_corr_consistency_check(l2r, r2l, thr))
+
+
+@pytest.mark.parametrize("r", [1, 2, 5])
+def test_outlier_filters(vwb, oracle, r):
+    rng = np.random.default_rng(14 + r)
+    for shape in [(40, 50), (7, 9), (100, 33)]:
+        d = _random_disp(rng, *shape, spread=4)
+        _assert_disp_equal(vwb.rm_outliers_using_thresh(d, r, r, 3.0, 0.5), oracle.rm_outliers_using_thresh(d, r, r, 3.0, 0.5), "rm_outliers")
+        _assert_disp_equal(vwb.disparity_cleanup_using_thresh(d, r, r, 3.0, 0.5), oracle.disparity_cleanup_using_thresh(d, r, r, 3.0, 0.5), "cleanup")
+
+
+def test_disparity_mask(vwb, oracle):
+    rng = np.random.default_rng(15)
+    d = _random_disp(rng, 40, 50, spread=8)
+    lm = (rng.random((40, 50)) > 0.1).astype(np.uint8) * 255
+    rm = (rng.random((45, 56)) > 0.1).astype(np.uint8) * 255
+    _assert_disp_equal(vwb.disparity_mask(d, lm, rm), oracle.disparity_mask(d, lm, rm))
+
+
+def _view_case(vwb, oracle, W, H, search, kernel, cost, levels, consistency, fhk, seed, bbox=None, collar=0, masks=True):
+    from visionworkbench_b200.synth import make_pair
+    left, right, lm, rm, _ = make_pair(W, H, search, seed, dropout=0.03 if masks else 0.0)
+    view = vwb.pyramid_correlate(left, right, lm, rm, vwb.PREFILTER_NONE, 0.0, search, kernel, cost, 0, 0.0,
+                                 consistency, 0, fhk, levels, collar_size=collar)
+    got = view.rasterize(None, bbox)
+    p = oracle.make_params(search, kernel, cost=cost, consistency_threshold=consistency, filter_half_kernel=fhk,
+                           max_pyramid_levels=levels, collar_size=collar)
+    ref = oracle.pyramid_correlate(p, left, right, lm, rm, bbox=bbox)
+    _assert_disp_equal(got, ref, f"view cost={cost} levels={levels} bbox={bbox}")
+    return got
+
+
+@pytest.mark.parametrize("cost", [0, 1, 2])
+def test_view_single_level(vwb, oracle, cost):
+    """BASELINE config 1 shape at reduced size: pyramid_correlate(max_pyramid_levels=0)."""
+    _view_case(vwb, oracle, 160, 128, (-8, -8, 8, 8), (7, 7), cost, 0, -1.0, 0, seed=101)
+
+
+@pytest.mark.parametrize("cost", [0, 1, 2])
+def test_view_pyramid_full_pipeline(vwb, oracle, cost):
+    """5 levels requested, L/R check, outlier filters, masks: the whole prerasterize()."""
+    got = _view_case(vwb, oracle, 300, 260, (-20, -12, 24, 16), (7, 7), cost, 5, 2.0, 5, seed=103)
+    assert got[..., 2].mean() > 0.5
+
+
+def test_view_tile_bboxes_and_collar(vwb, oracle):
+    """Parity is defined per bbox (pyramid phase depends on the tile origin, CorrelationView.cc:89-93)."""
+    for bbox in [(0, 0, 128, 128), (128, 64, 300, 200), (37, 41, 165, 169), (-16, -16, 64, 64), (250, 200, 330, 290)]:
+        _view_case(vwb, oracle, 320, 280, (-10, -6, 14, 10), (9, 9), 0, 3, 2.0, 3, seed=104, bbox=bbox)
+    _view_case(vwb, oracle, 320, 280, (-10, -6, 14, 10), (9, 9), 1, 3, 2.0, 3, seed=105, bbox=(64, 64, 192, 192), collar=16)
+
+
+def test_view_fully_masked_tile_is_all_invalid(vwb, oracle):
+    from visionworkbench_b200.synth import make_pair
+    left, right, lm, rm, _ = make_pair(200, 200, (-4, -4, 4, 4), 7, dropout=0)
+    lm[:] = 0
+    view = vwb.pyramid_correlate(left, right, lm, rm, 0, 0.0, (-4, -4, 4, 4), (7, 7), 0, 0, 0.0, 2.0, 0, 3, 2)
+    got = view.rasterize(None, (0, 0, 100, 100))
+    assert (got == 0).all()                                     # CorrelationView.cc:321-331
+    with pytest.raises(vwb.NoImplErr):
+        view(0, 0)
+
+
+def test_view_is_reentrant(vwb, oracle):
+    """prerasterize is called concurrently from the tile thread pool (Image/ImageIO.h:228-235)."""
+    import threading
+    from visionworkbench_b200.synth import make_pair
+    search, kernel = (-6, -6, 6, 6), (7, 7)
+    left, right, lm, rm, _ = make_pair(256, 256, search, 9)
+    view = vwb.pyramid_correlate(left, right, lm, rm, 0, 0.0, search, kernel, 0, 0, 0.0, 2.0, 0, 3, 3)
+    boxes = [(x, y, x + 128, y + 128) for y in (0, 128) for x in (0, 128)]
+    res = {}
+
+    def work(b):
+        res[b] = view.rasterize(None, b)
+    ts = [threading.Thread(target=work, args=(b,)) for b in boxes]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    p = oracle.make_params(search, kernel, consistency_threshold=2.0, filter_half_kernel=3, max_pyramid_levels=3)
+    for b in boxes:
+        _assert_disp_equal(res[b], oracle.pyramid_correlate(p, left, right, lm, rm, bbox=b), f"threaded {b}")
+
+
+def test_device_tensor_path(vwb, oracle):
+    import torch
+    from visionworkbench_b200.synth import make_rasters
+    left, right = make_rasters(100, 80, (12, 10), (9, 9), seed=21)
+    dl, dr = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+    got = vwb.calc_disparity(0, dl, dr, (12, 10), (9, 9))
+    assert got.is_cuda
+    _assert_disp_equal(got.cpu().numpy(), oracle.calc_disparity(0, left, right, (12, 10), (9, 9)))

@@ -1,0 +1,357 @@
+"""Python host-side mirror of the reference operator interface, over the C ABI (include/vwb200.h).
+
+Names, argument order and error behaviour follow Vision Workbench:
+  * calc_disparity            -- src/vw/Stereo/Correlation.h:50-57
+  * PyramidCorrelationView    -- src/vw/Stereo/CorrelationView.h:35-193 (cols/rows/planes,
+                                 prerasterize(bbox), rasterize(dest, bbox), operator() throws NoImplErr)
+  * pyramid_correlate         -- src/vw/Stereo/CorrelationView.h:195-230
+  * cross_corr_consistency_check, rm_outliers_using_thresh, disparity_cleanup_using_thresh,
+    disparity_mask            -- src/vw/Stereo/Correlate.h:52-58, DisparityMap.h:318-442,97-253
+
+There is no CPU path: every call goes to libvwb200.so (hand-written sm_100a kernels) and raises if
+the library or a CUDA device is missing.  Inputs may be numpy arrays (staged through HBM by the
+library) or torch CUDA tensors (used in place, results returned as torch CUDA tensors).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libvwb200.so")
+_LIB = None
+
+# vw::stereo::CostFunctionType (Stereo/CostFunctions.h:143-149)
+ABSOLUTE_DIFFERENCE, SQUARED_DIFFERENCE, CROSS_CORRELATION = 0, 1, 2
+# vw::stereo::PrefilterModeType (Stereo/PrefilterEnum.h:24-28)
+PREFILTER_NONE, PREFILTER_LOG, PREFILTER_MEANSUB = 0, 1, 2
+VW_CORRELATION_BM = 0
+
+
+class VwError(RuntimeError):
+    """Base of the vw::Exception mirror (Core/Exception.h:201-253)."""
+
+
+class ArgumentErr(VwError):
+    pass
+
+
+class MathErr(VwError):
+    pass
+
+
+class LogicErr(VwError):
+    pass
+
+
+class NoImplErr(VwError):
+    pass
+
+
+class CudaErr(VwError):
+    pass
+
+
+class NoDeviceErr(VwError):
+    pass
+
+
+_ERR = {-1: ArgumentErr, -2: MathErr, -3: LogicErr, -4: NoImplErr, -5: CudaErr, -6: NoDeviceErr, -7: MemoryError}
+
+
+class CorrParams(C.Structure):
+    _fields_ = [("search_x0", C.c_int32), ("search_y0", C.c_int32), ("search_x1", C.c_int32), ("search_y1", C.c_int32),
+                ("kernel_x", C.c_int32), ("kernel_y", C.c_int32), ("cost_type", C.c_int32),
+                ("prefilter_mode", C.c_int32), ("prefilter_width", C.c_float),
+                ("consistency_threshold", C.c_float), ("min_consistency_level", C.c_int32),
+                ("filter_half_kernel", C.c_int32), ("max_pyramid_levels", C.c_int32), ("collar_size", C.c_int32),
+                ("corr_timeout", C.c_int32), ("seconds_per_op", C.c_double),
+                ("algorithm", C.c_int32), ("blob_filter_area", C.c_int32)]
+
+
+class K1Stats(C.Structure):
+    _fields_ = [("path", C.c_int32), ("launches", C.c_int32), ("flagged_pixels", C.c_int32), ("reserved", C.c_int32)]
+
+
+def lib():
+    """Load libvwb200.so.  Fails loudly if it has not been built (python -m visionworkbench_b200.build)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_SO):
+            raise ImportError(f"{_SO} is missing: build it with `python visionworkbench_b200/build.py` "
+                              "(the engine has no CPU or PyTorch fallback)")
+        L = C.CDLL(_SO)
+        L.vwb200_last_error.restype = C.c_char_p
+        L.vwb200_version.restype = C.c_char_p
+        L.vwb200_kernel_launches.restype = C.c_longlong
+        P, I, Z, F, D = C.c_void_p, C.c_int, C.c_ssize_t, C.c_float, C.c_double
+        L.vwb200_calc_disparity.argtypes = [I, P, I, I, Z, P, I, I, Z, I, I, I, I, P, Z, I, P]
+        L.vwb200_pyramid_down.argtypes = [P, I, I, Z, P, Z, I, P]
+        L.vwb200_subsample_mask_by_two.argtypes = [P, I, I, Z, P, Z, I, P]
+        L.vwb200_cross_corr_consistency_check.argtypes = [P, I, I, Z, P, I, I, Z, F, I, P]
+        L.vwb200_rm_outliers_using_thresh.argtypes = [P, I, I, I, I, D, D, P, I, P]
+        L.vwb200_disparity_cleanup_using_thresh.argtypes = [P, I, I, I, I, D, D, P, I, P]
+        L.vwb200_disparity_mask.argtypes = [P, I, I, P, P, I, I, P, I, P]
+        L.vwb200_corr_create.argtypes = [C.POINTER(CorrParams), C.POINTER(P)]
+        L.vwb200_corr_set_inputs.argtypes = [P, P, I, I, Z, P, I, I, Z, P, Z, P, Z, I]
+        L.vwb200_corr_rasterize.argtypes = [P, I, I, I, I, P, Z, I, P]
+        L.vwb200_corr_num_levels.argtypes = [P, I, I]
+        L.vwb200_corr_cols.argtypes = [P]
+        L.vwb200_corr_rows.argtypes = [P]
+        L.vwb200_corr_destroy.argtypes = [P]
+        L.vwb200_corr_destroy.restype = None
+        L.vwb200_last_k1_stats.argtypes = [C.POINTER(K1Stats)]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        msg = lib().vwb200_last_error().decode("utf-8", "replace")
+        raise _ERR.get(rc, VwError)(msg)
+
+
+def device_count():
+    return lib().vwb200_device_count()
+
+
+def kernel_launches():
+    return lib().vwb200_kernel_launches()
+
+
+def last_k1_stats():
+    s = K1Stats()
+    lib().vwb200_last_k1_stats(C.byref(s))
+    return {"path": "exact-int" if s.path == 0 else "general-fp64", "launches": s.launches}
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def calc_disparity(cost_type, left_in, right_in, search_volume, kernel_size):
+    """vw::stereo::calc_disparity (Stereo/Correlation.h:50-57) on already-cropped rasters.
+
+    left_in : (H+ky-1, W+kx-1) float32;  right_in: at least (H+ky-1+sy-1, W+kx-1+sx-1).
+    search_volume = (sx, sy), kernel_size = (kx, ky).
+    Returns int32 (H, W, 3) {dx, dy, valid} -- PixelMask<Vector2i>.
+    """
+    sx, sy = search_volume
+    kx, ky = kernel_size
+    if _is_torch(left_in):
+        import torch
+        l = left_in.contiguous().float()
+        r = right_in.contiguous().float()
+        H, W = l.shape[0] - ky + 1, l.shape[1] - kx + 1
+        if H <= 0 or W <= 0:
+            raise ArgumentErr("calc_disparity: Kernel size too large of active region.")
+        out = torch.empty((H, W, 3), dtype=torch.int32, device=l.device)
+        _check(lib().vwb200_calc_disparity(cost_type, l.data_ptr(), l.shape[1], l.shape[0], l.stride(0),
+                                           r.data_ptr(), r.shape[1], r.shape[0], r.stride(0),
+                                           sx, sy, kx, ky, out.data_ptr(), W, 1, _stream_ptr()))
+        return out
+    l, r = _np(left_in, np.float32), _np(right_in, np.float32)
+    H, W = l.shape[0] - ky + 1, l.shape[1] - kx + 1
+    if H <= 0 or W <= 0:
+        raise ArgumentErr("calc_disparity: Kernel size too large of active region.")
+    out = np.empty((H, W, 3), np.int32)
+    _check(lib().vwb200_calc_disparity(cost_type, l.ctypes.data, l.shape[1], l.shape[0], l.shape[1],
+                                       r.ctypes.data, r.shape[1], r.shape[0], r.shape[1],
+                                       sx, sy, kx, ky, out.ctypes.data, W, 0, None))
+    return out
+
+
+def pyramid_down(img):
+    """subsample(separable_convolution_filter(img, k, k), 2) with k = [1,4,6,4,1]/16
+    (Stereo/CorrelationView.cc:210-214)."""
+    a = _np(img, np.float32)
+    h, w = a.shape
+    out = np.empty((1 + (h - 1) // 2, 1 + (w - 1) // 2), np.float32)
+    _check(lib().vwb200_pyramid_down(a.ctypes.data, w, h, w, out.ctypes.data, out.shape[1], 0, None))
+    return out
+
+
+def subsample_mask_by_two(mask):
+    a = _np(mask, np.uint8)
+    h, w = a.shape
+    out = np.empty((1 + (h - 1) // 2, 1 + (w - 1) // 2), np.uint8)
+    _check(lib().vwb200_subsample_mask_by_two(a.ctypes.data, w, h, w, out.ctypes.data, out.shape[1], 0, None))
+    return out
+
+
+def cross_corr_consistency_check(l2r, r2l, cross_corr_threshold):
+    """Stereo/Correlate.h:52-58; returns the checked copy of l2r."""
+    a = _np(l2r, np.int32).copy()
+    b = _np(r2l, np.int32)
+    _check(lib().vwb200_cross_corr_consistency_check(a.ctypes.data, a.shape[1], a.shape[0], a.shape[1],
+                                                     b.ctypes.data, b.shape[1], b.shape[0], b.shape[1],
+                                                     float(cross_corr_threshold), 0, None))
+    return a
+
+
+def rm_outliers_using_thresh(disparity_map, half_h_kernel, half_v_kernel, pixel_threshold, rejection_threshold):
+    a = _np(disparity_map, np.int32)
+    out = np.empty_like(a)
+    _check(lib().vwb200_rm_outliers_using_thresh(a.ctypes.data, a.shape[1], a.shape[0], half_h_kernel, half_v_kernel,
+                                                 pixel_threshold, rejection_threshold, out.ctypes.data, 0, None))
+    return out
+
+
+def disparity_cleanup_using_thresh(disparity_map, h_half_kernel, v_half_kernel, pixel_threshold, rejection_threshold):
+    a = _np(disparity_map, np.int32)
+    out = np.empty_like(a)
+    _check(lib().vwb200_disparity_cleanup_using_thresh(a.ctypes.data, a.shape[1], a.shape[0], h_half_kernel, v_half_kernel,
+                                                       pixel_threshold, rejection_threshold, out.ctypes.data, 0, None))
+    return out
+
+
+def disparity_mask(disparity_map, left_mask, right_mask):
+    a = _np(disparity_map, np.int32)
+    lm, rm = _np(left_mask, np.uint8), _np(right_mask, np.uint8)
+    if lm.shape != a.shape[:2]:
+        raise ArgumentErr("disparity_mask: input and left mask are not same dimensions.")
+    out = np.empty_like(a)
+    _check(lib().vwb200_disparity_mask(a.ctypes.data, a.shape[1], a.shape[0], lm.ctypes.data, rm.ctypes.data,
+                                       rm.shape[1], rm.shape[0], out.ctypes.data, 0, None))
+    return out
+
+
+class BBox2i:
+    """vw::BBox2i: half-open [min, max).  BBox2i(x, y, w, h) like Math/BBox.tcc:55-59."""
+
+    def __init__(self, x=0, y=0, w=0, h=0):
+        self.x0, self.y0, self.x1, self.y1 = x, y, x + w, y + h
+
+    @classmethod
+    def from_corners(cls, x0, y0, x1, y1):
+        return cls(x0, y0, x1 - x0, y1 - y0)
+
+    def width(self):
+        return max(self.x1 - self.x0, 0)
+
+    def height(self):
+        return max(self.y1 - self.y0, 0)
+
+    def __repr__(self):
+        return f"BBox2i(({self.x0},{self.y0})-({self.x1},{self.y1}))"
+
+
+class PyramidCorrelationView:
+    """vw::stereo::PyramidCorrelationView (Stereo/CorrelationView.h:35-193) rasterised on a B200.
+
+    Lazy like the reference: construction only records parameters and places the inputs in HBM;
+    work happens in rasterize()/prerasterize(), one call per tile bbox, from any number of threads.
+    """
+
+    def __init__(self, left, right, left_mask, right_mask, prefilter_mode, prefilter_width,
+                 search_region, kernel_size, cost_type, corr_timeout, seconds_per_op,
+                 consistency_threshold, min_consistency_level, filter_half_kernel, max_pyramid_levels,
+                 algorithm=VW_CORRELATION_BM, collar_size=0, sgm_subpixel_mode=None, sgm_search_buffer=(2, 2),
+                 memory_limit_mb=6000, blob_filter_area=0, lr_disp_diff=None, region_ul=(0, 0),
+                 write_debug_images=False):
+        if isinstance(search_region, BBox2i):
+            s = (search_region.x0, search_region.y0, search_region.x1, search_region.y1)
+        else:
+            s = tuple(int(v) for v in search_region)
+        if lr_disp_diff is not None:
+            raise NoImplErr("lr_disp_diff output is not implemented by the vwb200 engine")
+        self._p = CorrParams(s[0], s[1], s[2], s[3], int(kernel_size[0]), int(kernel_size[1]), int(cost_type),
+                             int(prefilter_mode), float(prefilter_width), float(consistency_threshold),
+                             int(min_consistency_level), int(filter_half_kernel), int(max_pyramid_levels),
+                             int(collar_size), int(corr_timeout), float(seconds_per_op), int(algorithm),
+                             int(blob_filter_area))
+        self._h = C.c_void_p()
+        _check(lib().vwb200_corr_create(C.byref(self._p), C.byref(self._h)))
+        self._keep = None
+        self._device = _is_torch(left)
+        if self._device:
+            l, r = left.contiguous().float(), right.contiguous().float()
+            lm, rm = left_mask.contiguous(), right_mask.contiguous()
+            self._keep = (l, r, lm, rm)
+            _check(lib().vwb200_corr_set_inputs(self._h, l.data_ptr(), l.shape[1], l.shape[0], l.stride(0),
+                                                r.data_ptr(), r.shape[1], r.shape[0], r.stride(0),
+                                                lm.data_ptr(), lm.stride(0), rm.data_ptr(), rm.stride(0), 1))
+        else:
+            l, r = _np(left, np.float32), _np(right, np.float32)
+            lm, rm = _np(left_mask, np.uint8), _np(right_mask, np.uint8)
+            if lm.shape != l.shape or rm.shape != r.shape:
+                raise ArgumentErr("masks must have the size of their images")
+            _check(lib().vwb200_corr_set_inputs(self._h, l.ctypes.data, l.shape[1], l.shape[0], l.shape[1],
+                                                r.ctypes.data, r.shape[1], r.shape[0], r.shape[1],
+                                                lm.ctypes.data, lm.shape[1], rm.ctypes.data, rm.shape[1], 0))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().vwb200_corr_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # --- standard ImageView interface (CorrelationView.h:109-117) ---
+    def cols(self):
+        return lib().vwb200_corr_cols(self._h)
+
+    def rows(self):
+        return lib().vwb200_corr_rows(self._h)
+
+    def planes(self):
+        return 1
+
+    def __call__(self, i, j, p=0):
+        raise NoImplErr("NewCorrelationView::operator() is not implemented.")
+
+    def num_levels(self, bbox):
+        b = _bbox(bbox)
+        return lib().vwb200_corr_num_levels(self._h, b[2] - b[0], b[3] - b[1])
+
+    def rasterize(self, dest=None, bbox=None):
+        """rasterize(dest, bbox) (CorrelationView.h:123-133).  dest: float32 (h, w, 3) numpy array (or torch
+        CUDA tensor) already sized to bbox, or None to allocate.  Pixels are {dx, dy, valid}."""
+        b = _bbox(bbox) if bbox is not None else (0, 0, self.cols(), self.rows())
+        w, h = b[2] - b[0], b[3] - b[1]
+        if dest is not None and _is_torch(dest) or (dest is None and self._device):
+            import torch
+            if dest is None:
+                dest = torch.empty((h, w, 3), dtype=torch.float32, device=self._keep[0].device)
+            assert dest.shape == (h, w, 3) and dest.dtype == torch.float32 and dest.stride(2) == 1 and dest.stride(1) == 3
+            _check(lib().vwb200_corr_rasterize(self._h, b[0], b[1], b[2], b[3], dest.data_ptr(), dest.stride(0) // 3, 1, _stream_ptr()))
+            return dest
+        if dest is None:
+            dest = np.empty((h, w, 3), np.float32)
+        assert dest.shape == (h, w, 3) and dest.dtype == np.float32 and dest.strides[2] == 4 and dest.strides[1] == 12
+        _check(lib().vwb200_corr_rasterize(self._h, b[0], b[1], b[2], b[3], dest.ctypes.data, dest.strides[0] // 12, 0, None))
+        return dest
+
+    def prerasterize(self, bbox):
+        """prerasterize(bbox): an owning buffer of bbox size (CorrelationView.cc:880-884); unlike rasterize()
+        no collar is added."""
+        saved = self._p.collar_size
+        if saved:
+            raise NoImplErr("prerasterize without collar on a collared view: call rasterize()")
+        return self.rasterize(None, bbox)
+
+
+def _bbox(b):
+    if isinstance(b, BBox2i):
+        return (b.x0, b.y0, b.x1, b.y1)
+    return tuple(int(v) for v in b)
+
+
+def pyramid_correlate(left, right, left_mask, right_mask, prefilter_mode, prefilter_width, search_region, kernel_size,
+                      cost_type, corr_timeout, seconds_per_op, consistency_threshold, min_consistency_level,
+                      filter_half_kernel, max_pyramid_levels, algorithm=VW_CORRELATION_BM, collar_size=0, **kw):
+    """vw::stereo::pyramid_correlate (Stereo/CorrelationView.h:195-230)."""
+    return PyramidCorrelationView(left, right, left_mask, right_mask, prefilter_mode, prefilter_width, search_region,
+                                  kernel_size, cost_type, corr_timeout, seconds_per_op, consistency_threshold,
+                                  min_consistency_level, filter_half_kernel, max_pyramid_levels, algorithm,
+                                  collar_size, **kw)

@@ -1,0 +1,112 @@
+// common.cuh -- shared declarations for the vwb200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <atomic>
+#include <vector>
+#include "../../include/vwb200.h"
+
+namespace vwb200 {
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define VWB_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::vwb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return VWB200_ECUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define VWB_TRY(expr)                        \
+  do {                                       \
+    int _rc = (expr);                        \
+    if (_rc != VWB200_OK) return _rc;        \
+  } while (0)
+
+#define VWB_LAUNCH_CHECK()                                                                  \
+  do {                                                                                      \
+    ::vwb200::g_launches.fetch_add(1, std::memory_order_relaxed);                           \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      ::vwb200::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return VWB200_ECUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+int ensure_device();   // VWB200_ENODEVICE when there is no CUDA device
+
+// ---- image descriptors (device pointers) ------------------------------------------------------
+struct ImgF { const float* p; int w, h; ptrdiff_t pitch; };
+struct ImgB { const uint8_t* p; int w, h; ptrdiff_t pitch; };
+
+// A zone of the level loop (Stereo/CorrelationView.cc:607-648) or a whole calc_disparity call.
+struct Zone {
+  long long obase;   // element offset of the zone's output (0,0) in the output buffer
+  int opitch;        // output row pitch (elements)
+  int w, h;          // output size
+  int lx, ly;        // left_region.min  (kernel-padded) in left image coordinates
+  int rx, ry;        // right_region.min in right image coordinates
+  int sx, sy;        // search volume
+  int addx, addy;    // constant added to the children by the K1 epilogue (R->L pass: -search size)
+};
+// One unit of work of the generic kernel: a TW x TH tile of a zone.
+struct Tile { int zone; int tx, ty; int pad; };
+
+// ---- K1 generic (fp64, any float input, zones) --------------------------------------------
+// cost: VWB200_* cost type.  inv_l / inv_r: for NCC, 1/boxsum(v^2) maps whose (0,0) sits at window
+// origin (l_ox,l_oy) / (r_ox,r_oy) in image coordinates, pitch in elements.
+struct NccMaps { const double* inv_l; int l_ox, l_oy, l_w, l_h; const double* inv_r; int r_ox, r_oy, r_w, r_h; };
+int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
+                      int kx, int ky, NccMaps ncc, vwb200_dispi* out, cudaStream_t st);
+int k1_generic_tile_w(int kx);
+int k1_generic_tile_h(int ky);
+// 1/boxsum(v*v) over window origins [ox0,ox0+ow) x [oy0,oy0+oh) with clamped (constant edge) reads.
+int box_sq_inv_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* out, cudaStream_t st);
+// exact sequential re-evaluation of pixels flagged NaN by k1 (NCC zero-energy windows)
+int k1_nan_fixup_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, int nzones, int kx, int ky,
+                        NccMaps ncc, vwb200_dispi* out, cudaStream_t st);
+
+// ---- K1 fast (exact-integer path, single big zone) -------------------------------------------
+// Returns VWB200_ENOIMPL if the configuration is outside what the fast path handles.
+int k1_fast_supported(int cost, int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued);
+int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky,
+                   vwb200_dispi* out, ptrdiff_t opitch, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t k1_fast_workspace_bytes(int W, int H, int sx, int sy, int kx, int ky);
+// min / max / integer-valuedness of an image (device reduction); result[0]=min,[1]=max,[2]=all-integers(1/0)
+int image_stats_launch(ImgF img, float* d_result3, cudaStream_t st);
+
+// ---- K2 pyramid ---------------------------------------------------------------------------------
+int crop_extend_f32_launch(ImgF src, int x0, int y0, int w, int h, float* dst, ptrdiff_t dpitch, cudaStream_t st);
+int crop_extend_u8_launch(ImgB src, int x0, int y0, int w, int h, int zero_outside, uint8_t* dst, ptrdiff_t dpitch, cudaStream_t st);
+// masked mean over every 2nd pixel (CorrelationView.cc:133-136): d_acc = {double sum, double count}
+int masked_mean_launch(ImgF img, ImgB mask, double* d_acc2, cudaStream_t st);
+int mean_fill_launch(float* img, int w, int h, ptrdiff_t pitch, ImgB mask, const double* d_acc2, cudaStream_t st);
+int pyramid_down_launch(ImgF in, float* out, ptrdiff_t opitch, cudaStream_t st);
+int subsample_mask_launch(ImgB in, uint8_t* out, ptrdiff_t opitch, cudaStream_t st);
+
+// ---- K3 / K4 -------------------------------------------------------------------------------------
+int consistency_launch(vwb200_dispi* l2r, int lw, int lh, ptrdiff_t lpitch, const vwb200_dispi* r2l, int rw, int rh,
+                       ptrdiff_t rpitch, float thr, cudaStream_t st);
+// pass 1 of the outlier filter evaluated over [x0,x0+ow) x [y0,y0+oh) of the constant-edge-extended input
+int rm_outliers_launch(const vwb200_dispi* in, int w, int h, int hx, int hy, double pt, double rt,
+                       int x0, int y0, int ow, int oh, vwb200_dispi* out, cudaStream_t st);
+// pass 2 (1,1,3.0,0.20) reading the padded pass-1 buffer (w+2)x(h+2)
+int cleanup_pass2_launch(const vwb200_dispi* p1, int w, int h, vwb200_dispi* out, cudaStream_t st);
+int disparity_mask_launch(const vwb200_dispi* in, int w, int h, ImgB lmask, ImgB rmask, vwb200_dispi* out, cudaStream_t st);
+// out[i] = {dx+ax, dy+ay, valid} as float triples (CorrelationView.cc:880-884)
+int finalize_launch(const vwb200_dispi* in, int w, int h, int ax, int ay, float* out, ptrdiff_t opitch_px,
+                    int ox, int oy, int ow, int oh, cudaStream_t st);
+
+// ---- host-side restatement-free logic -----------------------------------------------------------
+struct Box { int x0, y0, x1, y1; };
+struct HostZone { Box img; Box disp; };
+// quad-tree search-range refinement (behaviour of Stereo/Correlation.cc:139-328), host side.
+void subdivide_regions_host(const vwb200_dispi* disp, int w, int h, int kx, int ky, std::vector<HostZone>& out);
+
+}  // namespace vwb200

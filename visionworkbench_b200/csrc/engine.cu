@@ -1,0 +1,685 @@
+// engine.cu -- host side of the vwb200 engine: error plumbing, the extern "C" ABI of
+// include/vwb200.h, and the per-tile level loop of PyramidCorrelationView::prerasterize
+// (behaviour of Stereo/CorrelationView.cc:273-886, block-matching branch) driving the CUDA kernels.
+//
+// Everything here is re-entrant: no mutable globals except the launch counter; each rasterize call
+// owns a stream and stream-ordered allocations (VW calls prerasterize concurrently from its tile
+// thread pool, Image/ImageIO.h:228-235).
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+namespace vwb200 {
+
+std::atomic<long long> g_launches{0};
+static thread_local char t_error[512] = "";
+static thread_local vwb200_k1_stats t_k1_stats = {0, 0, 0, 0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_error, sizeof(t_error), fmt, ap);
+  va_end(ap);
+}
+
+int ensure_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no CUDA device available (%s); the vwb200 engine has no CPU path",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return VWB200_ENODEVICE;
+  }
+  return VWB200_OK;
+}
+
+int zone_post_launch(const Tile* d_tiles, int ntiles, const Zone* d_zones, const Zone* d_rlzones, const int2* d_post_add,
+                     vwb200_dispi* disp, const vwb200_dispi* rl, float thr, int tile, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------
+// small RAII helpers: stream-ordered device buffers, an owned-or-borrowed stream
+// ---------------------------------------------------------------------------------------------------
+struct Arena {
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  explicit Arena(cudaStream_t s) : st(s) {}
+  ~Arena() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+  template <class T> int alloc(T** out, size_t n) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st);
+    if (e != cudaSuccess) { set_error("cudaMallocAsync(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return VWB200_ENOMEM; }
+    ptrs.push_back(p);
+    *out = static_cast<T*>(p);
+    return VWB200_OK;
+  }
+};
+struct StreamGuard {
+  cudaStream_t st = nullptr; bool own = false;
+  int init(void* user) {
+    if (user) { st = static_cast<cudaStream_t>(user); return VWB200_OK; }
+    VWB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    own = true;
+    return VWB200_OK;
+  }
+  ~StreamGuard() { if (own && st) cudaStreamDestroy(st); }
+};
+
+static void make_tiles(const std::vector<Zone>& zones, int tile, std::vector<Tile>& tiles) {
+  tiles.clear();
+  for (size_t zi = 0; zi < zones.size(); ++zi)
+    for (int ty = 0; ty < zones[zi].h; ty += tile)
+      for (int tx = 0; tx < zones[zi].w; tx += tile) tiles.push_back(Tile{(int)zi, tx, ty, 0});
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1 dispatch for one batch of zones (generic path).  NCC maps are built over the bounding domain of
+// the window origins the zones touch.
+// ---------------------------------------------------------------------------------------------------
+static int run_k1_zones(int cost, ImgF left, ImgF right, const std::vector<Zone>& zones, int kx, int ky,
+                        vwb200_dispi* d_out, Arena& ar, cudaStream_t st, const Zone** d_zones_out = nullptr,
+                        const Tile** d_tiles_out = nullptr, int* ntiles_out = nullptr) {
+  if (zones.empty()) { if (ntiles_out) *ntiles_out = 0; return VWB200_OK; }
+  std::vector<Tile> tiles;
+  make_tiles(zones, k1_generic_tile_w(kx), tiles);
+  Zone* d_zones; Tile* d_tiles;
+  VWB_TRY(ar.alloc(&d_zones, zones.size()));
+  VWB_TRY(ar.alloc(&d_tiles, tiles.size()));
+  VWB_CUDA(cudaMemcpyAsync(d_zones, zones.data(), zones.size() * sizeof(Zone), cudaMemcpyHostToDevice, st));
+  VWB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+  NccMaps ncc = {};
+  if (cost == VWB200_CROSS_CORRELATION) {
+    int lx0 = INT_MAX, ly0 = INT_MAX, lx1 = INT_MIN, ly1 = INT_MIN, rx0 = INT_MAX, ry0 = INT_MAX, rx1 = INT_MIN, ry1 = INT_MIN;
+    for (const Zone& z : zones) {
+      lx0 = std::min(lx0, z.lx); ly0 = std::min(ly0, z.ly); lx1 = std::max(lx1, z.lx + z.w); ly1 = std::max(ly1, z.ly + z.h);
+      rx0 = std::min(rx0, z.rx); ry0 = std::min(ry0, z.ry);
+      rx1 = std::max(rx1, z.rx + z.w + z.sx - 1); ry1 = std::max(ry1, z.ry + z.h + z.sy - 1);
+    }
+    double *il, *ir;
+    VWB_TRY(ar.alloc(&il, (size_t)(lx1 - lx0) * (ly1 - ly0)));
+    VWB_TRY(ar.alloc(&ir, (size_t)(rx1 - rx0) * (ry1 - ry0)));
+    VWB_TRY(box_sq_inv_launch(left, kx, ky, lx0, ly0, lx1 - lx0, ly1 - ly0, il, st));
+    VWB_TRY(box_sq_inv_launch(right, kx, ky, rx0, ry0, rx1 - rx0, ry1 - ry0, ir, st));
+    ncc = NccMaps{il, lx0, ly0, lx1 - lx0, ly1 - ly0, ir, rx0, ry0, rx1 - rx0, ry1 - ry0};
+  }
+  VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles, (int)tiles.size(), kx, ky, ncc, d_out, st));
+  if (cost == VWB200_CROSS_CORRELATION)
+    VWB_TRY(k1_nan_fixup_launch(cost, left, right, d_zones, (int)zones.size(), kx, ky, ncc, d_out, st));
+  if (d_zones_out) *d_zones_out = d_zones;
+  if (d_tiles_out) *d_tiles_out = d_tiles;
+  if (ntiles_out) *ntiles_out = (int)tiles.size();
+  return VWB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side quad-tree search-range refinement.  Behaviour of vw::stereo::subdivide_regions
+// (Stereo/Correlation.cc:139-328): see DESIGN.md "zones".  Box arithmetic follows vw::BBox2i
+// (Math/BBox.tcc): half-open, "empty" when min >= max in any axis.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct Range { bool any = false; int x0 = 0, y0 = 0, x1 = 0, y1 = 0; };   // [min, max+1) of valid disparities
+inline bool same_range(const Range& a, const Range& b) {
+  if (a.any != b.any) return false;
+  return !a.any || (a.x0 == b.x0 && a.y0 == b.y0 && a.x1 == b.x1 && a.y1 == b.y1);
+}
+inline int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+inline int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+
+struct Subdivider {
+  const vwb200_dispi* d; int w, h, kx, ky;
+  std::vector<HostZone>* out;
+
+  Range scan(Box b) const {
+    Range r;
+    for (int y = b.y0; y < b.y1; ++y) {
+      const vwb200_dispi* row = d + (size_t)y * w;
+      for (int x = b.x0; x < b.x1; ++x) {
+        if (!row[x].valid) continue;
+        const int vx = row[x].dx, vy = row[x].dy;
+        if (!r.any) { r.any = true; r.x0 = vx; r.x1 = vx + 1; r.y0 = vy; r.y1 = vy + 1; }
+        else { r.x0 = std::min(r.x0, vx); r.x1 = std::max(r.x1, vx + 1); r.y0 = std::min(r.y0, vy); r.y1 = std::max(r.y1, vy + 1); }
+      }
+    }
+    return r;
+  }
+  static Box to_box(const Range& r) {
+    if (!r.any) return Box{INT_MAX - 1, INT_MAX - 1, -(INT_MAX - 1), -(INT_MAX - 1)};   // default (empty) BBox2i
+    return Box{r.x0, r.y0, r.x1, r.y1};
+  }
+  void emit(Box img, const Range& r) const { out->push_back(HostZone{img, to_box(r)}); }
+  static int area(const Range& r) { return r.any ? (r.x1 - r.x0) * (r.y1 - r.y0) : 0; }
+  static Range merge(Range a, const Range& b) {
+    if (!b.any) return a;
+    if (!a.any) return b;
+    a.x0 = std::min(a.x0, b.x0); a.y0 = std::min(a.y0, b.y0); a.x1 = std::max(a.x1, b.x1); a.y1 = std::max(a.y1, b.y1);
+    return a;
+  }
+  static Box hull(Box a, Box b) { return Box{std::min(a.x0, b.x0), std::min(a.y0, b.y0), std::max(a.x1, b.x1), std::max(a.y1, b.y1)}; }
+
+  // returns false only for "second failure" (the caller then treats the quadrant as unsplittable)
+  bool run(Box cur, int fails) const {
+    const int cw = cur.x1 - cur.x0, ch = cur.y1 - cur.y0;
+    if (cw * ch <= 200 || cw < 16 || ch < 16) {
+      Box e{std::max(cur.x0 - 1, 0), std::max(cur.y0 - 1, 0), std::min(cur.x1 + 1, w), std::min(cur.y1 + 1, h)};
+      Range r = scan(e);
+      if (r.any) emit(cur, r);
+      return true;
+    }
+    const int mx = cur.x0 + cw / 2, my = cur.y0 + ch / 2;
+    const Box q[4] = {{cur.x0, cur.y0, mx, my}, {mx, cur.y0, cur.x1, my}, {cur.x0, my, mx, cur.y1}, {mx, my, cur.x1, cur.y1}};
+    Range rq[4], all;
+    int32_t split_cost = 0;
+    for (int i = 0; i < 4; ++i) {
+      rq[i] = scan(q[i]);
+      if (rq[i].any) split_cost = wadd(split_cost, wmul(area(rq[i]), wmul(q[i].x1 - q[i].x0 + kx, q[i].y1 - q[i].y0 + ky)));
+      all = merge(all, rq[i]);
+    }
+    const int32_t whole_cost = wmul(area(all), wmul(cw + kx, ch + ky));
+    const bool worthwhile = !((double)split_cost > (double)whole_cost * 0.8);
+    if (worthwhile) {
+      for (int i = 0; i < 4; ++i) run(q[i], 0);
+      return true;
+    }
+    if (fails > 0) return false;
+    // first failure: give every quadrant one more chance, then deal with the ones that refused
+    int bad[4], nbad = 0;
+    for (int i = 0; i < 4; ++i) if (!run(q[i], fails + 1)) bad[nbad++] = i;
+    auto adjacent_same = [&](int a, int b) {
+      return (q[a].x0 == q[b].x0 || q[a].y0 == q[b].y0) && same_range(rq[a], rq[b]);
+    };
+    if (nbad == 4) { emit(cur, all); return true; }
+    if (nbad == 3) {
+      const int pairs[3][3] = {{0, 1, 2}, {1, 2, 0}, {0, 2, 1}};      // (merge a, merge b, leftover)
+      for (const auto& p : pairs)
+        if (adjacent_same(bad[p[0]], bad[p[1]])) {
+          out->push_back(HostZone{hull(q[bad[p[0]]], q[bad[p[1]]]), to_box(rq[bad[p[0]]])});
+          emit(q[bad[p[2]]], rq[bad[p[2]]]);
+          return true;
+        }
+      for (int i = 0; i < 3; ++i) emit(q[bad[i]], rq[bad[i]]);
+    } else if (nbad == 2) {
+      if (adjacent_same(bad[0], bad[1])) out->push_back(HostZone{hull(q[bad[0]], q[bad[1]]), to_box(rq[bad[0]])});
+      else { emit(q[bad[0]], rq[bad[0]]); emit(q[bad[1]], rq[bad[1]]); }
+    } else if (nbad == 1) {
+      emit(q[bad[0]], rq[bad[0]]);
+    }
+    return true;
+  }
+};
+}  // namespace
+
+void subdivide_regions_host(const vwb200_dispi* disp, int w, int h, int kx, int ky, std::vector<HostZone>& out) {
+  Subdivider s{disp, w, h, kx, ky, &out};
+  s.run(Box{0, 0, w, h}, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the view handle
+// ---------------------------------------------------------------------------------------------------
+}  // namespace vwb200
+
+using namespace vwb200;
+
+struct vwb200_corr {
+  vwb200_corr_params p;
+  int max_level_by_search = 0;
+  // inputs in HBM
+  const float* L = nullptr; const float* R = nullptr; const uint8_t* Lm = nullptr; const uint8_t* Rm = nullptr;
+  int lcols = 0, lrows = 0, rcols = 0, rrows = 0;
+  ptrdiff_t lpitch = 0, rpitch = 0, lmpitch = 0, rmpitch = 0;
+  bool owned = false;
+  int device = 0;
+  ~vwb200_corr() { release(); }
+  void release() {
+    if (owned) { cudaFree((void*)L); cudaFree((void*)R); cudaFree((void*)Lm); cudaFree((void*)Rm); }
+    L = R = nullptr; Lm = Rm = nullptr; owned = false;
+  }
+  int num_levels(int bw, int bh) const {
+    // CorrelationView.cc:301-310: log(int) is double, log(2.0f) is float
+    const int smallest = std::min(bw, bh), largest_kernel = std::max(p.kernel_x, p.kernel_y);
+    int levels = (int)std::floor(std::log((double)smallest) / (double)std::log(2.0f) - std::log((double)largest_kernel) / (double)std::log(2.0f));
+    if (max_level_by_search < levels) levels = max_level_by_search;
+    if (levels < 1) levels = 0;
+    return levels;
+  }
+  int prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_invalid, Arena& ar, cudaStream_t st) const;
+};
+
+namespace {
+inline Box bexpand(Box b, int ex, int ey) { if (b.x0 >= b.x1 || b.y0 >= b.y1) return b; return Box{b.x0 - ex, b.y0 - ey, b.x1 + ex, b.y1 + ey}; }
+inline bool bempty(Box b) { return b.x0 >= b.x1 || b.y0 >= b.y1; }
+struct LevelImgs { float* l; float* r; uint8_t* lm; uint8_t* rm; int lw, lh, rw, rh, lmw, lmh, rmw, rmh; };
+}
+
+// The per-tile pipeline.  Result: integer disparity (bw x bh, dense) in device memory, WITHOUT the
+// final "+ search_region.min()" (finalize_kernel adds it while casting to float).
+int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_invalid, Arena& ar, cudaStream_t st) const {
+  const int bw = bbox.x1 - bbox.x0, bh = bbox.y1 - bbox.y0;
+  const int kx = p.kernel_x, ky = p.kernel_y, hkx = kx / 2, hky = ky / 2;
+  const int ssx = p.search_x1 - p.search_x0, ssy = p.search_y1 - p.search_y0;
+  const int levels = num_levels(bw, bh);
+  const int up = 1 << levels;
+  *all_invalid = 0;
+  if (p.prefilter_mode != VWB200_PREFILTER_NONE) { set_error("prefilter mode %d not implemented yet", p.prefilter_mode); return VWB200_ENOIMPL; }
+
+  // ---- build_image_pyramids (CorrelationView.cc:67-239) ----
+  const Box lg = bexpand(bbox, hkx * up, hky * up);
+  Box rg{lg.x0 + p.search_x0, lg.y0 + p.search_y0, lg.x1 + p.search_x0 + ssx, lg.y1 + p.search_y0 + ssy};
+  std::vector<LevelImgs> py(levels + 1);
+  LevelImgs& b0 = py[0];
+  b0.lw = lg.x1 - lg.x0; b0.lh = lg.y1 - lg.y0; b0.rw = rg.x1 - rg.x0; b0.rh = rg.y1 - rg.y0;
+  VWB_TRY(ar.alloc(&b0.l, (size_t)b0.lw * b0.lh));
+  VWB_TRY(ar.alloc(&b0.r, (size_t)b0.rw * b0.rh));
+  const ImgF Lin{L, lcols, lrows, lpitch}, Rin{R, rcols, rrows, rpitch};
+  const ImgB Lmin{Lm, lcols, lrows, lmpitch}, Rmin{Rm, rcols, rrows, rmpitch};
+  VWB_TRY(crop_extend_f32_launch(Lin, lg.x0, lg.y0, b0.lw, b0.lh, b0.l, b0.lw, st));
+  VWB_TRY(crop_extend_f32_launch(Rin, rg.x0, rg.y0, b0.rw, b0.rh, b0.r, b0.rw, st));
+  {  // mean fill of masked pixels (:116-149); masks here are constant-edge-extended over the padded ROI
+    uint8_t *lmb, *rmb; double* acc;
+    VWB_TRY(ar.alloc(&lmb, (size_t)b0.lw * b0.lh));
+    VWB_TRY(ar.alloc(&rmb, (size_t)b0.rw * b0.rh));
+    VWB_TRY(ar.alloc(&acc, 2 * (2 + 2 * 256)));
+    VWB_TRY(crop_extend_u8_launch(Lmin, lg.x0, lg.y0, b0.lw, b0.lh, 0, lmb, b0.lw, st));
+    VWB_TRY(crop_extend_u8_launch(Rmin, rg.x0, rg.y0, b0.rw, b0.rh, 0, rmb, b0.rw, st));
+    double* acc_r = acc + (2 + 2 * 256);
+    VWB_TRY(masked_mean_launch(ImgF{b0.l, b0.lw, b0.lh, b0.lw}, ImgB{lmb, b0.lw, b0.lh, b0.lw}, acc, st));
+    VWB_TRY(masked_mean_launch(ImgF{b0.r, b0.rw, b0.rh, b0.rw}, ImgB{rmb, b0.rw, b0.rh, b0.rw}, acc_r, st));
+    double hacc[4];
+    VWB_CUDA(cudaMemcpyAsync(hacc, acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VWB_CUDA(cudaMemcpyAsync(hacc + 2, acc_r, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VWB_CUDA(cudaStreamSynchronize(st));
+    if (hacc[1] == 0.0 || hacc[3] == 0.0) { *all_invalid = 1; *d_disp_out = nullptr; return VWB200_OK; }   // :137-142, :320-331
+    VWB_TRY(mean_fill_launch(b0.l, b0.lw, b0.lh, b0.lw, ImgB{lmb, b0.lw, b0.lh, b0.lw}, acc, st));
+    VWB_TRY(mean_fill_launch(b0.r, b0.rw, b0.rh, b0.rw, ImgB{rmb, b0.rw, b0.rh, b0.rw}, acc_r, st));
+  }
+  // final masks: zero edge extension, no kernel padding (:192-197)
+  b0.lmw = bw; b0.lmh = bh; b0.rmw = bw + ssx; b0.rmh = bh + ssy;
+  VWB_TRY(ar.alloc(&b0.lm, (size_t)b0.lmw * b0.lmh));
+  VWB_TRY(ar.alloc(&b0.rm, (size_t)b0.rmw * b0.rmh));
+  VWB_TRY(crop_extend_u8_launch(Lmin, bbox.x0, bbox.y0, b0.lmw, b0.lmh, 1, b0.lm, b0.lmw, st));
+  VWB_TRY(crop_extend_u8_launch(Rmin, bbox.x0 + p.search_x0, bbox.y0 + p.search_y0, b0.rmw, b0.rmh, 1, b0.rm, b0.rmw, st));
+  for (int i = 1; i <= levels; ++i) {   // :209-216
+    const LevelImgs& a = py[i - 1];
+    LevelImgs& b = py[i];
+    b.lw = 1 + (a.lw - 1) / 2; b.lh = 1 + (a.lh - 1) / 2; b.rw = 1 + (a.rw - 1) / 2; b.rh = 1 + (a.rh - 1) / 2;
+    b.lmw = 1 + (a.lmw - 1) / 2; b.lmh = 1 + (a.lmh - 1) / 2; b.rmw = 1 + (a.rmw - 1) / 2; b.rmh = 1 + (a.rmh - 1) / 2;
+    VWB_TRY(ar.alloc(&b.l, (size_t)b.lw * b.lh));
+    VWB_TRY(ar.alloc(&b.r, (size_t)b.rw * b.rh));
+    VWB_TRY(ar.alloc(&b.lm, (size_t)b.lmw * b.lmh));
+    VWB_TRY(ar.alloc(&b.rm, (size_t)b.rmw * b.rmh));
+    VWB_TRY(pyramid_down_launch(ImgF{a.l, a.lw, a.lh, a.lw}, b.l, b.lw, st));
+    VWB_TRY(pyramid_down_launch(ImgF{a.r, a.rw, a.rh, a.rw}, b.r, b.rw, st));
+    VWB_TRY(subsample_mask_launch(ImgB{a.lm, a.lmw, a.lmh, a.lmw}, b.lm, b.lmw, st));
+    VWB_TRY(subsample_mask_launch(ImgB{a.rm, a.rmw, a.rmh, a.rmw}, b.rm, b.rmw, st));
+  }
+
+  // ---- level loop (CorrelationView.cc:363-830) ----
+  std::vector<HostZone> zones;
+  zones.push_back(HostZone{Box{0, 0, py[levels].lmw, py[levels].lmh}, Box{0, 0, ssx / up + 1, ssy / up + 1}});   // :338-342
+  vwb200_dispi* disp = nullptr;
+  std::vector<vwb200_dispi> hdisp;
+  const int tile = k1_generic_tile_w(kx);
+  for (int level = levels; level >= 0; --level) {
+    const LevelImgs& lv = py[level];
+    const int scaling = 1 << level;
+    const int dw = lv.lmw, dh = lv.lmh;
+    VWB_TRY(ar.alloc(&disp, (size_t)dw * dh));
+    VWB_CUDA(cudaMemsetAsync(disp, 0, (size_t)dw * dh * sizeof(vwb200_dispi), st));    // fresh ImageView: (0,0) invalid
+    const int rox = up * hkx / scaling, roy = up * hky / scaling;                     // :381
+    std::vector<Zone> zl, zr;
+    std::vector<int2> post;
+    const bool check = (p.consistency_threshold >= 0 && level == 0);
+    long long rl_elems = 0;
+    for (const HostZone& hz : zones) {
+      const int zw = hz.img.x1 - hz.img.x0, zh = hz.img.y1 - hz.img.y0;
+      if (zw <= 0 || zh <= 0) continue;
+      const int dsx = hz.disp.x1 - hz.disp.x0, dsy = hz.disp.y1 - hz.disp.y0;
+      if (dsx <= 0 || dsy <= 0) { set_error("zone with empty disparity range"); return VWB200_ELOGIC; }
+      Zone z{};
+      z.obase = (long long)hz.img.y0 * dw + hz.img.x0; z.opitch = dw; z.w = zw; z.h = zh;
+      z.lx = hz.img.x0 + rox - hkx; z.ly = hz.img.y0 + roy - hky;                      // :611-612 (expand by half kernel)
+      z.rx = z.lx + hz.disp.x0; z.ry = z.ly + hz.disp.y0;                             // :615
+      z.sx = dsx; z.sy = dsy; z.addx = 0; z.addy = 0;
+      zl.push_back(z);
+      post.push_back(make_int2(hz.disp.x0, hz.disp.y0));
+      if (check) {   // R->L (:669-675): reference = right crop, search in left shifted by -size
+        Zone q{};
+        q.obase = rl_elems; q.opitch = zw + dsx; q.w = zw + dsx; q.h = zh + dsy;
+        q.lx = z.rx; q.ly = z.ry; q.rx = z.lx - dsx; q.ry = z.ly - dsy;
+        q.sx = dsx; q.sy = dsy; q.addx = -dsx; q.addy = -dsy;
+        rl_elems += (long long)q.w * q.h;
+        zr.push_back(q);
+      }
+    }
+    const ImgF Ll{lv.l, lv.lw, lv.lh, lv.lw}, Rl{lv.r, lv.rw, lv.rh, lv.rw};
+    const Zone* d_zl = nullptr; const Tile* d_tl = nullptr; int ntl = 0;
+    VWB_TRY(run_k1_zones(p.cost_type, Ll, Rl, zl, kx, ky, disp, ar, st, &d_zl, &d_tl, &ntl));
+    vwb200_dispi* rl = nullptr; const Zone* d_zr = nullptr;
+    if (check && !zr.empty()) {
+      VWB_TRY(ar.alloc(&rl, (size_t)rl_elems));
+      VWB_TRY(run_k1_zones(p.cost_type, Rl, Ll, zr, kx, ky, rl, ar, st, &d_zr));
+    }
+    if (!zl.empty()) {
+      int2* d_post;
+      VWB_TRY(ar.alloc(&d_post, post.size()));
+      VWB_CUDA(cudaMemcpyAsync(d_post, post.data(), post.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+      VWB_TRY(zone_post_launch(d_tl, ntl, d_zl, d_zr, d_post, disp, rl, p.consistency_threshold, tile, st));
+    }
+    if (p.filter_half_kernel > 0) {   // :713-744
+      const int fh = p.filter_half_kernel;
+      vwb200_dispi *t1, *t2;
+      VWB_TRY(ar.alloc(&t2, (size_t)dw * dh));
+      if (level != 0) {
+        VWB_TRY(ar.alloc(&t1, (size_t)(dw + 2) * (dh + 2)));
+        VWB_TRY(rm_outliers_launch(disp, dw, dh, fh, fh, 3.0, 0.5, -1, -1, dw + 2, dh + 2, t1, st));
+        VWB_TRY(cleanup_pass2_launch(t1, dw, dh, t2, st));
+      } else {
+        VWB_TRY(rm_outliers_launch(disp, dw, dh, fh, fh, 3.0, 0.5, 0, 0, dw, dh, t2, st));
+      }
+      VWB_TRY(disparity_mask_launch(t2, dw, dh, ImgB{lv.lm, lv.lmw, lv.lmh, lv.lmw}, ImgB{lv.rm, lv.rmw, lv.rmh, lv.rmw}, disp, st));
+    }
+    if (level != 0) {   // :754-799 refine the search zones on the host (zones are O(10^3), data dependent)
+      hdisp.resize((size_t)dw * dh);
+      VWB_CUDA(cudaMemcpyAsync(hdisp.data(), disp, hdisp.size() * sizeof(vwb200_dispi), cudaMemcpyDeviceToHost, st));
+      VWB_CUDA(cudaStreamSynchronize(st));
+      zones.clear();
+      subdivide_regions_host(hdisp.data(), dw, dh, kx, ky, zones);
+      const LevelImgs& nl = py[level - 1];
+      const Box scale_search{0, 0, nl.rw - nl.lw, nl.rh - nl.lh};
+      for (HostZone& z : zones) {
+        if (!bempty(z.img)) { z.img.x0 *= 2; z.img.y0 *= 2; z.img.x1 *= 2; z.img.y1 *= 2; }
+        z.img.x0 = std::max(z.img.x0, 0); z.img.y0 = std::max(z.img.y0, 0);
+        z.img.x1 = std::min(z.img.x1, nl.lmw); z.img.y1 = std::min(z.img.y1, nl.lmh);
+        if (!bempty(z.disp)) { z.disp.x0 *= 2; z.disp.y0 *= 2; z.disp.x1 *= 2; z.disp.y1 *= 2; }
+        z.disp = bexpand(z.disp, 2, 2);
+        z.disp.x0 = std::max(z.disp.x0, scale_search.x0); z.disp.y0 = std::max(z.disp.y0, scale_search.y0);
+        z.disp.x1 = std::min(z.disp.x1, scale_search.x1); z.disp.y1 = std::min(z.disp.y1, scale_search.y1);
+        if (bempty(z.disp)) z.disp = Box{0, 0, ssx, ssy};
+      }
+    }
+  }
+  const LevelImgs& l0 = py[0];
+  if (l0.lmw != bw || l0.lmh != bh) { set_error("PyramidCorrelation: Solved disparity doesn't match requested bbox size."); return VWB200_EMATH; }
+  *d_disp_out = disp;
+  return VWB200_OK;
+}
+
+// stage a host image into HBM (or pass a device image through)
+template <class T>
+static int stage_in(const T* src, int w, int h, ptrdiff_t pitch, int on_device, Arena& ar, cudaStream_t st, const T** out, ptrdiff_t* opitch) {
+  if (on_device) { *out = src; *opitch = pitch; return VWB200_OK; }
+  T* d;
+  VWB_TRY(ar.alloc(&d, (size_t)w * h));
+  VWB_CUDA(cudaMemcpy2DAsync(d, (size_t)w * sizeof(T), src, (size_t)pitch * sizeof(T), (size_t)w * sizeof(T), h, cudaMemcpyHostToDevice, st));
+  *out = d; *opitch = w;
+  return VWB200_OK;
+}
+
+
+// ===================================================================================================
+// extern "C" ABI
+// ===================================================================================================
+extern "C" {
+
+const char* vwb200_last_error(void) { return t_error; }
+const char* vwb200_version(void) { return "vwb200 0.1 (sm_100a)"; }
+int vwb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+long long vwb200_kernel_launches(void) { return g_launches.load(); }
+int vwb200_last_k1_stats(vwb200_k1_stats* out) { if (!out) return VWB200_EARG; *out = t_k1_stats; return VWB200_OK; }
+
+int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrdiff_t lpitch,
+                          const float* right, int rw, int rh, ptrdiff_t rpitch,
+                          int sx, int sy, int kx, int ky, vwb200_dispi* out, ptrdiff_t opitch,
+                          int on_device, void* stream) {
+  // argument checks of calc_disparity (Stereo/Correlation.cc:340-353)
+  if (kx % 2 != 1 || ky % 2 != 1) { set_error("calc_disparity: Kernel input not sized with odd values."); return VWB200_EARG; }
+  if (kx > lw || ky > lh) { set_error("calc_disparity: Kernel size too large of active region."); return VWB200_EARG; }
+  if (sx <= 0 || sy <= 0) { set_error("calc_disparity: Search volume must be greater than 0."); return VWB200_EARG; }
+  if (rw < lw + sx - 1 || rh < lh + sy - 1) { set_error("calc_disparity: right raster smaller than region + search volume - 1."); return VWB200_EARG; }
+  if (cost_type < 0 || cost_type > 2) { set_error("calc_disparity: unsupported cost type %d", cost_type); return VWB200_EARG; }
+  if (!left || !right || !out) { set_error("calc_disparity: null pointer"); return VWB200_EARG; }
+  VWB_TRY(ensure_device());
+  StreamGuard sg; VWB_TRY(sg.init(stream));
+  cudaStream_t st = sg.st;
+  const long long launches0 = g_launches.load();
+  {
+    Arena ar(st);
+    const int W = lw - kx + 1, H = lh - ky + 1;
+    const float *dl, *dr; ptrdiff_t dlp, drp;
+    VWB_TRY(stage_in(left, lw, lh, lpitch, on_device, ar, st, &dl, &dlp));
+    VWB_TRY(stage_in(right, lw + sx - 1, lh + sy - 1, rpitch, on_device, ar, st, &dr, &drp));
+    vwb200_dispi* dout = out; ptrdiff_t dop = opitch;
+    if (!on_device) { VWB_TRY(ar.alloc(&dout, (size_t)W * H)); dop = W; }
+    const ImgF Li{dl, lw, lh, dlp}, Ri{dr, lw + sx - 1, lh + sy - 1, drp};
+    int path = 1;
+    // exact-integer fast path when the imagery allows it
+    {
+      float* d_stats; float hs[6];
+      VWB_TRY(ar.alloc(&d_stats, 6));
+      VWB_TRY(image_stats_launch(Li, d_stats, st));
+      VWB_TRY(image_stats_launch(Ri, d_stats + 3, st));
+      VWB_CUDA(cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+      VWB_CUDA(cudaStreamSynchronize(st));
+      const float vmin = std::min(hs[0], hs[3]), vmax = std::max(hs[1], hs[4]);
+      const bool integer = hs[2] != 0.0f && hs[5] != 0.0f;
+      if (k1_fast_supported(cost_type, kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK) {
+        const size_t wb = k1_fast_workspace_bytes(W, H, sx, sy, kx, ky);
+        unsigned char* ws;
+        VWB_TRY(ar.alloc(&ws, wb));
+        VWB_TRY(k1_fast_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, dout, dop, ws, wb, st));
+        path = 0;
+      }
+    }
+    if (path == 1) {
+      std::vector<Zone> zones(1);
+      Zone& z = zones[0];
+      z.obase = 0; z.opitch = (int)dop; z.w = W; z.h = H; z.lx = 0; z.ly = 0; z.rx = 0; z.ry = 0; z.sx = sx; z.sy = sy; z.addx = 0; z.addy = 0;
+      VWB_TRY(run_k1_zones(cost_type, Li, Ri, zones, kx, ky, dout, ar, st));
+    }
+    if (!on_device)
+      VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch * sizeof(vwb200_dispi), dout, (size_t)W * sizeof(vwb200_dispi),
+                                 (size_t)W * sizeof(vwb200_dispi), H, cudaMemcpyDeviceToHost, st));
+    t_k1_stats.path = path;
+  }
+  VWB_CUDA(cudaStreamSynchronize(st));
+  t_k1_stats.launches = (int)(g_launches.load() - launches0);
+  return VWB200_OK;
+}
+
+int vwb200_pyramid_down(const float* in, int w, int h, ptrdiff_t pitch, float* out, ptrdiff_t opitch, int on_device, void* stream) {
+  if (!in || !out || w <= 0 || h <= 0) { set_error("pyramid_down: bad arguments"); return VWB200_EARG; }
+  VWB_TRY(ensure_device());
+  StreamGuard sg; VWB_TRY(sg.init(stream));
+  cudaStream_t st = sg.st;
+  {
+    Arena ar(st);
+    const int ow = 1 + (w - 1) / 2, oh = 1 + (h - 1) / 2;
+    const float* din; ptrdiff_t dp;
+    VWB_TRY(stage_in(in, w, h, pitch, on_device, ar, st, &din, &dp));
+    float* dout = out; ptrdiff_t dop = opitch;
+    if (!on_device) { VWB_TRY(ar.alloc(&dout, (size_t)ow * oh)); dop = ow; }
+    VWB_TRY(pyramid_down_launch(ImgF{din, w, h, dp}, dout, dop, st));
+    if (!on_device)
+      VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch * sizeof(float), dout, (size_t)ow * sizeof(float), (size_t)ow * sizeof(float), oh, cudaMemcpyDeviceToHost, st));
+  }
+  VWB_CUDA(cudaStreamSynchronize(st));
+  return VWB200_OK;
+}
+
+int vwb200_subsample_mask_by_two(const uint8_t* in, int w, int h, ptrdiff_t pitch, uint8_t* out, ptrdiff_t opitch, int on_device, void* stream) {
+  if (!in || !out || w <= 0 || h <= 0) { set_error("subsample_mask_by_two: bad arguments"); return VWB200_EARG; }
+  VWB_TRY(ensure_device());
+  StreamGuard sg; VWB_TRY(sg.init(stream));
+  cudaStream_t st = sg.st;
+  {
+    Arena ar(st);
+    const int ow = 1 + (w - 1) / 2, oh = 1 + (h - 1) / 2;
+    const uint8_t* din; ptrdiff_t dp;
+    VWB_TRY(stage_in(in, w, h, pitch, on_device, ar, st, &din, &dp));
+    uint8_t* dout = out; ptrdiff_t dop = opitch;
+    if (!on_device) { VWB_TRY(ar.alloc(&dout, (size_t)ow * oh)); dop = ow; }
+    VWB_TRY(subsample_mask_launch(ImgB{din, w, h, dp}, dout, dop, st));
+    if (!on_device)
+      VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch, dout, (size_t)ow, (size_t)ow, oh, cudaMemcpyDeviceToHost, st));
+  }
+  VWB_CUDA(cudaStreamSynchronize(st));
+  return VWB200_OK;
+}
+
+int vwb200_cross_corr_consistency_check(vwb200_dispi* l2r, int lw, int lh, ptrdiff_t lpitch, const vwb200_dispi* r2l, int rw, int rh,
+                                        ptrdiff_t rpitch, float threshold, int on_device, void* stream) {
+  if (!l2r || !r2l) { set_error("cross_corr_consistency_check: null pointer"); return VWB200_EARG; }
+  VWB_TRY(ensure_device());
+  StreamGuard sg; VWB_TRY(sg.init(stream));
+  cudaStream_t st = sg.st;
+  {
+    Arena ar(st);
+    vwb200_dispi* dl = l2r; const vwb200_dispi* dr = r2l; ptrdiff_t dlp = lpitch, drp = rpitch;
+    if (!on_device) {
+      VWB_TRY(ar.alloc(&dl, (size_t)lw * lh));
+      VWB_CUDA(cudaMemcpy2DAsync(dl, (size_t)lw * 12, l2r, (size_t)lpitch * 12, (size_t)lw * 12, lh, cudaMemcpyHostToDevice, st));
+      dlp = lw;
+      VWB_TRY(stage_in(r2l, rw, rh, rpitch, 0, ar, st, &dr, &drp));
+    }
+    VWB_TRY(consistency_launch(dl, lw, lh, dlp, dr, rw, rh, drp, threshold, st));
+    if (!on_device)
+      VWB_CUDA(cudaMemcpy2DAsync(l2r, (size_t)lpitch * 12, dl, (size_t)lw * 12, (size_t)lw * 12, lh, cudaMemcpyDeviceToHost, st));
+  }
+  VWB_CUDA(cudaStreamSynchronize(st));
+  return VWB200_OK;
+}
+
+static int filter_common(int which, const vwb200_dispi* in, int w, int h, int hx, int hy, double pt, double rt,
+                         const uint8_t* lm, const uint8_t* rm, int rmw, int rmh, vwb200_dispi* out, int on_device, void* stream) {
+  if (!in || !out || w <= 0 || h <= 0) { set_error("disparity filter: bad arguments"); return VWB200_EARG; }
+  VWB_TRY(ensure_device());
+  StreamGuard sg; VWB_TRY(sg.init(stream));
+  cudaStream_t st = sg.st;
+  {
+    Arena ar(st);
+    const vwb200_dispi* din; ptrdiff_t dp;
+    VWB_TRY(stage_in(in, w, h, (ptrdiff_t)w, on_device, ar, st, &din, &dp));
+    vwb200_dispi* dout = out;
+    if (!on_device) VWB_TRY(ar.alloc(&dout, (size_t)w * h));
+    if (which == 0) {
+      VWB_TRY(rm_outliers_launch(din, w, h, hx, hy, pt, rt, 0, 0, w, h, dout, st));
+    } else if (which == 1) {
+      vwb200_dispi* t1;
+      VWB_TRY(ar.alloc(&t1, (size_t)(w + 2) * (h + 2)));
+      VWB_TRY(rm_outliers_launch(din, w, h, hx, hy, pt, rt, -1, -1, w + 2, h + 2, t1, st));
+      VWB_TRY(cleanup_pass2_launch(t1, w, h, dout, st));
+    } else {
+      const uint8_t *dlm, *drm; ptrdiff_t p1, p2;
+      VWB_TRY(stage_in(lm, w, h, (ptrdiff_t)w, on_device, ar, st, &dlm, &p1));
+      VWB_TRY(stage_in(rm, rmw, rmh, (ptrdiff_t)rmw, on_device, ar, st, &drm, &p2));
+      VWB_TRY(disparity_mask_launch(din, w, h, ImgB{dlm, w, h, p1}, ImgB{drm, rmw, rmh, p2}, dout, st));
+    }
+    if (!on_device) VWB_CUDA(cudaMemcpyAsync(out, dout, (size_t)w * h * sizeof(vwb200_dispi), cudaMemcpyDeviceToHost, st));
+  }
+  VWB_CUDA(cudaStreamSynchronize(st));
+  return VWB200_OK;
+}
+int vwb200_rm_outliers_using_thresh(const vwb200_dispi* in, int w, int h, int hx, int hy, double pt, double rt, vwb200_dispi* out, int on_device, void* stream) {
+  return filter_common(0, in, w, h, hx, hy, pt, rt, nullptr, nullptr, 0, 0, out, on_device, stream);
+}
+int vwb200_disparity_cleanup_using_thresh(const vwb200_dispi* in, int w, int h, int hx, int hy, double pt, double rt, vwb200_dispi* out, int on_device, void* stream) {
+  return filter_common(1, in, w, h, hx, hy, pt, rt, nullptr, nullptr, 0, 0, out, on_device, stream);
+}
+int vwb200_disparity_mask(const vwb200_dispi* in, int w, int h, const uint8_t* lm, const uint8_t* rm, int rmw, int rmh, vwb200_dispi* out, int on_device, void* stream) {
+  if (!lm || !rm) { set_error("disparity_mask: null mask"); return VWB200_EARG; }
+  return filter_common(2, in, w, h, 1, 1, 0, 0, lm, rm, rmw, rmh, out, on_device, stream);
+}
+
+// ---- the view -------------------------------------------------------------------------------------
+int vwb200_corr_create(const vwb200_corr_params* p, vwb200_corr** out) {
+  if (!p || !out) { set_error("corr_create: null pointer"); return VWB200_EARG; }
+  const double w = (double)p->search_x1 - p->search_x0, h = (double)p->search_y1 - p->search_y0;
+  if (!(w * h == w * h)) { set_error("PyramidCorrelationView: Invalid search region"); return VWB200_EARG; }   // CorrelationView.h:88-94
+  if (p->search_x1 <= p->search_x0 || p->search_y1 <= p->search_y0) { set_error("PyramidCorrelationView: empty search region"); return VWB200_EARG; }
+  if (p->kernel_x % 2 != 1 || p->kernel_y % 2 != 1 || p->kernel_x < 1 || p->kernel_y < 1) { set_error("PyramidCorrelationView: kernel size must be odd"); return VWB200_EARG; }
+  if (p->algorithm != 0) { set_error("only VW_CORRELATION_BM is implemented by the vwb200 engine"); return VWB200_ENOIMPL; }
+  if (p->blob_filter_area > 0) { set_error("blob_filter_area > 0 is not implemented"); return VWB200_ENOIMPL; }
+  if (p->cost_type < 0 || p->cost_type > 2) { set_error("cost type %d is only valid for SGM", p->cost_type); return VWB200_EARG; }
+  vwb200_corr* h_ = new vwb200_corr();
+  h_->p = *p;
+  // CorrelationView.h:96-105 (float maths)
+  const int largest_search = std::max(p->search_x1 - p->search_x0, p->search_y1 - p->search_y0);
+  int m = (int)(std::floor(std::log((float)largest_search) / std::log(2.0f)) - 1);
+  if (m > p->max_pyramid_levels) m = p->max_pyramid_levels;
+  if (m < 0) m = 0;
+  h_->max_level_by_search = m;
+  *out = h_;
+  return VWB200_OK;
+}
+
+int vwb200_corr_set_inputs(vwb200_corr* h, const float* left, int lcols, int lrows, ptrdiff_t lpitch,
+                           const float* right, int rcols, int rrows, ptrdiff_t rpitch,
+                           const uint8_t* lmask, ptrdiff_t lmpitch, const uint8_t* rmask, ptrdiff_t rmpitch, int on_device) {
+  if (!h || !left || !right || !lmask || !rmask || lcols <= 0 || lrows <= 0 || rcols <= 0 || rrows <= 0) { set_error("corr_set_inputs: bad arguments"); return VWB200_EARG; }
+  VWB_TRY(ensure_device());
+  h->release();
+  VWB_CUDA(cudaGetDevice(&h->device));
+  h->lcols = lcols; h->lrows = lrows; h->rcols = rcols; h->rrows = rrows;
+  if (on_device) {
+    h->L = left; h->R = right; h->Lm = lmask; h->Rm = rmask;
+    h->lpitch = lpitch; h->rpitch = rpitch; h->lmpitch = lmpitch; h->rmpitch = rmpitch;
+    return VWB200_OK;
+  }
+  float *dl, *dr; uint8_t *dlm, *drm;
+  VWB_CUDA(cudaMalloc(&dl, (size_t)lcols * lrows * 4)); VWB_CUDA(cudaMalloc(&dr, (size_t)rcols * rrows * 4));
+  VWB_CUDA(cudaMalloc(&dlm, (size_t)lcols * lrows)); VWB_CUDA(cudaMalloc(&drm, (size_t)rcols * rrows));
+  h->L = dl; h->R = dr; h->Lm = dlm; h->Rm = drm; h->owned = true;
+  h->lpitch = lcols; h->rpitch = rcols; h->lmpitch = lcols; h->rmpitch = rcols;
+  VWB_CUDA(cudaMemcpy2D(dl, (size_t)lcols * 4, left, (size_t)lpitch * 4, (size_t)lcols * 4, lrows, cudaMemcpyHostToDevice));
+  VWB_CUDA(cudaMemcpy2D(dr, (size_t)rcols * 4, right, (size_t)rpitch * 4, (size_t)rcols * 4, rrows, cudaMemcpyHostToDevice));
+  VWB_CUDA(cudaMemcpy2D(dlm, (size_t)lcols, lmask, (size_t)lmpitch, (size_t)lcols, lrows, cudaMemcpyHostToDevice));
+  VWB_CUDA(cudaMemcpy2D(drm, (size_t)rcols, rmask, (size_t)rmpitch, (size_t)rcols, rrows, cudaMemcpyHostToDevice));
+  return VWB200_OK;
+}
+
+int vwb200_corr_cols(const vwb200_corr* h) { return h ? h->lcols : 0; }
+int vwb200_corr_rows(const vwb200_corr* h) { return h ? h->lrows : 0; }
+int vwb200_corr_num_levels(const vwb200_corr* h, int bw, int bh) { return h ? h->num_levels(bw, bh) : VWB200_EARG; }
+
+int vwb200_corr_rasterize(vwb200_corr* h, int x0, int y0, int x1, int y1, float* dest, ptrdiff_t dest_pitch, int dest_on_device, void* stream) {
+  if (!h || !dest) { set_error("corr_rasterize: null pointer"); return VWB200_EARG; }
+  if (!h->L) { set_error("corr_rasterize: inputs not set"); return VWB200_ELOGIC; }
+  if (x1 <= x0 || y1 <= y0) { set_error("corr_rasterize: empty bbox"); return VWB200_EARG; }
+  VWB_TRY(ensure_device());
+  VWB_CUDA(cudaSetDevice(h->device));
+  StreamGuard sg; VWB_TRY(sg.init(stream));
+  cudaStream_t st = sg.st;
+  {
+    Arena ar(st);
+    const int bw = x1 - x0, bh = y1 - y0;
+    Box proc{x0, y0, x1, y1};
+    if (h->p.collar_size > 0) proc = bexpand(proc, h->p.collar_size, h->p.collar_size);   // CorrelationView.h:128-131
+    const int pw = proc.x1 - proc.x0;
+    vwb200_dispi* disp = nullptr; int all_invalid = 0;
+    VWB_TRY(h->prerasterize(proc, &disp, &all_invalid, ar, st));
+    float* dout = dest; ptrdiff_t dop = dest_pitch;
+    if (!dest_on_device) { VWB_TRY(ar.alloc(&dout, (size_t)bw * bh * 3)); dop = bw; }
+    if (all_invalid) {
+      VWB_CUDA(cudaMemset2DAsync(dout, (size_t)dop * 12, 0, (size_t)bw * 12, bh, st));
+    } else {
+      VWB_TRY(finalize_launch(disp, pw, proc.y1 - proc.y0, h->p.search_x0, h->p.search_y0, dout, dop, x0 - proc.x0, y0 - proc.y0, bw, bh, st));
+    }
+    if (!dest_on_device)
+      VWB_CUDA(cudaMemcpy2DAsync(dest, (size_t)dest_pitch * 12, dout, (size_t)bw * 12, (size_t)bw * 12, bh, cudaMemcpyDeviceToHost, st));
+  }
+  VWB_CUDA(cudaStreamSynchronize(st));
+  return VWB200_OK;
+}
+
+void vwb200_corr_destroy(vwb200_corr* h) { delete h; }
+
+}  // extern "C"

@@ -1,0 +1,278 @@
+// k1_generic.cu -- general (any float input, fp64 accumulation, zone-table driven) fused
+// cost-volume + arg-best kernel.  This is the kernel the pyramid level loop uses: thousands of
+// small zones with narrow search windows per level (Stereo/CorrelationView.cc:607-648), all handled
+// by ONE launch per level through a tile table.
+//
+// Semantics follow vw::stereo::best_of_search_convolution (Stereo/Correlation.cc:33-137):
+//  * per-pixel cost in FLOAT (|a-b|, (a-b)^2, a*b; Stereo/CostFunctions.h:72-141), widened to double
+//  * kx x ky window sums in double
+//  * NCC: cost *= sqrt(lp * rp[d]) in double (CostFunctions.h:227-231), "better" is '>'
+//  * disparities visited dy-major / dx-minor; strict comparison => first disparity wins ties
+//  * pixel invalid iff every disparity produced the same cost (best == worst, :121-133)
+//  * NaN costs (NCC zero-energy windows) follow the reference's order-dependent best/worst state
+//    machine exactly: such pixels are flagged here and re-evaluated sequentially by k1_nan_fixup.
+//
+// Structure per CTA (one TW x TH tile of one zone), per disparity:
+//   phase 1: thread = (padded column, row segment): vertical sliding sum of the per-pixel cost,
+//            stored to shared memory V[y][x']            (O(1) per pixel, coalesced global reads)
+//   phase 2: thread = (row, column chunk): horizontal sliding sum over V, compare with the running
+//            best kept in shared memory                  (O(1) per pixel)
+// Window sums are exact (hence order independent, hence identical to the reference's sliding sums)
+// whenever the cost terms are multiples of 2^-32 below 2^21 (see DESIGN.md "exactness").
+#include "common.cuh"
+#include <vector>
+
+namespace vwb200 {
+
+static constexpr int K1G_THREADS = 256;
+static constexpr int K1G_TILE = 64;
+static constexpr int IDX_MASK = 0x0fffffff;
+static constexpr int FLAG_DIFF = 0x40000000;
+static constexpr int FLAG_NAN = 0x20000000;
+
+int k1_generic_tile_w(int kx) { (void)kx; return K1G_TILE; }
+int k1_generic_tile_h(int ky) { (void)ky; return K1G_TILE; }
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <int COST>
+__device__ __forceinline__ double pix_cost(float a, float b) {
+  if (COST == VWB200_SQUARED_DIFFERENCE) { float d = __fsub_rn(a, b); return (double)__fmul_rn(d, d); }
+  if (COST == VWB200_CROSS_CORRELATION) { return (double)__fmul_rn(a, b); }
+  return (double)fabsf(__fsub_rn(a, b));
+}
+template <int COST>
+__device__ __forceinline__ bool better(double c, double q) {
+  return COST == VWB200_CROSS_CORRELATION ? (c > q) : (c < q);
+}
+
+__device__ __forceinline__ float ld_clamped(const ImgF& im, int x, int y) {
+  return __ldg(im.p + (ptrdiff_t)clampi(y, 0, im.h - 1) * im.pitch + clampi(x, 0, im.w - 1));
+}
+
+template <int COST>
+__global__ void __launch_bounds__(K1G_THREADS)
+k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __restrict__ tiles,
+                  int kx, int ky, NccMaps ncc, vwb200_dispi* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Tile t = tiles[blockIdx.x];
+  const Zone z = zones[t.zone];
+  const int tw = min(K1G_TILE, z.w - t.tx), th = min(K1G_TILE, z.h - t.ty);
+  const int pw = tw + kx - 1;
+  const int vp = pw | 1;                                   // odd pitch: conflict-free row walking
+  double* V = reinterpret_cast<double*>(smem_raw);         // [th][vp]
+  double* best = V + (size_t)K1G_TILE * ((K1G_TILE + kx - 1) | 1);   // [th*tw]
+  int* bidx = reinterpret_cast<int*>(best + K1G_TILE * K1G_TILE);    // [th*tw]
+  const int tid = threadIdx.x, nth = blockDim.x;
+
+  // work decomposition
+  int S = nth / pw; if (S < 1) S = 1; { int m = th / 8; if (m < 1) m = 1; if (S > m) S = m; }
+  const int rps = (th + S - 1) / S;
+  int C = nth / th; if (C < 1) C = 1; { int m = tw / 8; if (m < 1) m = 1; if (C > m) C = m; }
+  const int cw = (tw + C - 1) / C;
+
+  const int lx0 = z.lx + t.tx, ly0 = z.ly + t.ty;          // left coords of the tile's padded origin
+  const int rx0 = z.rx + t.tx, ry0 = z.ry + t.ty;
+
+  for (int dy = 0; dy < z.sy; ++dy) {
+    for (int dx = 0; dx < z.sx; ++dx) {
+      // ---- phase 1: vertical sliding sums -------------------------------------------------------
+      for (int item = tid; item < pw * S; item += nth) {
+        const int xp = item % pw, s = item / pw;
+        const int yb = s * rps, ye = min(th, yb + rps);
+        if (yb < ye) {
+          const int gl = lx0 + xp, gr = rx0 + xp + dx;
+          double v = 0.0;
+          for (int j = 0; j < ky; ++j)
+            v += pix_cost<COST>(ld_clamped(L, gl, ly0 + yb + j), ld_clamped(R, gr, ry0 + yb + j + dy));
+          V[yb * vp + xp] = v;
+          for (int y = yb + 1; y < ye; ++y) {
+            v += pix_cost<COST>(ld_clamped(L, gl, ly0 + y + ky - 1), ld_clamped(R, gr, ry0 + y + ky - 1 + dy));
+            v -= pix_cost<COST>(ld_clamped(L, gl, ly0 + y - 1), ld_clamped(R, gr, ry0 + y - 1 + dy));
+            V[y * vp + xp] = v;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: horizontal sliding sums + running best ---------------------------------------
+      const int d = dy * z.sx + dx;
+      for (int item = tid; item < th * C; item += nth) {
+        const int y = item % th, c = item / th;
+        const int xb = c * cw, xe = min(tw, xb + cw);
+        if (xb < xe) {
+          const double* vr = V + y * vp;
+          double h = 0.0;
+          for (int i = 0; i < kx; ++i) h += vr[xb + i];
+          for (int x = xb; x < xe; ++x) {
+            double cost = h;
+            if (COST == VWB200_CROSS_CORRELATION) {
+              const double lp = ncc.inv_l[(ptrdiff_t)(ly0 + y - ncc.l_oy) * ncc.l_w + (lx0 + x - ncc.l_ox)];
+              const double rp = ncc.inv_r[(ptrdiff_t)(ry0 + y + dy - ncc.r_oy) * ncc.r_w + (rx0 + x + dx - ncc.r_ox)];
+              cost = __dmul_rn(h, sqrt(__dmul_rn(lp, rp)));
+            }
+            const int k = y * tw + x;
+            if (d == 0) {
+              best[k] = cost;
+              bidx[k] = (cost != cost) ? FLAG_NAN : 0;
+            } else {
+              const double b = best[k];
+              int bi = bidx[k];
+              if (cost != b) bi |= FLAG_DIFF;
+              if (cost != cost) bi |= FLAG_NAN;
+              if (better<COST>(cost, b)) { best[k] = cost; bi = (bi & ~IDX_MASK) | d; }
+              bidx[k] = bi;
+            }
+            if (x + 1 < xe) h += vr[x + kx] - vr[x];
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- epilogue: coalesced-ish 12-byte pixel writes -------------------------------------------------
+  for (int k = tid; k < tw * th; k += nth) {
+    const int y = k / tw, x = k % tw;
+    const int bi = bidx[k];
+    const int d = bi & IDX_MASK;
+    vwb200_dispi o;
+    o.dx = d % z.sx + z.addx;
+    o.dy = d / z.sx + z.addy;
+    o.valid = (bi & FLAG_NAN) ? 2 : ((bi & FLAG_DIFF) ? 1 : 0);
+    out[z.obase + (ptrdiff_t)(t.ty + y) * z.opitch + (t.tx + x)] = o;
+  }
+}
+
+static size_t k1g_smem_bytes(int kx) {
+  size_t vp = (size_t)((K1G_TILE + kx - 1) | 1);
+  return (size_t)K1G_TILE * vp * sizeof(double) + (size_t)K1G_TILE * K1G_TILE * (sizeof(double) + sizeof(int));
+}
+
+int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
+                      int kx, int ky, NccMaps ncc, vwb200_dispi* out, cudaStream_t st) {
+  if (ntiles <= 0) return VWB200_OK;
+  if (kx > 129 || ky > 129) { set_error("kernel size %dx%d exceeds the supported 129", kx, ky); return VWB200_ENOIMPL; }
+  const size_t smem = k1g_smem_bytes(kx);
+  void (*kern)(ImgF, ImgF, const Zone*, const Tile*, int, int, NccMaps, vwb200_dispi*);
+  switch (cost) {
+    case VWB200_SQUARED_DIFFERENCE: kern = k1_generic_kernel<VWB200_SQUARED_DIFFERENCE>; break;
+    case VWB200_CROSS_CORRELATION:  kern = k1_generic_kernel<VWB200_CROSS_CORRELATION>; break;
+    default:                        kern = k1_generic_kernel<VWB200_ABSOLUTE_DIFFERENCE>; break;
+  }
+  VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ntiles, K1G_THREADS, smem, st>>>(left, right, d_zones, d_tiles, kx, ky, ncc, out);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1 / boxsum(v*v): NCCCost's left_precision / right_precision (Stereo/CostFunctions.h:214-219).
+// square() is the float product v*v (Math/Functors.h:316-321), summed in double.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K1G_THREADS)
+box_sq_inv_kernel(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* V = reinterpret_cast<double*>(smem_raw);
+  const int tx0 = blockIdx.x * K1G_TILE, ty0 = blockIdx.y * K1G_TILE;
+  const int tw = min(K1G_TILE, ow - tx0), th = min(K1G_TILE, oh - ty0);
+  const int pw = tw + kx - 1, vp = pw | 1;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  int S = nth / pw; if (S < 1) S = 1; { int m = th / 8; if (m < 1) m = 1; if (S > m) S = m; }
+  const int rps = (th + S - 1) / S;
+  for (int item = tid; item < pw * S; item += nth) {
+    const int xp = item % pw, s = item / pw;
+    const int yb = s * rps, ye = min(th, yb + rps);
+    if (yb < ye) {
+      const int gx = ox0 + tx0 + xp, gy = oy0 + ty0;
+      double v = 0.0;
+      for (int j = 0; j < ky; ++j) { float a = ld_clamped(img, gx, gy + yb + j); v += (double)__fmul_rn(a, a); }
+      V[yb * vp + xp] = v;
+      for (int y = yb + 1; y < ye; ++y) {
+        float a = ld_clamped(img, gx, gy + y + ky - 1); v += (double)__fmul_rn(a, a);
+        float b = ld_clamped(img, gx, gy + y - 1); v -= (double)__fmul_rn(b, b);
+        V[y * vp + xp] = v;
+      }
+    }
+  }
+  __syncthreads();
+  int C = nth / th; if (C < 1) C = 1; { int m = tw / 8; if (m < 1) m = 1; if (C > m) C = m; }
+  const int cw = (tw + C - 1) / C;
+  for (int item = tid; item < th * C; item += nth) {
+    const int y = item % th, c = item / th;
+    const int xb = c * cw, xe = min(tw, xb + cw);
+    if (xb < xe) {
+      const double* vr = V + y * vp;
+      double h = 0.0;
+      for (int i = 0; i < kx; ++i) h += vr[xb + i];
+      for (int x = xb; x < xe; ++x) {
+        out[(ptrdiff_t)(ty0 + y) * ow + (tx0 + x)] = __ddiv_rn(1.0, h);
+        if (x + 1 < xe) h += vr[x + kx] - vr[x];
+      }
+    }
+  }
+}
+
+int box_sq_inv_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* out, cudaStream_t st) {
+  if (ow <= 0 || oh <= 0) return VWB200_OK;
+  size_t smem = (size_t)K1G_TILE * ((K1G_TILE + kx - 1) | 1) * sizeof(double);
+  VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((ow + K1G_TILE - 1) / K1G_TILE, (oh + K1G_TILE - 1) / K1G_TILE);
+  box_sq_inv_kernel<<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, out);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NaN fix-up: pixels the main kernel marked valid==2 saw at least one NaN cost.  Replays the
+// reference's sequential best/worst state machine (Stereo/Correlation.cc:97-133) for them.
+// ------------------------------------------------------------------------------------------------
+template <int COST>
+__global__ void k1_nan_fixup_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, int kx, int ky, NccMaps ncc,
+                                    vwb200_dispi* __restrict__ out) {
+  const Zone z = zones[blockIdx.y];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < z.w * z.h; k += gridDim.x * blockDim.x) {
+    const int x = k % z.w, y = k / z.w;
+    vwb200_dispi* o = out + z.obase + (ptrdiff_t)y * z.opitch + x;
+    if (o->valid != 2) continue;
+    double best = 0, worst = 0;
+    int bd = 0;
+    for (int dy = 0; dy < z.sy; ++dy)
+      for (int dx = 0; dx < z.sx; ++dx) {
+        double h = 0.0;
+        for (int j = 0; j < ky; ++j)
+          for (int i = 0; i < kx; ++i)
+            h += pix_cost<COST>(ld_clamped(L, z.lx + x + i, z.ly + y + j), ld_clamped(R, z.rx + x + i + dx, z.ry + y + j + dy));
+        double cost = h;
+        if (COST == VWB200_CROSS_CORRELATION) {
+          const double lp = ncc.inv_l[(ptrdiff_t)(z.ly + y - ncc.l_oy) * ncc.l_w + (z.lx + x - ncc.l_ox)];
+          const double rp = ncc.inv_r[(ptrdiff_t)(z.ry + y + dy - ncc.r_oy) * ncc.r_w + (z.rx + x + dx - ncc.r_ox)];
+          cost = __dmul_rn(h, sqrt(__dmul_rn(lp, rp)));
+        }
+        if (dx == 0 && dy == 0) { best = worst = cost; }
+        else if (better<COST>(cost, best)) { best = cost; bd = dy * z.sx + dx; }
+        else if (!better<COST>(cost, worst)) { worst = cost; }
+      }
+    o->dx = bd % z.sx + z.addx;
+    o->dy = bd / z.sx + z.addy;
+    o->valid = (best == worst) ? 0 : 1;
+  }
+}
+
+int k1_nan_fixup_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, int nzones, int kx, int ky,
+                        NccMaps ncc, vwb200_dispi* out, cudaStream_t st) {
+  for (int z0 = 0; z0 < nzones; z0 += 32768) {
+    const int n = nzones - z0 < 32768 ? nzones - z0 : 32768;
+    dim3 grid(8, n);
+    switch (cost) {
+      case VWB200_SQUARED_DIFFERENCE:
+        k1_nan_fixup_kernel<VWB200_SQUARED_DIFFERENCE><<<grid, 128, 0, st>>>(left, right, d_zones + z0, kx, ky, ncc, out); break;
+      case VWB200_CROSS_CORRELATION:
+        k1_nan_fixup_kernel<VWB200_CROSS_CORRELATION><<<grid, 128, 0, st>>>(left, right, d_zones + z0, kx, ky, ncc, out); break;
+      default:
+        k1_nan_fixup_kernel<VWB200_ABSOLUTE_DIFFERENCE><<<grid, 128, 0, st>>>(left, right, d_zones + z0, kx, ky, ncc, out); break;
+    }
+    VWB_LAUNCH_CHECK();
+  }
+  return VWB200_OK;
+}
+
+}  // namespace vwb200
