@@ -222,3 +222,31 @@ def test_device_tensor_path(vwb, oracle):
     got = vwb.calc_disparity(0, dl, dr, (12, 10), (9, 9))
     assert got.is_cuda
     _assert_disp_equal(got.cpu().numpy(), oracle.calc_disparity(0, left, right, (12, 10), (9, 9)))
+
+
+@pytest.mark.parametrize("shape", [((300, 70), (16, 8), (21, 21)), ((500, 40), (32, 4), (7, 7)), ((237, 33), (64, 3), (15, 15)),
+                                   ((64, 64), (8, 8), (3, 5)), ((260, 100), (128, 2), (21, 21)), ((473, 65), (12, 11), (31, 9))])
+def test_calc_disparity_exact_int_fast_path(vwb, oracle, shape):
+    """The exact-integer TMA/shuffle kernel (k1_fast) must be bit-identical to the oracle: strips (W > 236),
+    bands (H > 32), ragged edges, ties (first disparity in raster order wins)."""
+    from visionworkbench_b200.synth import make_rasters
+    (W, H), search, kernel = shape
+    left, right = make_rasters(W, H, search, kernel, seed=7 + W)
+    got = vwb.calc_disparity(0, left, right, search, kernel)
+    assert vwb.last_k1_stats()["path"] == "exact-int"
+    ref = oracle.calc_disparity(0, left, right, search, kernel)
+    _assert_disp_equal(got, ref, f"fast {shape}")
+
+
+def test_fast_path_ties_and_constant_regions(vwb, oracle):
+    """8-bit imagery with flat regions: many exact ties and all-equal (invalid) pixels."""
+    rng = np.random.default_rng(77)
+    W, H, search, kernel = 280, 70, (16, 8), (7, 7)
+    right = np.floor(rng.random((H + 6 + 7, W + 6 + 15)) * 4).astype(np.float32)    # 2-bit noise: ties everywhere
+    right[20:60, 40:200] = 3.0                                                        # flat block: all-equal costs
+    left = np.ascontiguousarray(right[2:2 + H + 6, 5:5 + W + 6])
+    got = vwb.calc_disparity(0, left, right, search, kernel)
+    assert vwb.last_k1_stats()["path"] == "exact-int"
+    ref = oracle.calc_disparity(0, left, right, search, kernel)
+    assert (ref[..., 2] == 0).any() and (ref[..., 2] == 1).any()
+    _assert_disp_equal(got, ref, "ties")

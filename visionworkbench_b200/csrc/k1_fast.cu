@@ -1,9 +1,37 @@
-// k1_fast.cu -- exact-integer fast path of the fused cost-volume + arg-best kernel (placeholder
-// dispatch: filled in by the optimised kernel; until then every configuration reports "unsupported"
-// and the generic fp64 kernel runs).
+// k1_fast.cu -- exact-integer fast path of the fused cost-volume + arg-best kernel (AbsoluteCost).
+//
+// When both rasters are integer valued with (max-min)*4 < 2^16 (8..14-bit imagery), every quantity
+// of best_of_search_convolution (Stereo/Correlation.cc:33-137) is an exact integer: the float
+// per-pixel cost |a-b|, the double box sums and therefore the comparison results.  The kernel below
+// evaluates the same cost volume in int32 and applies the same selection rule (strict '<', dy-major /
+// dx-minor order => first disparity wins ties; all-equal => invalid), so it is bit-identical to the
+// reference while doing ~10 issue slots per (pixel, disparity) instead of ~70 bytes of DRAM traffic.
+//
+// Decomposition (persistent CTAs of 4 warps, one CTA per SM; work item = 236-column x 32-row band):
+//   * values are pre-packed (pack kernels) as u16 (v-vmin)*4 in a per-strip "lane-transposed" layout
+//     [row][a][lane] so that a warp's j-th load is 64 contiguous bytes (conflict-free LDS.U16)
+//   * the left tile (32+ky-1 rows) and a ring of right rows are staged in shared memory with TMA bulk
+//     copies (cp.async.bulk + mbarrier); one new right row is prefetched per dy while the CTA computes
+//   * lane l owns padded columns 8l..8l+7 and 4 consecutive dx: V[8][4] vertical sliding sums live in
+//     registers (VABSDIFF accumulate: +new row, -old row)
+//   * the kx-wide horizontal sums are formed without shared memory: in-lane prefix sums + 9 warp
+//     shuffles per 8 outputs (blocked-prefix scheme), 3-input IADD3
+//   * arg-best: costs are pre-scaled by 4 so key = cost*4 + b; min over the 4 dx is 3 VIADDMNMX;
+//     the running best (cost only) sits in shared memory, the index goes to a global scratch plane
+//     on the (rare) improvements; warps cover disjoint dx subsets and are merged at the end of the band
+//   * pixels whose arg-best is disparity (0,0) are re-checked by a small kernel for the
+//     "every disparity gave the same cost => invalid" rule (Correlation.cc:121-133)
 #include "common.cuh"
 
 namespace vwb200 {
+
+static constexpr int F_TH = 32;        // output rows per band
+static constexpr int F_COLS = 256;     // padded columns per strip (32 lanes x 8)
+static constexpr int F_WARPS = 4;
+static constexpr int F_THREADS = F_WARPS * 32;
+static constexpr int F_RP = 56;        // lane slots per 'a' plane of a right row (supports sx <= 186)
+static constexpr int F_RROW = 8 * F_RP;   // u16 per right row
+static constexpr uint32_t S4_INIT = 0x7ffffffcu;
 
 // ---- min / max / integer-valuedness reduction -------------------------------------------------------
 __global__ void image_stats_kernel(ImgF img, float* __restrict__ result) {
@@ -20,7 +48,7 @@ __global__ void image_stats_kernel(ImgF img, float* __restrict__ result) {
     allint &= __shfl_xor_sync(0xffffffffu, allint, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    // float atomics on bit patterns: values are compared as floats via CAS-free min/max on ordered ints
+    // order-preserving float->int mapping so integer atomics can be used
     atomicMin(reinterpret_cast<int*>(result) + 0, mn >= 0 ? __float_as_int(mn) : (int)(0x80000000u - (unsigned)__float_as_int(mn)));
     atomicMax(reinterpret_cast<int*>(result) + 1, mx >= 0 ? __float_as_int(mx) : (int)(0x80000000u - (unsigned)__float_as_int(mx)));
     if (!allint) atomicExch(reinterpret_cast<int*>(result) + 2, 0);
@@ -47,11 +75,329 @@ int image_stats_launch(ImgF img, float* d_result3, cudaStream_t st) {
   return VWB200_OK;
 }
 
-int k1_fast_supported(int, int, int, int, int, float, float, bool) { return VWB200_ENOIMPL; }
-size_t k1_fast_workspace_bytes(int, int, int, int, int, int) { return 16; }
-int k1_fast_launch(int, ImgF, ImgF, int, int, int, int, int, int, vwb200_dispi*, ptrdiff_t, void*, size_t, cudaStream_t) {
-  set_error("k1_fast: not built");
-  return VWB200_ENOIMPL;
+// ---- geometry -----------------------------------------------------------------------------------------
+struct FastGeom {
+  int W, H, sx, sy, kx, ky;
+  int out_cols;      // output columns per strip = 256 - (kx-1)
+  int NS, NB;        // strips, bands
+  int lrows, rrows;  // padded row counts of the packed arrays
+  int ltile_rows;    // F_TH + ky - 1
+  int ring_slots;    // F_TH + ky
+};
+static FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
+  FastGeom g;
+  g.W = W; g.H = H; g.sx = sx; g.sy = sy; g.kx = kx; g.ky = ky;
+  g.out_cols = F_COLS - (kx - 1);
+  g.NS = (W + g.out_cols - 1) / g.out_cols;
+  g.NB = (H + F_TH - 1) / F_TH;
+  g.ltile_rows = F_TH + ky - 1;
+  g.ring_slots = F_TH + ky;
+  g.lrows = g.NB * F_TH + ky - 1;
+  g.rrows = g.NB * F_TH + ky - 1 + sy;
+  return g;
+}
+static size_t fast_smem_bytes(const FastGeom& g) {
+  return (size_t)F_WARPS * F_TH * F_COLS * 4 + (size_t)g.ltile_rows * F_COLS * 2 + (size_t)g.ring_slots * F_RROW * 2 + 64;
+}
+
+int k1_fast_supported(int cost, int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued) {
+  if (cost != VWB200_ABSOLUTE_DIFFERENCE) return VWB200_ENOIMPL;
+  if (!integer_valued) return VWB200_ENOIMPL;
+  if (!(vmax - vmin <= 16383.0f) || !(fabsf(vmin) < 1.0e6f) || !(fabsf(vmax) < 1.0e6f)) return VWB200_ENOIMPL;
+  if (kx < 3 || kx > 31 || ky < 1 || ky > 41) return VWB200_ENOIMPL;
+  if (sx % 4 != 0 || sx < 4 || sx > 8 * (F_RP - 32) - 10 || sy < 1) return VWB200_ENOIMPL;
+  if ((long long)sx * sy > 65536) return VWB200_ENOIMPL;
+  if ((long long)sx * sy < 64) return VWB200_ENOIMPL;      // tiny searches: the generic kernel is as good
+  FastGeom g = make_geom(256, 32, sx, sy, kx, ky);
+  if (fast_smem_bytes(g) > 227 * 1024) return VWB200_ENOIMPL;
+  return VWB200_OK;
+}
+
+size_t k1_fast_workspace_bytes(int W, int H, int sx, int sy, int kx, int ky) {
+  FastGeom g = make_geom(W, H, sx, sy, kx, ky);
+  size_t l = (size_t)g.NS * g.lrows * F_COLS * 2;
+  size_t r = (size_t)g.NS * g.rrows * F_RROW * 2;
+  size_t idx = (size_t)1024 * F_WARPS * F_TH * F_COLS * 2;    // per-CTA index planes (<= 1024 CTAs)
+  return l + r + idx + 256;
+}
+
+// ---- pack kernels: float raster -> u16 (v - vmin) * 4 in the lane-transposed strip layout ------------
+__global__ void pack_left_kernel(ImgF img, float vmin, FastGeom g, uint16_t* __restrict__ out) {
+  const int row = blockIdx.x, strip = blockIdx.y;
+  const int s0 = strip * g.out_cols;
+  uint16_t* o = out + ((size_t)strip * g.lrows + row) * F_COLS;
+  for (int c = threadIdx.x; c < F_COLS; c += blockDim.x) {      // c = strip-relative padded column (coalesced reads)
+    const int gx = s0 + c;
+    uint16_t v = 0;
+    if (row < img.h && gx < img.w) v = (uint16_t)((int)(img.p[(ptrdiff_t)row * img.pitch + gx] - vmin) * 4);
+    o[(c & 7) * 32 + (c >> 3)] = v;
+  }
+}
+__global__ void pack_right_kernel(ImgF img, float vmin, FastGeom g, uint16_t* __restrict__ out) {
+  const int row = blockIdx.x, strip = blockIdx.y;
+  const int s0 = strip * g.out_cols;
+  uint16_t* o = out + ((size_t)strip * g.rrows + row) * F_RROW;
+  for (int c = threadIdx.x; c < F_RROW; c += blockDim.x) {
+    const int gx = s0 + c;
+    uint16_t v = 0;
+    if (row < img.h && gx < img.w) v = (uint16_t)((int)(img.p[(ptrdiff_t)row * img.pitch + gx] - vmin) * 4);
+    o[(c & 7) * F_RP + (c >> 3)] = v;
+  }
+}
+
+// ---- PTX helpers: mbarrier + TMA bulk copy -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- horizontal kx-window sums of 8 per-lane columns via in-lane prefix + warp shuffles -----------------------
+// p[a] = inclusive prefix of the lane's 8 column sums.  out[r] = sum of the KX columns starting at
+// column 8*lane + r.  Static structure for a given KX (all loops unrolled).
+template <int KX>
+__device__ __forceinline__ void window_sums(const int (&p)[8], int (&out)[8]) {
+  const int T = p[7];
+  constexpr int MAXL = (KX - 1) / 8;            // most full following lanes any window needs
+  int Tn[MAXL + 1];                             // Tn[k] = total of lane l+k
+  Tn[0] = T;
+#pragma unroll
+  for (int k = 1; k <= MAXL; ++k) Tn[k] = __shfl_down_sync(0xffffffffu, T, k);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int own = 8 - r;                      // columns available in the own lane from r
+    if (KX <= own) {
+      out[r] = p[r + KX - 1] - (r ? p[r - 1] : 0);
+    } else {
+      const int rem = KX - own;                 // columns still needed from the following lanes
+      const int full = rem / 8, part = rem % 8;
+      int acc = T - (r ? p[r - 1] : 0);
+#pragma unroll
+      for (int k = 1; k <= full; ++k) acc += Tn[k];
+      if (part) acc += __shfl_down_sync(0xffffffffu, p[part - 1], full + 1);
+      out[r] = acc;
+    }
+  }
+}
+
+// ---- one pass: 4 consecutive dx (group g) x 8 columns per lane, sliding down the 32-row band -------------
+template <int KX, int J0>
+__device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, const uint16_t* __restrict__ rring,
+                                          uint32_t* __restrict__ state, uint16_t* __restrict__ idxp,
+                                          int lane, int goff, int ky, int ring_slots, int ring_base, int idx_base) {
+  int V[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) V[a][b] = 0;
+  const uint16_t* lp = ltile + lane;                     // + row*256 + a*32
+  const uint16_t* rp = rring + lane + goff;              // + slot*F_RROW + (jj&7)*F_RP + (jj>>3)
+  int slot_new = ring_base;                              // ring slot of right row (dy + t)
+  // ---- seed: first ky rows ----
+  for (int t = 0; t < ky; ++t) {
+    const uint16_t* lr = lp + t * F_COLS;
+    const uint16_t* rr = rp + slot_new * F_RROW;
+    int Lv[8], Rv[11];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) Lv[a] = lr[a * 32];
+#pragma unroll
+    for (int j = 0; j < 11; ++j) Rv[j] = rr[((J0 + j) & 7) * F_RP + ((J0 + j) >> 3)];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) V[a][b] = __sad(Lv[a], Rv[a + b], V[a][b]);
+    if (++slot_new == ring_slots) slot_new = 0;
+  }
+  int slot_old = ring_base;
+  for (int y = 0; y < F_TH; ++y) {
+    if (y > 0) {
+      const uint16_t* lrn = lp + (y + ky - 1) * F_COLS;
+      const uint16_t* rrn = rp + slot_new * F_RROW;
+      const uint16_t* lro = lp + (y - 1) * F_COLS;
+      const uint16_t* rro = rp + slot_old * F_RROW;
+      int Lv[8], Rv[11], Lo[8], Ro[11];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) { Lv[a] = lrn[a * 32]; Lo[a] = lro[a * 32]; }
+#pragma unroll
+      for (int j = 0; j < 11; ++j) {
+        Rv[j] = rrn[((J0 + j) & 7) * F_RP + ((J0 + j) >> 3)];
+        Ro[j] = rro[((J0 + j) & 7) * F_RP + ((J0 + j) >> 3)];
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) V[a][b] = __sad(Lv[a], Rv[a + b], V[a][b]) - __sad(Lo[a], Ro[a + b], 0);
+      if (++slot_new == ring_slots) slot_new = 0;
+      if (++slot_old == ring_slots) slot_old = 0;
+    }
+    // ---- horizontal window sums + min over the 4 dx (keys = cost*4 + b) ----
+    int m[8];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int p[8], o[8];
+      p[0] = V[0][b];
+#pragma unroll
+      for (int a = 1; a < 8; ++a) p[a] = p[a - 1] + V[a][b];
+      window_sums<KX>(p, o);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) m[r] = (b == 0) ? o[r] : min(o[r] + b, m[r]);
+    }
+    // ---- running best (shared memory), index plane (global) on improvement ----
+    uint32_t* srow = state + y * F_COLS + lane;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t s4 = srow[r * 32];
+      if ((uint32_t)m[r] < s4) {
+        srow[r * 32] = (uint32_t)m[r] & ~3u;
+        idxp[y * F_COLS + r * 32 + lane] = (uint16_t)(idx_base + (m[r] & 3));
+      }
+    }
+  }
+}
+
+template <int KX>
+__global__ void __launch_bounds__(F_THREADS, 1)
+k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict__ R16, FastGeom G,
+                   uint16_t* __restrict__ idx_scratch, vwb200_dispi* __restrict__ out, ptrdiff_t opitch) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint32_t* state = reinterpret_cast<uint32_t*>(smem);                                  // [4][32][8][32]
+  uint16_t* ltile = reinterpret_cast<uint16_t*>(smem + (size_t)F_WARPS * F_TH * F_COLS * 4);
+  uint16_t* rring = ltile + (size_t)G.ltile_rows * F_COLS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rring + (size_t)G.ring_slots * F_RROW);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int ngroups = G.sx / 4;
+  uint16_t* idxp_block = idx_scratch + (size_t)blockIdx.x * F_WARPS * F_TH * F_COLS;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  uint32_t ph0 = 0, ph1 = 0;
+  const uint32_t lbytes = (uint32_t)G.ltile_rows * F_COLS * 2, rrow_bytes = F_RROW * 2;
+  for (int item = blockIdx.x; item < G.NS * G.NB; item += gridDim.x) {
+    const int strip = item % G.NS, band = item / G.NS;
+    const int y0 = band * F_TH;
+    const uint16_t* lsrc = L16 + ((size_t)strip * G.lrows + y0) * F_COLS;
+    const uint16_t* rsrc = R16 + ((size_t)strip * G.rrows + y0) * F_RROW;
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&bars[0], lbytes + (uint32_t)G.ltile_rows * rrow_bytes);
+      tma_load_1d(ltile, lsrc, lbytes, &bars[0]);
+      tma_load_1d(rring, rsrc, (uint32_t)G.ltile_rows * rrow_bytes, &bars[0]);     // right rows y0 .. y0+ltile_rows-1 -> slots 0..
+    }
+    for (int k = tid; k < F_WARPS * F_TH * F_COLS; k += F_THREADS) state[k] = S4_INIT;
+    __syncthreads();
+    mbar_wait(&bars[0], ph0); ph0 ^= 1;
+    uint32_t* wstate = state + (size_t)w * F_TH * F_COLS;
+    uint16_t* widx = idxp_block + (size_t)w * F_TH * F_COLS;
+    for (int dy = 0; dy < G.sy; ++dy) {
+      const int ring_base = dy % G.ring_slots;
+      if (tid == 0 && dy + 1 < G.sy) {       // prefetch the row iteration dy+1 adds, into the slot iteration dy-1 freed
+        fence_proxy_async();
+        mbar_expect_tx(&bars[1], rrow_bytes);
+        tma_load_1d(rring + (size_t)((dy + G.ltile_rows) % G.ring_slots) * F_RROW, rsrc + (size_t)(dy + G.ltile_rows) * F_RROW, rrow_bytes, &bars[1]);
+      }
+      for (int g = w; g < ngroups; g += F_WARPS) {
+        const int idx_base = dy * G.sx + 4 * g;
+        if (g & 1) fast_pass<KX, 4>(ltile, rring, wstate, widx, lane, g >> 1, G.ky, G.ring_slots, ring_base, idx_base);
+        else       fast_pass<KX, 0>(ltile, rring, wstate, widx, lane, g >> 1, G.ky, G.ring_slots, ring_base, idx_base);
+      }
+      if (dy + 1 < G.sy) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
+      __syncthreads();
+    }
+    // ---- merge the 4 warps' private bests and write {dx, dy, valid} ----
+    const int nw = ngroups < F_WARPS ? ngroups : F_WARPS;
+    const int s0 = strip * G.out_cols;
+    for (int pix = tid; pix < F_TH * G.out_cols; pix += F_THREADS) {
+      const int x = pix % G.out_cols, y = pix / G.out_cols;
+      const int gx = s0 + x, gy = y0 + y;
+      if (gx >= G.W || gy >= G.H) continue;
+      const int off = y * F_COLS + (x & 7) * 32 + (x >> 3);
+      uint32_t best = state[off];
+      int bidx = idxp_block[off];
+      for (int ww = 1; ww < nw; ++ww) {
+        const uint32_t c = state[(size_t)ww * F_TH * F_COLS + off];
+        const int i = idxp_block[(size_t)ww * F_TH * F_COLS + off];
+        if (c < best || (c == best && i < bidx)) { best = c; bidx = i; }
+      }
+      vwb200_dispi o;
+      o.dx = bidx % G.sx; o.dy = bidx / G.sx; o.valid = 1;
+      out[(ptrdiff_t)gy * opitch + gx] = o;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- "every disparity gave the same cost" fix-up for pixels whose arg-best is (0,0) --------------------------
+__global__ void k1_fast_allequal_fixup(ImgF L, ImgF R, int W, int H, int sx, int sy, int kx, int ky,
+                                       vwb200_dispi* __restrict__ out, ptrdiff_t opitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  vwb200_dispi* o = out + (ptrdiff_t)y * opitch + x;
+  if (o->dx != 0 || o->dy != 0) return;
+  // arg-best (0,0): valid iff some disparity has a different (necessarily larger) cost
+  long long c0 = 0;   // integer-valued inputs: exact integer arithmetic
+  for (int j = 0; j < ky; ++j)
+    for (int i = 0; i < kx; ++i) c0 += abs((int)L.p[(ptrdiff_t)(y + j) * L.pitch + x + i] - (int)R.p[(ptrdiff_t)(y + j) * R.pitch + x + i]);
+  for (int dy = 0; dy < sy; ++dy)
+    for (int dx = 0; dx < sx; ++dx) {
+      if (dx == 0 && dy == 0) continue;
+      long long c = 0;
+      for (int j = 0; j < ky; ++j)
+        for (int i = 0; i < kx; ++i) c += abs((int)L.p[(ptrdiff_t)(y + j) * L.pitch + x + i] - (int)R.p[(ptrdiff_t)(y + j + dy) * R.pitch + x + i + dx]);
+      if (c != c0) return;      // not all equal -> stays valid
+    }
+  o->valid = 0;
+}
+
+int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin,
+                   vwb200_dispi* out, ptrdiff_t opitch, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  (void)cost; (void)workspace_bytes;
+  FastGeom g = make_geom(W, H, sx, sy, kx, ky);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  uint16_t* L16 = reinterpret_cast<uint16_t*>(ws);
+  uint16_t* R16 = L16 + (size_t)g.NS * g.lrows * F_COLS;
+  uint16_t* idx = R16 + (size_t)g.NS * g.rrows * F_RROW;
+  {
+    dim3 gl(g.lrows, g.NS), gr(g.rrows, g.NS);
+    pack_left_kernel<<<gl, 256, 0, st>>>(left, vmin, g, L16);
+    VWB_LAUNCH_CHECK();
+    pack_right_kernel<<<gr, 256, 0, st>>>(right, vmin, g, R16);
+    VWB_LAUNCH_CHECK();
+  }
+  int dev = 0, nsm = 148;
+  VWB_CUDA(cudaGetDevice(&dev));
+  VWB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int items = g.NS * g.NB;
+  const int grid = items < nsm ? items : nsm;
+  const size_t smem = fast_smem_bytes(g);
+  void (*kern)(const uint16_t*, const uint16_t*, FastGeom, uint16_t*, vwb200_dispi*, ptrdiff_t) = nullptr;
+  switch (kx) {
+#define KCASE(K) case K: kern = k1_fast_abs_kernel<K>; break;
+    KCASE(3) KCASE(5) KCASE(7) KCASE(9) KCASE(11) KCASE(13) KCASE(15) KCASE(17) KCASE(19) KCASE(21) KCASE(23) KCASE(25)
+    KCASE(27) KCASE(29) KCASE(31)
+#undef KCASE
+    default: set_error("k1_fast: unsupported kernel width %d", kx); return VWB200_ENOIMPL;
+  }
+  VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, F_THREADS, smem, st>>>(L16, R16, g, idx, out, opitch);
+  VWB_LAUNCH_CHECK();
+  dim3 b(32, 8), gg((W + 31) / 32, (H + 7) / 8);
+  k1_fast_allequal_fixup<<<gg, b, 0, st>>>(left, right, W, H, sx, sy, kx, ky, out, opitch);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
 }
 
 }  // namespace vwb200
