@@ -70,8 +70,9 @@ int vwb200_calc_disparity(int cost_type,
                           int on_device, void* stream);
 
 /* Statistics of the last vwb200_calc_disparity on this thread: which kernel path ran
- * (0 = exact-integer fast path, 1 = general fp64 path), kernel launches issued. */
-typedef struct { int32_t path; int32_t launches; int32_t flagged_pixels; int32_t reserved; } vwb200_k1_stats;
+ * (0 = exact-integer fast path, 1 = general fp64 path), kernel launches issued, and the device time of
+ * the dominant (fused cost-volume + arg-best) kernel measured with CUDA events on its stream. */
+typedef struct { int32_t path; int32_t launches; float kernel_ms; int32_t reserved; } vwb200_k1_stats;
 int vwb200_last_k1_stats(vwb200_k1_stats* out);
 
 /* ---------------------------------------------------------------------------------------------

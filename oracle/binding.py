@@ -76,6 +76,19 @@ def calc_disparity(cost, left, right, search, kernel):
     return out
 
 
+def calc_disparity_tiled(cost, left, right, search, kernel, tile=128, nthreads=0):
+    l, r = _f32(left), _f32(right)
+    sx, sy = search
+    kx, ky = kernel
+    H, W = l.shape[0] - ky + 1, l.shape[1] - kx + 1
+    out = np.empty((H, W, 3), np.int32)
+    rc = lib().vwo_calc_disparity_tiled(cost, _p(l), l.shape[1], l.shape[0], l.shape[1],
+                                        _p(r), r.shape[1], r.shape[0], r.shape[1], sx, sy, kx, ky, tile, nthreads, _p(out))
+    if rc:
+        raise ValueError(f"vwo_calc_disparity_tiled rc={rc}")
+    return out
+
+
 def cost_pixel(cost, a, b):
     f = lib().vwo_cost_pixel
     f.restype = C.c_double

@@ -828,6 +828,35 @@ int vwo_pyramid_correlate_rasterize(const vwo_corr_params* p, const vwo_corr_inp
   return rc;
 }
 
+int vwo_max_threads(void);
+/* Tile-parallel calc_disparity for the CPU baseline: the reference parallelises over independent
+ * output tiles on a thread pool (Image/ImageIO.h:289-311); within a tile best_of_search_convolution is
+ * single threaded.  Rasters are shared, each tile works on its own sub-rectangles via pitches. */
+int vwo_calc_disparity_tiled(int cost, const float* left, int lw, int lh, int lpitch,
+                             const float* right, int rw, int rh, int rpitch,
+                             int sx, int sy, int kx, int ky, int tile, int nthreads, vwo_disp_t* out) {
+  const int W = lw - kx + 1, H = lh - ky + 1;
+  if (W <= 0 || H <= 0 || rw < lw + sx - 1 || rh < lh + sy - 1) return -1;
+  const int tx = (W + tile - 1) / tile, ty = (H + tile - 1) / tile;
+  int err = 0;
+  if (nthreads <= 0) nthreads = vwo_max_threads();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+#endif
+  for (int t = 0; t < tx * ty; ++t) {
+    const int x0 = (t % tx) * tile, y0 = (t / tx) * tile;
+    const int tw = x0 + tile < W ? tile : W - x0, th = y0 + tile < H ? tile : H - y0;
+    vwo_disp_t* tmp = (vwo_disp_t*)malloc((size_t)tw * th * sizeof(vwo_disp_t));
+    int rc = vwo_calc_disparity(cost, left + (size_t)y0 * lpitch + x0, tw + kx - 1, th + ky - 1, lpitch,
+                                right + (size_t)y0 * rpitch + x0, tw + kx - 1 + sx - 1, th + ky - 1 + sy - 1, rpitch,
+                                sx, sy, kx, ky, tmp);
+    if (rc) err = rc;
+    else for (int y = 0; y < th; ++y) memcpy(out + (size_t)(y0 + y) * W + x0, tmp + (size_t)y * tw, (size_t)tw * sizeof(vwo_disp_t));
+    free(tmp);
+  }
+  return err;
+}
+
 int vwo_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -130,6 +130,10 @@ int vwo_num_levels(const vwo_corr_params* p, int bw, int bh);
 int vwo_pyramid_correlate_tiled(const vwo_corr_params* p, const vwo_corr_inputs* in,
                                 int tile, int nthreads, float* dest /* cols*rows*3 */);
 int vwo_max_threads(void);
+/* calc_disparity over independent tile x tile output tiles on nthreads OpenMP threads (baseline timing) */
+int vwo_calc_disparity_tiled(int cost, const float* left, int lw, int lh, int lpitch,
+                             const float* right, int rw, int rh, int rpitch,
+                             int sx, int sy, int kx, int ky, int tile, int nthreads, vwo_disp_t* out);
 
 #ifdef __cplusplus
 }

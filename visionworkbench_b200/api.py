@@ -70,7 +70,7 @@ class CorrParams(C.Structure):
 
 
 class K1Stats(C.Structure):
-    _fields_ = [("path", C.c_int32), ("launches", C.c_int32), ("flagged_pixels", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("path", C.c_int32), ("launches", C.c_int32), ("kernel_ms", C.c_float), ("reserved", C.c_int32)]
 
 
 def lib():
@@ -122,7 +122,7 @@ def kernel_launches():
 def last_k1_stats():
     s = K1Stats()
     lib().vwb200_last_k1_stats(C.byref(s))
-    return {"path": "exact-int" if s.path == 0 else "general-fp64", "launches": s.launches}
+    return {"path": "exact-int" if s.path == 0 else "general-fp64", "launches": s.launches, "kernel_ms": s.kernel_ms}
 
 
 def _is_torch(x):

@@ -62,8 +62,10 @@ struct Tile { int zone; int tx, ty; int pad; };
 // cost: VWB200_* cost type.  inv_l / inv_r: for NCC, 1/boxsum(v^2) maps whose (0,0) sits at window
 // origin (l_ox,l_oy) / (r_ox,r_oy) in image coordinates, pitch in elements.
 struct NccMaps { const double* inv_l; int l_ox, l_oy, l_w, l_h; const double* inv_r; int r_ox, r_oy, r_w, r_h; };
+// optional event pair recorded around the dominant kernel (kernel-only timing for the roofline)
+struct KEvents { cudaEvent_t e0 = nullptr, e1 = nullptr; };
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
-                      int kx, int ky, NccMaps ncc, vwb200_dispi* out, cudaStream_t st);
+                      int kx, int ky, NccMaps ncc, vwb200_dispi* out, cudaStream_t st, const KEvents* ev = nullptr);
 int k1_generic_tile_w(int kx);
 int k1_generic_tile_h(int ky);
 // 1/boxsum(v*v) over window origins [ox0,ox0+ow) x [oy0,oy0+oh) with clamped (constant edge) reads.
@@ -76,7 +78,8 @@ int k1_nan_fixup_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, in
 // Returns VWB200_ENOIMPL if the configuration is outside what the fast path handles.
 int k1_fast_supported(int cost, int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued);
 int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin,
-                   vwb200_dispi* out, ptrdiff_t opitch, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                   vwb200_dispi* out, ptrdiff_t opitch, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                   const KEvents* ev = nullptr);
 size_t k1_fast_workspace_bytes(int W, int H, int sx, int sy, int kx, int ky);
 // min / max / integer-valuedness of an image (device reduction); result[0]=min,[1]=max,[2]=all-integers(1/0)
 int image_stats_launch(ImgF img, float* d_result3, cudaStream_t st);

@@ -18,7 +18,7 @@ namespace vwb200 {
 
 std::atomic<long long> g_launches{0};
 static thread_local char t_error[512] = "";
-static thread_local vwb200_k1_stats t_k1_stats = {0, 0, 0, 0};
+static thread_local vwb200_k1_stats t_k1_stats = {0, 0, 0.0f, 0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -83,7 +83,7 @@ static void make_tiles(const std::vector<Zone>& zones, int tile, std::vector<Til
 // ---------------------------------------------------------------------------------------------------
 static int run_k1_zones(int cost, ImgF left, ImgF right, const std::vector<Zone>& zones, int kx, int ky,
                         vwb200_dispi* d_out, Arena& ar, cudaStream_t st, const Zone** d_zones_out = nullptr,
-                        const Tile** d_tiles_out = nullptr, int* ntiles_out = nullptr) {
+                        const Tile** d_tiles_out = nullptr, int* ntiles_out = nullptr, const KEvents* ev = nullptr) {
   if (zones.empty()) { if (ntiles_out) *ntiles_out = 0; return VWB200_OK; }
   std::vector<Tile> tiles;
   make_tiles(zones, k1_generic_tile_w(kx), tiles);
@@ -107,7 +107,7 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, const std::vector<Zone>
     VWB_TRY(box_sq_inv_launch(right, kx, ky, rx0, ry0, rx1 - rx0, ry1 - ry0, ir, st));
     ncc = NccMaps{il, lx0, ly0, lx1 - lx0, ly1 - ly0, ir, rx0, ry0, rx1 - rx0, ry1 - ry0};
   }
-  VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles, (int)tiles.size(), kx, ky, ncc, d_out, st));
+  VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles, (int)tiles.size(), kx, ky, ncc, d_out, st, ev));
   if (cost == VWB200_CROSS_CORRELATION)
     VWB_TRY(k1_nan_fixup_launch(cost, left, right, d_zones, (int)zones.size(), kx, ky, ncc, d_out, st));
   if (d_zones_out) *d_zones_out = d_zones;
@@ -451,6 +451,9 @@ int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrd
   StreamGuard sg; VWB_TRY(sg.init(stream));
   cudaStream_t st = sg.st;
   const long long launches0 = g_launches.load();
+  KEvents kev;
+  VWB_CUDA(cudaEventCreate(&kev.e0));
+  VWB_CUDA(cudaEventCreate(&kev.e1));
   {
     Arena ar(st);
     const int W = lw - kx + 1, H = lh - ky + 1;
@@ -475,7 +478,7 @@ int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrd
         const size_t wb = k1_fast_workspace_bytes(W, H, sx, sy, kx, ky);
         unsigned char* ws;
         VWB_TRY(ar.alloc(&ws, wb));
-        VWB_TRY(k1_fast_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, vmin, dout, dop, ws, wb, st));
+        VWB_TRY(k1_fast_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, vmin, dout, dop, ws, wb, st, &kev));
         path = 0;
       }
     }
@@ -483,7 +486,7 @@ int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrd
       std::vector<Zone> zones(1);
       Zone& z = zones[0];
       z.obase = 0; z.opitch = (int)dop; z.w = W; z.h = H; z.lx = 0; z.ly = 0; z.rx = 0; z.ry = 0; z.sx = sx; z.sy = sy; z.addx = 0; z.addy = 0;
-      VWB_TRY(run_k1_zones(cost_type, Li, Ri, zones, kx, ky, dout, ar, st));
+      VWB_TRY(run_k1_zones(cost_type, Li, Ri, zones, kx, ky, dout, ar, st, nullptr, nullptr, nullptr, &kev));
     }
     if (!on_device)
       VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch * sizeof(vwb200_dispi), dout, (size_t)W * sizeof(vwb200_dispi),
@@ -492,6 +495,9 @@ int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrd
   }
   VWB_CUDA(cudaStreamSynchronize(st));
   t_k1_stats.launches = (int)(g_launches.load() - launches0);
+  t_k1_stats.kernel_ms = 0.0f;
+  cudaEventElapsedTime(&t_k1_stats.kernel_ms, kev.e0, kev.e1);
+  cudaEventDestroy(kev.e0); cudaEventDestroy(kev.e1);
   return VWB200_OK;
 }
 

@@ -363,7 +363,8 @@ __global__ void k1_fast_allequal_fixup(ImgF L, ImgF R, int W, int H, int sx, int
 }
 
 int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin,
-                   vwb200_dispi* out, ptrdiff_t opitch, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                   vwb200_dispi* out, ptrdiff_t opitch, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                   const KEvents* ev) {
   (void)cost; (void)workspace_bytes;
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
@@ -392,8 +393,10 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
     default: set_error("k1_fast: unsupported kernel width %d", kx); return VWB200_ENOIMPL;
   }
   VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ev && ev->e0) cudaEventRecord(ev->e0, st);
   kern<<<grid, F_THREADS, smem, st>>>(L16, R16, g, idx, out, opitch);
   VWB_LAUNCH_CHECK();
+  if (ev && ev->e1) cudaEventRecord(ev->e1, st);
   dim3 b(32, 8), gg((W + 31) / 32, (H + 7) / 8);
   k1_fast_allequal_fixup<<<gg, b, 0, st>>>(left, right, W, H, sx, sy, kx, ky, out, opitch);
   VWB_LAUNCH_CHECK();

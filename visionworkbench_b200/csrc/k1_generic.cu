@@ -148,7 +148,7 @@ static size_t k1g_smem_bytes(int kx) {
 }
 
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
-                      int kx, int ky, NccMaps ncc, vwb200_dispi* out, cudaStream_t st) {
+                      int kx, int ky, NccMaps ncc, vwb200_dispi* out, cudaStream_t st, const KEvents* ev) {
   if (ntiles <= 0) return VWB200_OK;
   if (kx > 129 || ky > 129) { set_error("kernel size %dx%d exceeds the supported 129", kx, ky); return VWB200_ENOIMPL; }
   const size_t smem = k1g_smem_bytes(kx);
@@ -159,8 +159,10 @@ int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, cons
     default:                        kern = k1_generic_kernel<VWB200_ABSOLUTE_DIFFERENCE>; break;
   }
   VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ev && ev->e0) cudaEventRecord(ev->e0, st);
   kern<<<ntiles, K1G_THREADS, smem, st>>>(left, right, d_zones, d_tiles, kx, ky, ncc, out);
   VWB_LAUNCH_CHECK();
+  if (ev && ev->e1) cudaEventRecord(ev->e1, st);
   return VWB200_OK;
 }
 
