@@ -36,6 +36,18 @@ int ensure_device() {
     cudaGetLastError();
     return VWB200_ENODEVICE;
   }
+  // keep stream-ordered allocations cached in the pool between calls (the default threshold of 0
+  // returns the memory to the driver at every synchronisation: ~100 ms per call at 8K x 8K)
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev < 64 && !(configured.load() & (1ull << dev))) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    configured.fetch_or(1ull << dev);
+  }
   return VWB200_OK;
 }
 

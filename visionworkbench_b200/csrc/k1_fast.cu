@@ -27,7 +27,10 @@ namespace vwb200 {
 
 static constexpr int F_TH = 32;        // output rows per band
 static constexpr int F_COLS = 256;     // padded columns per strip (32 lanes x 8)
-static constexpr int F_WARPS = 4;
+static constexpr int F_WARPS = 8;       // 4 dx subsets x 2 row halves (2 warps per SM sub-partition)
+static constexpr int F_SUBSETS = 4;
+static constexpr int F_HALVES = F_WARPS / F_SUBSETS;
+static constexpr int F_RH = F_TH / F_HALVES;      // output rows per warp
 static constexpr int F_THREADS = F_WARPS * 32;
 static constexpr int F_RP = 56;        // lane slots per 'a' plane of a right row (supports sx <= 186)
 static constexpr int F_RROW = 8 * F_RP;   // u16 per right row
@@ -97,7 +100,7 @@ static FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
   return g;
 }
 static size_t fast_smem_bytes(const FastGeom& g) {
-  return (size_t)F_WARPS * F_TH * F_COLS * 4 + (size_t)g.ltile_rows * F_COLS * 2 + (size_t)g.ring_slots * F_RROW * 2 + 64;
+  return (size_t)F_SUBSETS * F_TH * F_COLS * 4 + (size_t)g.ltile_rows * F_COLS * 2 + (size_t)g.ring_slots * F_RROW * 2 + 64;
 }
 
 int k1_fast_supported(int cost, int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued) {
@@ -117,7 +120,7 @@ size_t k1_fast_workspace_bytes(int W, int H, int sx, int sy, int kx, int ky) {
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
   size_t l = (size_t)g.NS * g.lrows * F_COLS * 2;
   size_t r = (size_t)g.NS * g.rrows * F_RROW * 2;
-  size_t idx = (size_t)1024 * F_WARPS * F_TH * F_COLS * 2;    // per-CTA index planes (<= 1024 CTAs)
+  size_t idx = (size_t)1024 * F_SUBSETS * F_TH * F_COLS * 2;    // per-CTA index planes (<= 1024 CTAs)
   return l + r + idx + 256;
 }
 
@@ -174,23 +177,25 @@ template <int KX>
 __device__ __forceinline__ void window_sums(const int (&p)[8], int (&out)[8]) {
   const int T = p[7];
   constexpr int MAXL = (KX - 1) / 8;            // most full following lanes any window needs
-  int Tn[MAXL + 1];                             // Tn[k] = total of lane l+k
-  Tn[0] = T;
+  // W[k] = T_l + T_{l+1} + ... + T_{l+k}
+  int W[MAXL + 1];
+  W[0] = T;
 #pragma unroll
-  for (int k = 1; k <= MAXL; ++k) Tn[k] = __shfl_down_sync(0xffffffffu, T, k);
+  for (int k = 1; k <= MAXL; ++k) W[k] = W[k - 1] + __shfl_down_sync(0xffffffffu, T, k);
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int own = 8 - r;                      // columns available in the own lane from r
     if (KX <= own) {
-      out[r] = p[r + KX - 1] - (r ? p[r - 1] : 0);
+      out[r] = r ? p[r + KX - 1] - p[r - 1] : p[KX - 1];
     } else {
       const int rem = KX - own;                 // columns still needed from the following lanes
       const int full = rem / 8, part = rem % 8;
-      int acc = T - (r ? p[r - 1] : 0);
-#pragma unroll
-      for (int k = 1; k <= full; ++k) acc += Tn[k];
-      if (part) acc += __shfl_down_sync(0xffffffffu, p[part - 1], full + 1);
-      out[r] = acc;
+      if (part) {
+        const int q = __shfl_down_sync(0xffffffffu, p[part - 1], full + 1);
+        out[r] = r ? (W[full] + q) - p[r - 1] : W[full] + q;      // one IADD3
+      } else {
+        out[r] = r ? W[full] - p[r - 1] : W[full];
+      }
     }
   }
 }
@@ -199,13 +204,13 @@ __device__ __forceinline__ void window_sums(const int (&p)[8], int (&out)[8]) {
 template <int KX, int J0>
 __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, const uint16_t* __restrict__ rring,
                                           uint32_t* __restrict__ state, uint16_t* __restrict__ idxp,
-                                          int lane, int goff, int ky, int ring_slots, int ring_base, int idx_base) {
+                                          int lane, int goff, int ky, int ring_slots, int ring_base, int idx_base, int row0) {
   int V[8][4];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) V[a][b] = 0;
-  const uint16_t* lp = ltile + lane;                     // + row*256 + a*32
+  const uint16_t* lp = ltile + row0 * F_COLS + lane;     // + row*256 + a*32
   const uint16_t* rp = rring + lane + goff;              // + slot*F_RROW + (jj&7)*F_RP + (jj>>3)
   int slot_new = ring_base;                              // ring slot of right row (dy + t)
   // ---- seed: first ky rows ----
@@ -224,7 +229,7 @@ __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, co
     if (++slot_new == ring_slots) slot_new = 0;
   }
   int slot_old = ring_base;
-  for (int y = 0; y < F_TH; ++y) {
+  for (int y = 0; y < F_RH; ++y) {
     if (y > 0) {
       const uint16_t* lrn = lp + (y + ky - 1) * F_COLS;
       const uint16_t* rrn = rp + slot_new * F_RROW;
@@ -259,12 +264,17 @@ __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, co
     }
     // ---- running best (shared memory), index plane (global) on improvement ----
     uint32_t* srow = state + y * F_COLS + lane;
+    uint32_t s4[8];
+    bool improved = false;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const uint32_t s4 = srow[r * 32];
-      if ((uint32_t)m[r] < s4) {
-        srow[r * 32] = (uint32_t)m[r] & ~3u;
-        idxp[y * F_COLS + r * 32 + lane] = (uint16_t)(idx_base + (m[r] & 3));
+    for (int r = 0; r < 8; ++r) { s4[r] = srow[r * 32]; improved |= ((uint32_t)m[r] < s4[r]); }
+    if (improved) {            // rare once the search has seen the neighbourhood of the true match
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if ((uint32_t)m[r] < s4[r]) {
+          srow[r * 32] = (uint32_t)m[r] & ~3u;
+          idxp[y * F_COLS + r * 32 + lane] = (uint16_t)(idx_base + (m[r] & 3));
+        }
       }
     }
   }
@@ -280,8 +290,9 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
   uint16_t* rring = ltile + (size_t)G.ltile_rows * F_COLS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(rring + (size_t)G.ring_slots * F_RROW);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int sub = w & (F_SUBSETS - 1), half = w / F_SUBSETS, row0 = half * F_RH;
   const int ngroups = G.sx / 4;
-  uint16_t* idxp_block = idx_scratch + (size_t)blockIdx.x * F_WARPS * F_TH * F_COLS;
+  uint16_t* idxp_block = idx_scratch + (size_t)blockIdx.x * F_SUBSETS * F_TH * F_COLS;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
   uint32_t ph0 = 0, ph1 = 0;
@@ -297,28 +308,28 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
       tma_load_1d(ltile, lsrc, lbytes, &bars[0]);
       tma_load_1d(rring, rsrc, (uint32_t)G.ltile_rows * rrow_bytes, &bars[0]);     // right rows y0 .. y0+ltile_rows-1 -> slots 0..
     }
-    for (int k = tid; k < F_WARPS * F_TH * F_COLS; k += F_THREADS) state[k] = S4_INIT;
+    for (int k = tid; k < F_SUBSETS * F_TH * F_COLS; k += F_THREADS) state[k] = S4_INIT;
     __syncthreads();
     mbar_wait(&bars[0], ph0); ph0 ^= 1;
-    uint32_t* wstate = state + (size_t)w * F_TH * F_COLS;
-    uint16_t* widx = idxp_block + (size_t)w * F_TH * F_COLS;
+    uint32_t* wstate = state + ((size_t)sub * F_TH + row0) * F_COLS;       // this warp's rows of its subset plane
+    uint16_t* widx = idxp_block + ((size_t)sub * F_TH + row0) * F_COLS;
     for (int dy = 0; dy < G.sy; ++dy) {
-      const int ring_base = dy % G.ring_slots;
+      const int ring_base = (dy + row0) % G.ring_slots;
       if (tid == 0 && dy + 1 < G.sy) {       // prefetch the row iteration dy+1 adds, into the slot iteration dy-1 freed
         fence_proxy_async();
         mbar_expect_tx(&bars[1], rrow_bytes);
         tma_load_1d(rring + (size_t)((dy + G.ltile_rows) % G.ring_slots) * F_RROW, rsrc + (size_t)(dy + G.ltile_rows) * F_RROW, rrow_bytes, &bars[1]);
       }
-      for (int g = w; g < ngroups; g += F_WARPS) {
+      for (int g = sub; g < ngroups; g += F_SUBSETS) {
         const int idx_base = dy * G.sx + 4 * g;
-        if (g & 1) fast_pass<KX, 4>(ltile, rring, wstate, widx, lane, g >> 1, G.ky, G.ring_slots, ring_base, idx_base);
-        else       fast_pass<KX, 0>(ltile, rring, wstate, widx, lane, g >> 1, G.ky, G.ring_slots, ring_base, idx_base);
+        if (g & 1) fast_pass<KX, 4>(ltile, rring, wstate, widx, lane, g >> 1, G.ky, G.ring_slots, ring_base, idx_base, row0);
+        else       fast_pass<KX, 0>(ltile, rring, wstate, widx, lane, g >> 1, G.ky, G.ring_slots, ring_base, idx_base, row0);
       }
       if (dy + 1 < G.sy) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
       __syncthreads();
     }
     // ---- merge the 4 warps' private bests and write {dx, dy, valid} ----
-    const int nw = ngroups < F_WARPS ? ngroups : F_WARPS;
+    const int nw = ngroups < F_SUBSETS ? ngroups : F_SUBSETS;
     const int s0 = strip * G.out_cols;
     for (int pix = tid; pix < F_TH * G.out_cols; pix += F_THREADS) {
       const int x = pix % G.out_cols, y = pix / G.out_cols;
