@@ -286,7 +286,7 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
                    uint16_t* __restrict__ idx_scratch, vwb200_dispi* __restrict__ out, ptrdiff_t opitch) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint32_t* state = reinterpret_cast<uint32_t*>(smem);                                  // [4][32][8][32]
-  uint16_t* ltile = reinterpret_cast<uint16_t*>(smem + (size_t)F_WARPS * F_TH * F_COLS * 4);
+  uint16_t* ltile = reinterpret_cast<uint16_t*>(smem + (size_t)F_SUBSETS * F_TH * F_COLS * 4);
   uint16_t* rring = ltile + (size_t)G.ltile_rows * F_COLS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(rring + (size_t)G.ring_slots * F_RROW);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
