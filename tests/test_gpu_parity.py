@@ -225,7 +225,7 @@ def test_device_tensor_path(vwb, oracle):
 
 
 @pytest.mark.parametrize("shape", [((300, 70), (16, 8), (21, 21)), ((500, 40), (32, 4), (7, 7)), ((237, 33), (64, 3), (15, 15)),
-                                   ((64, 64), (8, 8), (3, 5)), ((260, 100), (128, 2), (21, 21)), ((473, 65), (12, 11), (31, 9))])
+                                   ((64, 64), (8, 8), (3, 5)), ((260, 100), (128, 2), (21, 21)), ((473, 65), (24, 11), (31, 9))])
 def test_calc_disparity_exact_int_fast_path(vwb, oracle, shape):
     """The exact-integer TMA/shuffle kernel (k1_fast) must be bit-identical to the oracle: strips (W > 236),
     bands (H > 32), ragged edges, ties (first disparity in raster order wins)."""

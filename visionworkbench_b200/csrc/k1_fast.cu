@@ -1,6 +1,6 @@
 // k1_fast.cu -- exact-integer fast path of the fused cost-volume + arg-best kernel (AbsoluteCost).
 //
-// When both rasters are integer valued with (max-min)*4 < 2^16 (8..14-bit imagery), every quantity
+// When both rasters are integer valued with (max-min)*8 < 2^16 (8..13-bit imagery), every quantity
 // of best_of_search_convolution (Stereo/Correlation.cc:33-137) is an exact integer: the float
 // per-pixel cost |a-b|, the double box sums and therefore the comparison results.  The kernel below
 // evaluates the same cost volume in int32 and applies the same selection rule (strict '<', dy-major /
@@ -8,15 +8,15 @@
 // reference while doing ~10 issue slots per (pixel, disparity) instead of ~70 bytes of DRAM traffic.
 //
 // Decomposition (persistent CTAs of 4 warps, one CTA per SM; work item = 236-column x 32-row band):
-//   * values are pre-packed (pack kernels) as u16 (v-vmin)*4 in a per-strip "lane-transposed" layout
-//     [row][a][lane] so that a warp's j-th load is 64 contiguous bytes (conflict-free LDS.U16)
+//   * values are pre-packed (pack kernels) as u16 (v-vmin)*8, one contiguous row per strip, so that a
+//     lane fetches its 8 left / 16 right columns with conflict-free 16-byte LDS.128 loads
 //   * the left tile (32+ky-1 rows) and a ring of right rows are staged in shared memory with TMA bulk
 //     copies (cp.async.bulk + mbarrier); one new right row is prefetched per dy while the CTA computes
-//   * lane l owns padded columns 8l..8l+7 and 4 consecutive dx: V[8][4] vertical sliding sums live in
+//   * lane l owns padded columns 8l..8l+7 and 8 consecutive dx: V[8][8] vertical sliding sums live in
 //     registers (VABSDIFF accumulate: +new row, -old row)
 //   * the kx-wide horizontal sums are formed without shared memory: in-lane prefix sums + 9 warp
 //     shuffles per 8 outputs (blocked-prefix scheme), 3-input IADD3
-//   * arg-best: costs are pre-scaled by 4 so key = cost*4 + b; min over the 4 dx is 3 VIADDMNMX;
+//   * arg-best: costs are pre-scaled by 8 so key = cost*8 + b; min over the 8 dx is 7 VIADDMNMX;
 //     the running best (cost only) sits in shared memory, the index goes to a global scratch plane
 //     on the (rare) improvements; warps cover disjoint dx subsets and are merged at the end of the band
 //   * pixels whose arg-best is disparity (0,0) are re-checked by a small kernel for the
@@ -32,9 +32,8 @@ static constexpr int F_SUBSETS = 4;
 static constexpr int F_HALVES = F_WARPS / F_SUBSETS;
 static constexpr int F_RH = F_TH / F_HALVES;      // output rows per warp
 static constexpr int F_THREADS = F_WARPS * 32;
-static constexpr int F_RP = 56;        // lane slots per 'a' plane of a right row (supports sx <= 186)
-static constexpr int F_RROW = 8 * F_RP;   // u16 per right row
-static constexpr uint32_t S4_INIT = 0x7ffffffcu;
+static constexpr int F_B = 8;          // consecutive dx per thread (one "octet"); keys are cost*8 + b
+static constexpr uint32_t S_INIT = 0x7ffffff8u;
 
 // ---- min / max / integer-valuedness reduction -------------------------------------------------------
 __global__ void image_stats_kernel(ImgF img, float* __restrict__ result) {
@@ -86,6 +85,7 @@ struct FastGeom {
   int lrows, rrows;  // padded row counts of the packed arrays
   int ltile_rows;    // F_TH + ky - 1
   int ring_slots;    // F_TH + ky
+  int rw;            // u16 per packed right row = 256 + sx (multiple of 8)
 };
 static FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
   FastGeom g;
@@ -97,18 +97,19 @@ static FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
   g.ring_slots = F_TH + ky;
   g.lrows = g.NB * F_TH + ky - 1;
   g.rrows = g.NB * F_TH + ky - 1 + sy;
+  g.rw = ((F_COLS + sx + 7) / 8) * 8;
   return g;
 }
 static size_t fast_smem_bytes(const FastGeom& g) {
-  return (size_t)F_SUBSETS * F_TH * F_COLS * 4 + (size_t)g.ltile_rows * F_COLS * 2 + (size_t)g.ring_slots * F_RROW * 2 + 64;
+  return (size_t)F_SUBSETS * F_TH * F_COLS * 4 + (size_t)g.ltile_rows * F_COLS * 2 + (size_t)g.ring_slots * g.rw * 2 + 64;
 }
 
 int k1_fast_supported(int cost, int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued) {
   if (cost != VWB200_ABSOLUTE_DIFFERENCE) return VWB200_ENOIMPL;
   if (!integer_valued) return VWB200_ENOIMPL;
-  if (!(vmax - vmin <= 16383.0f) || !(fabsf(vmin) < 1.0e6f) || !(fabsf(vmax) < 1.0e6f)) return VWB200_ENOIMPL;
+  if (!(vmax - vmin <= 8191.0f) || !(fabsf(vmin) < 1.0e6f) || !(fabsf(vmax) < 1.0e6f)) return VWB200_ENOIMPL;
   if (kx < 3 || kx > 31 || ky < 1 || ky > 41) return VWB200_ENOIMPL;
-  if (sx % 4 != 0 || sx < 4 || sx > 8 * (F_RP - 32) - 10 || sy < 1) return VWB200_ENOIMPL;
+  if (sx % F_B != 0 || sx < F_B || sx > 512 || sy < 1) return VWB200_ENOIMPL;
   if ((long long)sx * sy > 65536) return VWB200_ENOIMPL;
   if ((long long)sx * sy < 64) return VWB200_ENOIMPL;      // tiny searches: the generic kernel is as good
   FastGeom g = make_geom(256, 32, sx, sy, kx, ky);
@@ -119,7 +120,7 @@ int k1_fast_supported(int cost, int kx, int ky, int sx, int sy, float vmin, floa
 size_t k1_fast_workspace_bytes(int W, int H, int sx, int sy, int kx, int ky) {
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
   size_t l = (size_t)g.NS * g.lrows * F_COLS * 2;
-  size_t r = (size_t)g.NS * g.rrows * F_RROW * 2;
+  size_t r = (size_t)g.NS * g.rrows * g.rw * 2;
   size_t idx = (size_t)1024 * F_SUBSETS * F_TH * F_COLS * 2;    // per-CTA index planes (<= 1024 CTAs)
   return l + r + idx + 256;
 }
@@ -132,19 +133,19 @@ __global__ void pack_left_kernel(ImgF img, float vmin, FastGeom g, uint16_t* __r
   for (int c = threadIdx.x; c < F_COLS; c += blockDim.x) {      // c = strip-relative padded column (coalesced reads)
     const int gx = s0 + c;
     uint16_t v = 0;
-    if (row < img.h && gx < img.w) v = (uint16_t)((int)(img.p[(ptrdiff_t)row * img.pitch + gx] - vmin) * 4);
-    o[(c & 7) * 32 + (c >> 3)] = v;
+    if (row < img.h && gx < img.w) v = (uint16_t)((int)(img.p[(ptrdiff_t)row * img.pitch + gx] - vmin) * F_B);
+    o[c] = v;
   }
 }
 __global__ void pack_right_kernel(ImgF img, float vmin, FastGeom g, uint16_t* __restrict__ out) {
   const int row = blockIdx.x, strip = blockIdx.y;
   const int s0 = strip * g.out_cols;
-  uint16_t* o = out + ((size_t)strip * g.rrows + row) * F_RROW;
-  for (int c = threadIdx.x; c < F_RROW; c += blockDim.x) {
+  uint16_t* o = out + ((size_t)strip * g.rrows + row) * g.rw;
+  for (int c = threadIdx.x; c < g.rw; c += blockDim.x) {
     const int gx = s0 + c;
     uint16_t v = 0;
-    if (row < img.h && gx < img.w) v = (uint16_t)((int)(img.p[(ptrdiff_t)row * img.pitch + gx] - vmin) * 4);
-    o[(c & 7) * F_RP + (c >> 3)] = v;
+    if (row < img.h && gx < img.w) v = (uint16_t)((int)(img.p[(ptrdiff_t)row * img.pitch + gx] - vmin) * F_B);
+    o[c] = v;
   }
 }
 
@@ -200,60 +201,70 @@ __device__ __forceinline__ void window_sums(const int (&p)[8], int (&out)[8]) {
   }
 }
 
-// ---- one pass: 4 consecutive dx (group g) x 8 columns per lane, sliding down the 32-row band -------------
-template <int KX, int J0>
+// ---- one pass: 8 consecutive dx (octet g) x 8 columns per lane, sliding down the warp's rows ----------------
+__device__ __forceinline__ void unpack8(const uint4 v, int (&o)[8]) {
+  o[0] = v.x & 0xffff; o[1] = v.x >> 16; o[2] = v.y & 0xffff; o[3] = v.y >> 16;
+  o[4] = v.z & 0xffff; o[5] = v.z >> 16; o[6] = v.w & 0xffff; o[7] = v.w >> 16;
+}
+__device__ __forceinline__ void load_row(const uint16_t* lrow, const uint16_t* rrow, int (&Lv)[8], int (&Rv)[16]) {
+  unpack8(*reinterpret_cast<const uint4*>(lrow), Lv);
+  int t[8];
+  unpack8(*reinterpret_cast<const uint4*>(rrow), t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Rv[i] = t[i];
+  unpack8(*reinterpret_cast<const uint4*>(rrow + 8), t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Rv[8 + i] = t[i];
+}
+
+template <int KX>
 __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, const uint16_t* __restrict__ rring,
                                           uint32_t* __restrict__ state, uint16_t* __restrict__ idxp,
-                                          int lane, int goff, int ky, int ring_slots, int ring_base, int idx_base, int row0) {
-  int V[8][4];
+                                          int lane, int g, int ky, int ring_slots, int rw, int ring_base, int idx_base, int row0) {
+  int V[8][F_B];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) V[a][b] = 0;
-  const uint16_t* lp = ltile + row0 * F_COLS + lane;     // + row*256 + a*32
-  const uint16_t* rp = rring + lane + goff;              // + slot*F_RROW + (jj&7)*F_RP + (jj>>3)
-  int slot_new = ring_base;                              // ring slot of right row (dy + t)
+    for (int b = 0; b < F_B; ++b) V[a][b] = 0;
+  const uint16_t* lp = ltile + row0 * F_COLS + 8 * lane;       // + row*256            (16-byte aligned)
+  const uint16_t* rp = rring + 8 * (lane + g);                 // + slot*rw            (16-byte aligned)
+  int slot_new = ring_base;                                     // ring slot of right row (dy + row0 + t)
   // ---- seed: first ky rows ----
   for (int t = 0; t < ky; ++t) {
-    const uint16_t* lr = lp + t * F_COLS;
-    const uint16_t* rr = rp + slot_new * F_RROW;
-    int Lv[8], Rv[11];
-#pragma unroll
-    for (int a = 0; a < 8; ++a) Lv[a] = lr[a * 32];
-#pragma unroll
-    for (int j = 0; j < 11; ++j) Rv[j] = rr[((J0 + j) & 7) * F_RP + ((J0 + j) >> 3)];
+    int Lv[8], Rv[16];
+    load_row(lp + t * F_COLS, rp + slot_new * rw, Lv, Rv);
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) V[a][b] = __sad(Lv[a], Rv[a + b], V[a][b]);
+      for (int b = 0; b < F_B; ++b) V[a][b] = __sad(Lv[a], Rv[a + b], V[a][b]);
     if (++slot_new == ring_slots) slot_new = 0;
   }
   int slot_old = ring_base;
   for (int y = 0; y < F_RH; ++y) {
     if (y > 0) {
-      const uint16_t* lrn = lp + (y + ky - 1) * F_COLS;
-      const uint16_t* rrn = rp + slot_new * F_RROW;
-      const uint16_t* lro = lp + (y - 1) * F_COLS;
-      const uint16_t* rro = rp + slot_old * F_RROW;
-      int Lv[8], Rv[11], Lo[8], Ro[11];
+      {
+        int Lv[8], Rv[16];
+        load_row(lp + (y + ky - 1) * F_COLS, rp + slot_new * rw, Lv, Rv);
 #pragma unroll
-      for (int a = 0; a < 8; ++a) { Lv[a] = lrn[a * 32]; Lo[a] = lro[a * 32]; }
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
-      for (int j = 0; j < 11; ++j) {
-        Rv[j] = rrn[((J0 + j) & 7) * F_RP + ((J0 + j) >> 3)];
-        Ro[j] = rro[((J0 + j) & 7) * F_RP + ((J0 + j) >> 3)];
+          for (int b = 0; b < F_B; ++b) V[a][b] = __sad(Lv[a], Rv[a + b], V[a][b]);
       }
+      {
+        int Lo[8], Ro[16];
+        load_row(lp + (y - 1) * F_COLS, rp + slot_old * rw, Lo, Ro);
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) V[a][b] = __sad(Lv[a], Rv[a + b], V[a][b]) - __sad(Lo[a], Ro[a + b], 0);
+          for (int b = 0; b < F_B; ++b) V[a][b] -= __sad(Lo[a], Ro[a + b], 0);
+      }
       if (++slot_new == ring_slots) slot_new = 0;
       if (++slot_old == ring_slots) slot_old = 0;
     }
-    // ---- horizontal window sums + min over the 4 dx (keys = cost*4 + b) ----
+    // ---- horizontal window sums + min over the 8 dx (keys = cost*8 + b) ----
     int m[8];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < F_B; ++b) {
       int p[8], o[8];
       p[0] = V[0][b];
 #pragma unroll
@@ -264,16 +275,16 @@ __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, co
     }
     // ---- running best (shared memory), index plane (global) on improvement ----
     uint32_t* srow = state + y * F_COLS + lane;
-    uint32_t s4[8];
+    uint32_t s8[8];
     bool improved = false;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { s4[r] = srow[r * 32]; improved |= ((uint32_t)m[r] < s4[r]); }
+    for (int r = 0; r < 8; ++r) { s8[r] = srow[r * 32]; improved |= ((uint32_t)m[r] < s8[r]); }
     if (improved) {            // rare once the search has seen the neighbourhood of the true match
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        if ((uint32_t)m[r] < s4[r]) {
-          srow[r * 32] = (uint32_t)m[r] & ~3u;
-          idxp[y * F_COLS + r * 32 + lane] = (uint16_t)(idx_base + (m[r] & 3));
+        if ((uint32_t)m[r] < s8[r]) {
+          srow[r * 32] = (uint32_t)m[r] & ~7u;
+          idxp[y * F_COLS + r * 32 + lane] = (uint16_t)(idx_base + (m[r] & 7));
         }
       }
     }
@@ -288,27 +299,27 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
   uint32_t* state = reinterpret_cast<uint32_t*>(smem);                                  // [4][32][8][32]
   uint16_t* ltile = reinterpret_cast<uint16_t*>(smem + (size_t)F_SUBSETS * F_TH * F_COLS * 4);
   uint16_t* rring = ltile + (size_t)G.ltile_rows * F_COLS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rring + (size_t)G.ring_slots * F_RROW);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rring + (size_t)G.ring_slots * G.rw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int sub = w & (F_SUBSETS - 1), half = w / F_SUBSETS, row0 = half * F_RH;
-  const int ngroups = G.sx / 4;
+  const int ngroups = G.sx / F_B;
   uint16_t* idxp_block = idx_scratch + (size_t)blockIdx.x * F_SUBSETS * F_TH * F_COLS;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
   uint32_t ph0 = 0, ph1 = 0;
-  const uint32_t lbytes = (uint32_t)G.ltile_rows * F_COLS * 2, rrow_bytes = F_RROW * 2;
+  const uint32_t lbytes = (uint32_t)G.ltile_rows * F_COLS * 2, rrow_bytes = (uint32_t)G.rw * 2;
   for (int item = blockIdx.x; item < G.NS * G.NB; item += gridDim.x) {
     const int strip = item % G.NS, band = item / G.NS;
     const int y0 = band * F_TH;
     const uint16_t* lsrc = L16 + ((size_t)strip * G.lrows + y0) * F_COLS;
-    const uint16_t* rsrc = R16 + ((size_t)strip * G.rrows + y0) * F_RROW;
+    const uint16_t* rsrc = R16 + ((size_t)strip * G.rrows + y0) * G.rw;
     if (tid == 0) {
       fence_proxy_async();
       mbar_expect_tx(&bars[0], lbytes + (uint32_t)G.ltile_rows * rrow_bytes);
       tma_load_1d(ltile, lsrc, lbytes, &bars[0]);
       tma_load_1d(rring, rsrc, (uint32_t)G.ltile_rows * rrow_bytes, &bars[0]);     // right rows y0 .. y0+ltile_rows-1 -> slots 0..
     }
-    for (int k = tid; k < F_SUBSETS * F_TH * F_COLS; k += F_THREADS) state[k] = S4_INIT;
+    for (int k = tid; k < F_SUBSETS * F_TH * F_COLS; k += F_THREADS) state[k] = S_INIT;
     __syncthreads();
     mbar_wait(&bars[0], ph0); ph0 ^= 1;
     uint32_t* wstate = state + ((size_t)sub * F_TH + row0) * F_COLS;       // this warp's rows of its subset plane
@@ -318,12 +329,10 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
       if (tid == 0 && dy + 1 < G.sy) {       // prefetch the row iteration dy+1 adds, into the slot iteration dy-1 freed
         fence_proxy_async();
         mbar_expect_tx(&bars[1], rrow_bytes);
-        tma_load_1d(rring + (size_t)((dy + G.ltile_rows) % G.ring_slots) * F_RROW, rsrc + (size_t)(dy + G.ltile_rows) * F_RROW, rrow_bytes, &bars[1]);
+        tma_load_1d(rring + (size_t)((dy + G.ltile_rows) % G.ring_slots) * G.rw, rsrc + (size_t)(dy + G.ltile_rows) * G.rw, rrow_bytes, &bars[1]);
       }
       for (int g = sub; g < ngroups; g += F_SUBSETS) {
-        const int idx_base = dy * G.sx + 4 * g;
-        if (g & 1) fast_pass<KX, 4>(ltile, rring, wstate, widx, lane, g >> 1, G.ky, G.ring_slots, ring_base, idx_base, row0);
-        else       fast_pass<KX, 0>(ltile, rring, wstate, widx, lane, g >> 1, G.ky, G.ring_slots, ring_base, idx_base, row0);
+        fast_pass<KX>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, dy * G.sx + F_B * g, row0);
       }
       if (dy + 1 < G.sy) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
       __syncthreads();
@@ -381,7 +390,7 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   uint16_t* L16 = reinterpret_cast<uint16_t*>(ws);
   uint16_t* R16 = L16 + (size_t)g.NS * g.lrows * F_COLS;
-  uint16_t* idx = R16 + (size_t)g.NS * g.rrows * F_RROW;
+  uint16_t* idx = R16 + (size_t)g.NS * g.rrows * g.rw;
   {
     dim3 gl(g.lrows, g.NS), gr(g.rrows, g.NS);
     pack_left_kernel<<<gl, 256, 0, st>>>(left, vmin, g, L16);
