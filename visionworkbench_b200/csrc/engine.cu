@@ -490,7 +490,7 @@ int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrd
         const size_t wb = k1_fast_workspace_bytes(W, H, sx, sy, kx, ky);
         unsigned char* ws;
         VWB_TRY(ar.alloc(&ws, wb));
-        VWB_TRY(k1_fast_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, vmin, dout, dop, ws, wb, st, &kev));
+        VWB_TRY(k1_fast_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, vmin, vmax, dout, dop, ws, wb, st, &kev));
         path = 0;
       }
     }
