@@ -22,6 +22,8 @@
 //   * pixels whose arg-best is disparity (0,0) are re-checked by a small kernel for the
 //     "every disparity gave the same cost => invalid" rule (Correlation.cc:121-133)
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace vwb200 {
 
@@ -217,27 +219,65 @@ __device__ __forceinline__ void load_row(const uint16_t* lrow, const uint16_t* r
   for (int i = 0; i < 8; ++i) Rv[8 + i] = t[i];
 }
 
-template <int KX>
+__device__ __forceinline__ void unpack8f(const uint4 v, float (&o)[8]) {
+  o[0] = __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7610)); o[1] = __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7632));
+  o[2] = __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7610)); o[3] = __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7632));
+  o[4] = __uint_as_float(__byte_perm(v.z, 0x4B000000u, 0x7610)); o[5] = __uint_as_float(__byte_perm(v.z, 0x4B000000u, 0x7632));
+  o[6] = __uint_as_float(__byte_perm(v.w, 0x4B000000u, 0x7610)); o[7] = __uint_as_float(__byte_perm(v.w, 0x4B000000u, 0x7632));
+}
+__device__ __forceinline__ void load_row_f(const uint16_t* lrow, const uint16_t* rrow, float (&Lv)[8], float (&Rv)[16]) {
+  unpack8f(*reinterpret_cast<const uint4*>(lrow), Lv);
+  float t[8];
+  unpack8f(*reinterpret_cast<const uint4*>(rrow), t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Rv[i] = t[i];
+  unpack8f(*reinterpret_cast<const uint4*>(rrow + 8), t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Rv[8 + i] = t[i];
+}
+template <int KX, bool FSEED>
 __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, const uint16_t* __restrict__ rring,
                                           uint32_t* __restrict__ state, uint16_t* __restrict__ idxp,
                                           int lane, int g, int ky, int ring_slots, int rw, int ring_base, int idx_base, int row0) {
   int V[8][F_B];
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < F_B; ++b) V[a][b] = 0;
   const uint16_t* lp = ltile + row0 * F_COLS + 8 * lane;       // + row*256            (16-byte aligned)
   const uint16_t* rp = rring + 8 * (lane + g);                 // + slot*rw            (16-byte aligned)
   int slot_new = ring_base;                                     // ring slot of right row (dy + row0 + t)
-  // ---- seed: first ky rows ----
-  for (int t = 0; t < ky; ++t) {
-    int Lv[8], Rv[16];
-    load_row(lp + t * F_COLS, rp + slot_new * rw, Lv, Rv);
+  // ---- seed: first ky rows.  The integer main loop is bound by the ALU pipe (VABSDIFF), so the seed
+  //      rows are summed in fp32 on the otherwise idle FMA pipes (exact: sums < 2^23) and converted once.
+  if (FSEED) {
+    float Vf[8][F_B];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-      for (int b = 0; b < F_B; ++b) V[a][b] = __sad(Lv[a], Rv[a + b], V[a][b]);
-    if (++slot_new == ring_slots) slot_new = 0;
+      for (int b = 0; b < F_B; ++b) Vf[a][b] = 0.0f;
+    for (int t = 0; t < ky; ++t) {
+      float Lv[8], Rv[16];
+      load_row_f(lp + t * F_COLS, rp + slot_new * rw, Lv, Rv);
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < F_B; ++b) Vf[a][b] = __fadd_rn(Vf[a][b], fabsf(__fsub_rn(Lv[a], Rv[a + b])));
+      if (++slot_new == ring_slots) slot_new = 0;
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < F_B; ++b) V[a][b] = (int)__float_as_uint(__fadd_rn(Vf[a][b], 8388608.0f)) - 0x4B000000;
+  } else {
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < F_B; ++b) V[a][b] = 0;
+    for (int t = 0; t < ky; ++t) {
+      int Lv[8], Rv[16];
+      load_row(lp + t * F_COLS, rp + slot_new * rw, Lv, Rv);
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < F_B; ++b) V[a][b] = __sad(Lv[a], Rv[a + b], V[a][b]);
+      if (++slot_new == ring_slots) slot_new = 0;
+    }
   }
   int slot_old = ring_base;
   for (int y = 0; y < F_RH; ++y) {
@@ -296,22 +336,6 @@ __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, co
 // pipes at twice the ALU rate.  Unpacking u16 -> "2^23 + x" biased floats is a single PRMT, differences
 // of biased floats are exact, and every sum stays below 2^24 (checked on the host), so the fp32 pass
 // produces the same integers.
-__device__ __forceinline__ void unpack8f(const uint4 v, float (&o)[8]) {
-  o[0] = __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7610)); o[1] = __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7632));
-  o[2] = __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7610)); o[3] = __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7632));
-  o[4] = __uint_as_float(__byte_perm(v.z, 0x4B000000u, 0x7610)); o[5] = __uint_as_float(__byte_perm(v.z, 0x4B000000u, 0x7632));
-  o[6] = __uint_as_float(__byte_perm(v.w, 0x4B000000u, 0x7610)); o[7] = __uint_as_float(__byte_perm(v.w, 0x4B000000u, 0x7632));
-}
-__device__ __forceinline__ void load_row_f(const uint16_t* lrow, const uint16_t* rrow, float (&Lv)[8], float (&Rv)[16]) {
-  unpack8f(*reinterpret_cast<const uint4*>(lrow), Lv);
-  float t[8];
-  unpack8f(*reinterpret_cast<const uint4*>(rrow), t);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) Rv[i] = t[i];
-  unpack8f(*reinterpret_cast<const uint4*>(rrow + 8), t);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) Rv[8 + i] = t[i];
-}
 template <int KX>
 __device__ __forceinline__ void window_sums_f(const float (&p)[8], float (&out)[8]) {
   const float T = p[7];
@@ -410,7 +434,7 @@ __device__ __forceinline__ void fast_pass_f(const uint16_t* __restrict__ ltile, 
   }
 }
 
-template <int KX, bool FLT>
+template <int KX, bool FLT, bool FSEED>
 __global__ void __launch_bounds__(F_THREADS, 1)
 k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict__ R16, FastGeom G,
                    uint16_t* __restrict__ idx_scratch, vwb200_dispi* __restrict__ out, ptrdiff_t opitch) {
@@ -452,7 +476,7 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
       }
       for (int g = sub; g < ngroups; g += F_SUBSETS) {
         if (FLT) fast_pass_f<KX>(ltile, rring, reinterpret_cast<float*>(wstate), widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, dy * G.sx + F_B * g, row0);
-        else     fast_pass<KX>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, dy * G.sx + F_B * g, row0);
+        else     fast_pass<KX, FSEED>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, dy * G.sx + F_B * g, row0);
       }
       if (dy + 1 < G.sy) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
       __syncthreads();
@@ -508,7 +532,13 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
   (void)cost; (void)workspace_bytes;
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
   // fp32 carries the integers exactly while every window sum * 8 (+7) stays below 2^24
-  const bool use_float = (double)(vmax - vmin) * kx * ky * F_B + F_B < 16777216.0;
+  // variants: all-int (always exact), int with fp32 seeding (column sums * 8 < 2^23), all-fp32 (window sums * 8 < 2^24;
+  // issue-bound, kept for comparison: VWB200_K1_FAST=float)
+  const char* mode = getenv("VWB200_K1_FAST");
+  const bool float_ok = (double)(vmax - vmin) * kx * ky * F_B + F_B < 16777216.0;
+  const bool fseed_ok = (double)(vmax - vmin) * ky * F_B < 8388608.0;
+  const bool use_float = float_ok && mode && !strcmp(mode, "float");
+  const bool float_seed = fseed_ok && !(mode && !strcmp(mode, "int"));
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   uint16_t* L16 = reinterpret_cast<uint16_t*>(ws);
   uint16_t* R16 = L16 + (size_t)g.NS * g.lrows * F_COLS;
@@ -528,7 +558,7 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
   const size_t smem = fast_smem_bytes(g);
   void (*kern)(const uint16_t*, const uint16_t*, FastGeom, uint16_t*, vwb200_dispi*, ptrdiff_t) = nullptr;
   switch (kx) {
-#define KCASE(K) case K: kern = use_float ? k1_fast_abs_kernel<K, true> : k1_fast_abs_kernel<K, false>; break;
+#define KCASE(K) case K: kern = use_float ? k1_fast_abs_kernel<K, true, false> : (float_seed ? k1_fast_abs_kernel<K, false, true> : k1_fast_abs_kernel<K, false, false>); break;
     KCASE(3) KCASE(5) KCASE(7) KCASE(9) KCASE(11) KCASE(13) KCASE(15) KCASE(17) KCASE(19) KCASE(21) KCASE(23) KCASE(25)
     KCASE(27) KCASE(29) KCASE(31)
 #undef KCASE
