@@ -532,13 +532,13 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
   (void)cost; (void)workspace_bytes;
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
   // fp32 carries the integers exactly while every window sum * 8 (+7) stays below 2^24
-  // variants: all-int (always exact), int with fp32 seeding (column sums * 8 < 2^23), all-fp32 (window sums * 8 < 2^24;
-  // issue-bound, kept for comparison: VWB200_K1_FAST=float)
+  // variants: all-int (default, ALU-pipe bound), int with fp32 seeding (VWB200_K1_FAST=fseed), all-fp32 on the FMA
+  // pipes (VWB200_K1_FAST=float; issue-bound).  All three are exact; profiles/k1_fast_variants_r01.md has the numbers.
   const char* mode = getenv("VWB200_K1_FAST");
   const bool float_ok = (double)(vmax - vmin) * kx * ky * F_B + F_B < 16777216.0;
   const bool fseed_ok = (double)(vmax - vmin) * ky * F_B < 8388608.0;
   const bool use_float = float_ok && mode && !strcmp(mode, "float");
-  const bool float_seed = fseed_ok && !(mode && !strcmp(mode, "int"));
+  const bool float_seed = fseed_ok && mode && !strcmp(mode, "fseed");     // measured 3 % slower than all-int (issue-bound)
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   uint16_t* L16 = reinterpret_cast<uint16_t*>(ws);
   uint16_t* R16 = L16 + (size_t)g.NS * g.lrows * F_COLS;
