@@ -167,35 +167,18 @@ def run_ours(a):
     cost = COSTS[a.cost]
     k, s, S = a.kernel, a.search, a.size
     left, right = gen_rasters(a)                        # same seed on every rank
-    # ---- shard output rows into bands; each rank OWNS the input rows of its band ----
-    band = (S + world - 1) // world
-    y0, y1 = rank * band, min(S, (rank + 1) * band)
-    H = y1 - y0
-    lh_need, rh_need = H + k - 1, H + k - 1 + s - 1     # rows this rank's kernel launch reads
-    own1 = y1 if rank < world - 1 else left.shape[0]      # rows [y0, own1) of the left raster are resident here
-    own1r = y1 if rank < world - 1 else right.shape[0]
+    # ---- shard output rows into bands; each rank OWNS the input rows of its band (visionworkbench_b200/sharding.py) ----
+    from visionworkbench_b200 import sharding
+    p = sharding.plan(rank, world, S, k, s, left.shape[0], right.shape[0])
+    y0, y1, H = p.y0, p.y1, p.y1 - p.y0
+    lh_need, rh_need = p.left_rows, p.right_rows          # rows this rank's kernel launch reads
     dl = torch.empty((lh_need, left.shape[1]), dtype=torch.float32, device="cuda")
     dr = torch.empty((rh_need, right.shape[1]), dtype=torch.float32, device="cuda")
-    nl_own, nr_own = min(own1 - y0, lh_need), min(own1r - y0, rh_need)
-    dl[:nl_own].copy_(torch.from_numpy(left[y0:y0 + nl_own]))
-    dr[:nr_own].copy_(torch.from_numpy(right[y0:y0 + nr_own]))
-    halo_l, halo_r = lh_need - nl_own, rh_need - nr_own     # rows to fetch from rank+1 (0 on the last rank)
-    send_l = (k - 1) if rank > 0 else 0                     # rows rank-1 needs from us
-    send_r = (k - 1 + s - 1) if rank > 0 else 0
+    dl[:p.own_left].copy_(torch.from_numpy(left[y0:y0 + p.own_left]))
+    dr[:p.own_right].copy_(torch.from_numpy(right[y0:y0 + p.own_right]))
 
     def halo_exchange():
-        if world == 1:
-            return 0
-        ops = []
-        if halo_l:
-            ops.append(dist.P2POp(dist.irecv, dl[nl_own:], rank + 1))
-            ops.append(dist.P2POp(dist.irecv, dr[nr_own:], rank + 1))
-        if send_l:
-            ops.append(dist.P2POp(dist.isend, dl[:send_l], rank - 1))
-            ops.append(dist.P2POp(dist.isend, dr[:send_r], rank - 1))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        return (halo_l * dl.shape[1] + halo_r * dr.shape[1]) * 4
+        return sharding.exchange_halos(p, dl, dr)
 
     def step_device():
         halo_exchange()

@@ -1,0 +1,63 @@
+"""world_size-2 (and 4) gloo tests of the band/halo logic bench.py uses for N > 1 GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from visionworkbench_b200 import sharding  # noqa: E402
+
+
+def test_plan_covers_every_output_row_once():
+    for world in (1, 2, 4, 8):
+        rows = []
+        for r in range(world):
+            p = sharding.plan(r, world, 8192, 21, 128)
+            rows += list(range(p.y0, p.y1))
+            assert p.left_rows == p.own_left + p.recv_left and p.right_rows == p.own_right + p.recv_right
+            if r == world - 1:
+                assert p.recv_left == 0 and p.recv_right == 0
+            else:
+                assert p.recv_left == 20 and p.recv_right == 20 + 127
+            assert p.send_left == (20 if r else 0)
+        assert rows == list(range(8192))
+    with pytest.raises(ValueError):
+        sharding.plan(0, 8, 512, 21, 128)       # 64-row bands cannot hold a 147-row halo
+
+
+def _worker(rank, world, port, out_rows, ky, sy, width, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    left = rng.random((out_rows + ky - 1, width + ky - 1)).astype(np.float32)
+    right = rng.random((out_rows + ky - 1 + sy - 1, width + ky - 1 + sy - 1)).astype(np.float32)
+    p = sharding.plan(rank, world, out_rows, ky, sy)
+    lb = torch.zeros((p.left_rows, left.shape[1]))
+    rb = torch.zeros((p.right_rows, right.shape[1]))
+    lb[:p.own_left] = torch.from_numpy(left[p.y0:p.y0 + p.own_left])
+    rb[:p.own_right] = torch.from_numpy(right[p.y0:p.y0 + p.own_right])
+    nbytes = sharding.exchange_halos(p, lb, rb)
+    ok = np.array_equal(lb.numpy(), left[p.y0:p.y0 + p.left_rows]) and np.array_equal(rb.numpy(), right[p.y0:p.y0 + p.right_rows])
+    q.put((rank, ok, nbytes))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_halo_exchange_reassembles_the_rasters(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000 + world
+    out_rows, ky, sy, width = 96 * world, 7, 9, 40
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out_rows, ky, sy, width, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    assert all(ok for _, ok, _ in res), res
+    by_rank = {r: n for r, _, n in res}
+    assert by_rank[world - 1] == 0
+    assert by_rank[0] == ((ky - 1) * (width + ky - 1) + (ky - 1 + sy - 1) * (width + ky - 1 + sy - 1)) * 4
