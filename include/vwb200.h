@@ -82,6 +82,10 @@ int vwb200_last_k1_stats(vwb200_k1_stats* out);
  * ------------------------------------------------------------------------------------------- */
 int vwb200_pyramid_down(const float* in, int w, int h, ptrdiff_t pitch,
                         float* out, ptrdiff_t opitch, int on_device, void* stream);
+/* vw::stereo::prefilter_image (src/vw/Stereo/PreFilter.h:75-95): NONE / LaplacianOfGaussian(width) /
+ * SubtractedMean(width); gaussian_filter + laplacian_filter of src/vw/Image/Filter.h:204-237,318-335. */
+int vwb200_prefilter(const float* in, int w, int h, ptrdiff_t pitch, int mode, float width,
+                     float* out, ptrdiff_t opitch, int on_device, void* stream);
 /* SubsampleMaskByTwoFunc, src/vw/Stereo/CorrelationView.cc:38-63 */
 int vwb200_subsample_mask_by_two(const uint8_t* in, int w, int h, ptrdiff_t pitch,
                                  uint8_t* out, ptrdiff_t opitch, int on_device, void* stream);

@@ -127,6 +127,18 @@ def subsample_mask_by_two(m):
     return out
 
 
+def prefilter(img, mode, width):
+    a = _f32(img)
+    h, w = a.shape
+    out = np.empty_like(a)
+    f = lib().vwo_prefilter
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    rc = f(_p(a), w, h, mode, width, _p(out))
+    if rc:
+        raise ValueError(rc)
+    return out
+
+
 def gaussian_kernel(sigma):
     k = np.zeros(512, np.float32)
     lib().vwo_gaussian_kernel.argtypes = [C.c_double, C.c_void_p, C.c_int]

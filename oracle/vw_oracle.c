@@ -553,9 +553,22 @@ int vwo_prefilter(const float* in, int w, int h, int mode, float width, float* o
     free(g);
     return 0;
   }
-  /* LoG: handled in a later revision together with the GPU prefilter row. */
+  /* LoG: 3x3 Laplacian {{0,1,0},{1,-4,1},{0,1,0}} of the gaussian view, ConstantEdgeExtension, accumulated
+   * row-major "result += k*s" in float (Image/Convolution.h:68-91, Image/Filter.h:318-326).  The zero taps
+   * contribute +-0 and are skipped; the remaining order is top, left, centre, right, bottom. */
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int xm = clampi(x - 1, 0, w - 1), xp = clampi(x + 1, 0, w - 1), ym = clampi(y - 1, 0, h - 1), yp = clampi(y + 1, 0, h - 1);
+      float r = 0.0f;
+      r = r + 1.0f * g[(size_t)ym * w + x];
+      r = r + 1.0f * g[(size_t)y * w + xm];
+      r = r + -4.0f * g[(size_t)y * w + x];
+      r = r + 1.0f * g[(size_t)y * w + xp];
+      r = r + 1.0f * g[(size_t)yp * w + x];
+      out[(size_t)y * w + x] = r;
+    }
   free(g);
-  return -10;
+  return 0;
 }
 
 /* ------------------------------------------------------------------ the view */

@@ -250,3 +250,28 @@ def test_fast_path_ties_and_constant_regions(vwb, oracle):
     ref = oracle.calc_disparity(0, left, right, search, kernel)
     assert (ref[..., 2] == 0).any() and (ref[..., 2] == 1).any()
     _assert_disp_equal(got, ref, "ties")
+
+
+@pytest.mark.parametrize("mode,width", [(1, 1.4), (2, 1.4), (1, 0.7), (2, 3.0)])
+def test_prefilter_bit_exact(vwb, oracle, mode, width):
+    """Stereo/PreFilter.h:45-95: LoG and subtracted-mean prefilters, identical float op order."""
+    rng = np.random.default_rng(31)
+    for shape in [(64, 80), (5, 3), (131, 77)]:
+        img = (rng.random(shape) * 4096).astype(np.float32)
+        a = vwb.prefilter_image(img, mode, width)
+        b = oracle.prefilter(img, mode, width)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (mode, width, shape)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_view_with_prefilter(vwb, oracle, mode):
+    """correlate's default is PREFILTER_LOG 1.4 (tools/correlate.cc:210): full pipeline on prefiltered pyramids."""
+    from visionworkbench_b200.synth import make_pair
+    search, kernel = (-10, -6, 14, 10), (9, 9)
+    left, right, lm, rm, _ = make_pair(260, 230, search, 41)
+    view = vwb.pyramid_correlate(left, right, lm, rm, mode, 1.4, search, kernel, 0, 0, 0.0, 2.0, 0, 3, 3)
+    got = view.rasterize(None, (0, 0, 260, 230))
+    p = oracle.make_params(search, kernel, cost=0, prefilter_mode=mode, prefilter_width=1.4, consistency_threshold=2.0,
+                           filter_half_kernel=3, max_pyramid_levels=3)
+    ref = oracle.pyramid_correlate(p, left, right, lm, rm)
+    _assert_disp_equal(got, ref, f"prefilter {mode}")

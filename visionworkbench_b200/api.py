@@ -88,6 +88,7 @@ def lib():
         L.vwb200_calc_disparity.argtypes = [I, P, I, I, Z, P, I, I, Z, I, I, I, I, P, Z, I, P]
         L.vwb200_pyramid_down.argtypes = [P, I, I, Z, P, Z, I, P]
         L.vwb200_subsample_mask_by_two.argtypes = [P, I, I, Z, P, Z, I, P]
+        L.vwb200_prefilter.argtypes = [P, I, I, Z, I, F, P, Z, I, P]
         L.vwb200_cross_corr_consistency_check.argtypes = [P, I, I, Z, P, I, I, Z, F, I, P]
         L.vwb200_rm_outliers_using_thresh.argtypes = [P, I, I, I, I, D, D, P, I, P]
         L.vwb200_disparity_cleanup_using_thresh.argtypes = [P, I, I, I, I, D, D, P, I, P]
@@ -177,6 +178,15 @@ def pyramid_down(img):
     h, w = a.shape
     out = np.empty((1 + (h - 1) // 2, 1 + (w - 1) // 2), np.float32)
     _check(lib().vwb200_pyramid_down(a.ctypes.data, w, h, w, out.ctypes.data, out.shape[1], 0, None))
+    return out
+
+
+def prefilter_image(image, prefilter_mode, prefilter_width):
+    """vw::stereo::prefilter_image (Stereo/PreFilter.h:75-95)."""
+    a = _np(image, np.float32)
+    h, w = a.shape
+    out = np.empty_like(a)
+    _check(lib().vwb200_prefilter(a.ctypes.data, w, h, w, int(prefilter_mode), float(prefilter_width), out.ctypes.data, w, 0, None))
     return out
 
 

@@ -92,6 +92,9 @@ int masked_mean_launch(ImgF img, ImgB mask, double* d_acc2, cudaStream_t st);
 int mean_fill_launch(float* img, int w, int h, ptrdiff_t pitch, ImgB mask, const double* d_acc2, cudaStream_t st);
 int pyramid_down_launch(ImgF in, float* out, ptrdiff_t opitch, cudaStream_t st);
 int subsample_mask_launch(ImgB in, uint8_t* out, ptrdiff_t opitch, cudaStream_t st);
+// gaussian (separable, constant edge) into out via work; then Laplacian (mode 1) or img - g (mode 2)
+int sepconv_launch(ImgF in, const float* d_taps, int n, float* work, float* out, cudaStream_t st);
+int prefilter_final_launch(ImgF img, const float* g, int mode, float* out, cudaStream_t st);
 
 // ---- K3 / K4 -------------------------------------------------------------------------------------
 int consistency_launch(vwb200_dispi* l2r, int lw, int lh, ptrdiff_t lpitch, const vwb200_dispi* r2l, int rw, int rh,

@@ -231,6 +231,54 @@ void subdivide_regions_host(const vwb200_dispi* disp, int w, int h, int kx, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// stereo pre-filter (behaviour of Stereo/PreFilter.h:45-95).  Gaussian taps: erf differences over unit
+// bins, normalised, stored as float (Image/Filter.tcc:36-79; default size 7*sigma made odd, >= 3,
+// Image/Filter.cc:31-37).  In place on a dense w x h float image.
+// ---------------------------------------------------------------------------------------------------
+static std::vector<float> gaussian_taps(double sigma) {
+  std::vector<float> k;
+  if (sigma == 0) return k;
+  int size = (int)(7 * sigma);
+  if (size < 3) size = 3; else if (size % 2 == 0) size -= 1;
+  k.resize(size);
+  const int c = size / 2;
+  const double z = 1 / (std::sqrt(2.0) * sigma);
+  double sum = 0.0;
+  for (int i = 1; i <= c; ++i) {
+    const double t = std::erf((i + 0.5) * z) - std::erf((i - 0.5) * z);
+    sum += t;
+    k[c + i] = k[c - i] = (float)t;
+  }
+  sum *= 2.0;
+  const double t0 = std::erf(0.5 * z) - std::erf(-0.5 * z);
+  sum += t0;
+  k[c] = (float)t0;
+  const double norm = 1.0 / sum;
+  for (float& v : k) v = (float)(v * norm);
+  return k;
+}
+static int prefilter_inplace(float* img, int w, int h, int mode, float width, Arena& ar, cudaStream_t st) {
+  if (mode == VWB200_PREFILTER_NONE) return VWB200_OK;
+  if (mode != VWB200_PREFILTER_LOG && mode != VWB200_PREFILTER_MEANSUB) { set_error("unknown prefilter mode %d", mode); return VWB200_EARG; }
+  const std::vector<float> taps = gaussian_taps((double)width);
+  float *d_taps, *work, *g;
+  VWB_TRY(ar.alloc(&d_taps, taps.size() + 1));
+  VWB_TRY(ar.alloc(&work, (size_t)w * h));
+  VWB_TRY(ar.alloc(&g, (size_t)w * h));
+  const ImgF im{img, w, h, w};
+  if (taps.empty()) {          // sigma 0: no smoothing, the view is the (edge-extended) image itself
+    VWB_CUDA(cudaMemcpyAsync(g, img, (size_t)w * h * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    VWB_CUDA(cudaMemcpyAsync(d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    VWB_CUDA(cudaStreamSynchronize(st));       // taps live on this frame's stack
+    VWB_TRY(sepconv_launch(im, d_taps, (int)taps.size(), work, g, st));
+  }
+  VWB_TRY(prefilter_final_launch(im, g, mode, work, st));
+  VWB_CUDA(cudaMemcpyAsync(img, work, (size_t)w * h * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return VWB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // the view handle
 // ---------------------------------------------------------------------------------------------------
 }  // namespace vwb200
@@ -277,7 +325,6 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
   const int levels = num_levels(bw, bh);
   const int up = 1 << levels;
   *all_invalid = 0;
-  if (p.prefilter_mode != VWB200_PREFILTER_NONE) { set_error("prefilter mode %d not implemented yet", p.prefilter_mode); return VWB200_ENOIMPL; }
 
   // ---- build_image_pyramids (CorrelationView.cc:67-239) ----
   const Box lg = bexpand(bbox, hkx * up, hky * up);
@@ -328,6 +375,11 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
     VWB_TRY(pyramid_down_launch(ImgF{a.r, a.rw, a.rh, a.rw}, b.r, b.rw, st));
     VWB_TRY(subsample_mask_launch(ImgB{a.lm, a.lmw, a.lmh, a.lmw}, b.lm, b.lmw, st));
     VWB_TRY(subsample_mask_launch(ImgB{a.rm, a.rmw, a.rmh, a.rmw}, b.rm, b.rmw, st));
+  }
+
+  for (int i = 0; i <= levels; ++i) {   // :233-236 prefilter every level
+    VWB_TRY(prefilter_inplace(py[i].l, py[i].lw, py[i].lh, p.prefilter_mode, p.prefilter_width, ar, st));
+    VWB_TRY(prefilter_inplace(py[i].r, py[i].rw, py[i].rh, p.prefilter_mode, p.prefilter_width, ar, st));
   }
 
   // ---- level loop (CorrelationView.cc:363-830) ----
@@ -530,6 +582,23 @@ int vwb200_pyramid_down(const float* in, int w, int h, ptrdiff_t pitch, float* o
       VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch * sizeof(float), dout, (size_t)ow * sizeof(float), (size_t)ow * sizeof(float), oh, cudaMemcpyDeviceToHost, st));
   }
   VWB_CUDA(cudaStreamSynchronize(st));
+  return VWB200_OK;
+}
+
+int vwb200_prefilter(const float* in, int w, int h, ptrdiff_t pitch, int mode, float width, float* out, ptrdiff_t opitch, int on_device, void* stream) {
+  if (!in || !out || w <= 0 || h <= 0) { set_error("prefilter: bad arguments"); return VWB200_EARG; }
+  VWB_TRY(ensure_device());
+  StreamGuard sg; VWB_TRY(sg.init(stream));
+  cudaStream_t st = sg.st;
+  {
+    Arena ar(st);
+    float* buf;
+    VWB_TRY(ar.alloc(&buf, (size_t)w * h));
+    VWB_CUDA(cudaMemcpy2DAsync(buf, (size_t)w * 4, in, (size_t)pitch * 4, (size_t)w * 4, h, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    VWB_TRY(prefilter_inplace(buf, w, h, mode, width, ar, st));
+    VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch * 4, buf, (size_t)w * 4, (size_t)w * 4, h, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    VWB_CUDA(cudaStreamSynchronize(st));
+  }
   return VWB200_OK;
 }
 

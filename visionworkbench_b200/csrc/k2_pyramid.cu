@@ -173,4 +173,60 @@ int subsample_mask_launch(ImgB in, uint8_t* out, ptrdiff_t opitch, cudaStream_t 
   return VWB200_OK;
 }
 
+
+// ---- stereo pre-filters (Stereo/PreFilter.h:45-95) ----------------------------------------------------------------
+// gaussian_filter = SeparableConvolutionView with ConstantEdgeExtension: row pass into a float work image, then the
+// column pass, each output "r = 0; for i: r += k[n-1-i] * src[i]" in float (Image/Convolution.h:56-65,286-289,318).
+// pass 0: rows (reads in, clamped x); pass 1: columns (reads the work image, clamped y).  Taps in global memory.
+__global__ void sepconv_pass_kernel(ImgF in, const float* __restrict__ taps, int n, int vertical, float* __restrict__ out, ptrdiff_t opitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= in.w || y >= in.h) return;
+  const int c = (n - 1) / 2, lo = n - c - 1;         // child bbox grows by (n-c-1) before, c after  (:281-283)
+  float r = 0.0f;
+  if (!vertical) {
+    const float* row = in.p + (ptrdiff_t)y * in.pitch;
+    for (int i = 0; i < n; ++i) r = __fadd_rn(r, __fmul_rn(taps[n - 1 - i], __ldg(row + clampi2(x - lo + i, 0, in.w - 1))));
+  } else {
+    for (int i = 0; i < n; ++i) r = __fadd_rn(r, __fmul_rn(taps[n - 1 - i], __ldg(in.p + (ptrdiff_t)clampi2(y - lo + i, 0, in.h - 1) * in.pitch + x)));
+  }
+  out[(ptrdiff_t)y * opitch + x] = r;
+}
+int sepconv_launch(ImgF in, const float* d_taps, int n, float* work, float* out, cudaStream_t st) {
+  if (in.w <= 0 || in.h <= 0) return VWB200_OK;
+  dim3 b(32, 8), g((in.w + 31) / 32, (in.h + 7) / 8);
+  // the reference convolves rows over the child's FULL padded height first; clamping the row index in the
+  // column pass reads the same values because the row pass of a clamped row equals the clamped row's result.
+  sepconv_pass_kernel<<<g, b, 0, st>>>(in, d_taps, n, 0, work, in.w);
+  VWB_LAUNCH_CHECK();
+  sepconv_pass_kernel<<<g, b, 0, st>>>(ImgF{work, in.w, in.h, in.w}, d_taps, n, 1, out, in.w);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+// mode 1: 3x3 Laplacian of g (order: top, left, centre*-4, right, bottom; Image/Filter.h:318-326, Convolution.h:68-91)
+// mode 2: img - g  (SubtractedMean, PreFilter.h:60-70)
+__global__ void prefilter_final_kernel(ImgF img, const float* __restrict__ g, int mode, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= img.w || y >= img.h) return;
+  const int w = img.w, h = img.h;
+  float r;
+  if (mode == 2) {
+    r = __fsub_rn(img.p[(ptrdiff_t)y * img.pitch + x], g[(ptrdiff_t)y * w + x]);
+  } else {
+    const int xm = clampi2(x - 1, 0, w - 1), xp = clampi2(x + 1, 0, w - 1), ym = clampi2(y - 1, 0, h - 1), yp = clampi2(y + 1, 0, h - 1);
+    r = __fadd_rn(0.0f, __fmul_rn(1.0f, g[(ptrdiff_t)ym * w + x]));
+    r = __fadd_rn(r, __fmul_rn(1.0f, g[(ptrdiff_t)y * w + xm]));
+    r = __fadd_rn(r, __fmul_rn(-4.0f, g[(ptrdiff_t)y * w + x]));
+    r = __fadd_rn(r, __fmul_rn(1.0f, g[(ptrdiff_t)y * w + xp]));
+    r = __fadd_rn(r, __fmul_rn(1.0f, g[(ptrdiff_t)yp * w + x]));
+  }
+  out[(ptrdiff_t)y * w + x] = r;
+}
+int prefilter_final_launch(ImgF img, const float* g, int mode, float* out, cudaStream_t st) {
+  if (img.w <= 0 || img.h <= 0) return VWB200_OK;
+  dim3 b(32, 8), gr((img.w + 31) / 32, (img.h + 7) / 8);
+  prefilter_final_kernel<<<gr, b, 0, st>>>(img, g, mode, out);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
 }  // namespace vwb200
