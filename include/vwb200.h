@@ -108,6 +108,17 @@ int vwb200_disparity_mask(const vwb200_dispi* in, int w, int h,
                           vwb200_dispi* out, int on_device, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * vw::stereo::ParabolaSubpixelView::rasterize(dest, bbox) (src/vw/Stereo/ParabolaSubpixelView.h:27-117,
+ * .cc:31-330): 3x3 AbsoluteCost patch around the integer disparity, 6x9 pseudo-inverse parabola fit,
+ * offset kept when its norm is below 5.  disparity: cols x rows PixelMask<Vector2f> triples (same size as
+ * the left image); dest: (x1-x0) x (y1-y0) triples.  Floats agree with the reference within 1e-5.
+ * ------------------------------------------------------------------------------------------- */
+int vwb200_parabola_subpixel(const float* disparity, int cols, int rows, const float* left, ptrdiff_t lpitch,
+                             const float* right, int rcols, int rrows, ptrdiff_t rpitch, int kx, int ky,
+                             int prefilter_mode, float prefilter_width, int x0, int y0, int x1, int y1,
+                             float* dest, ptrdiff_t dest_pitch, int on_device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * The lazy view: vw::stereo::PyramidCorrelationView (src/vw/Stereo/CorrelationView.h:35-193,
  * CorrelationView.cc:273-886) behind a handle.  vwb200_corr_params mirrors the constructor
  * arguments (CorrelationView.h:48-69) that the block-matching algorithm uses.

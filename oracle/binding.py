@@ -273,5 +273,23 @@ def build_pyramids(params, left, right, lmask=None, rmask=None, bbox=None, level
     return out
 
 
+def parabola_subpixel(disp, left, right, kernel, prefilter_mode=0, prefilter_width=0.0, bbox=None):
+    d = np.ascontiguousarray(disp, np.float32)
+    l, r = _f32(left), _f32(right)
+    rows, cols = l.shape
+    assert d.shape == (rows, cols, 3)
+    if bbox is None:
+        bbox = (0, 0, cols, rows)
+    out = np.empty((bbox[3] - bbox[1], bbox[2] - bbox[0], 3), np.float32)
+    f = lib().vwo_parabola_subpixel
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                  C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rc = f(_p(d), cols, rows, _p(l), cols, _p(r), r.shape[1], r.shape[0], r.shape[1], kernel[0], kernel[1],
+           prefilter_mode, prefilter_width, bbox[0], bbox[1], bbox[2], bbox[3], _p(out))
+    if rc:
+        raise ValueError(rc)
+    return out
+
+
 def max_threads():
     return lib().vwo_max_threads()

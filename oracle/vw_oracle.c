@@ -711,6 +711,166 @@ int vwo_build_pyramids(const vwo_corr_params* p, const vwo_corr_inputs* in,
 }
 void vwo_free(void* p) { free(p); }
 
+
+/* ------------------------------------------------------------------ ParabolaSubpixelView */
+/* prefilter.filter(image) evaluated over an arbitrary region of the lazily edge-extended view, as
+ * crop(prefilter.filter(img), region) does in ParabolaSubpixelView::prerasterize (ParabolaSubpixelView.cc:296-327):
+ *   NONE    : edge_extend(img, Constant)                                     (PreFilter.h:45-51)
+ *   MEANSUB : edge_extend(img) - gaussian_filter(img): the separable convolution of the replicate-extended
+ *             image, also at out-of-image coordinates                        (PreFilter.h:60-70, Convolution.h:275-297)
+ *   LOG     : laplacian over edge_extend(gaussian view, Constant): the stencil reads the in-image gaussian at
+ *             clamped coordinates                                            (PreFilter.h:53-58, Convolution.h:154-166) */
+static imgf_t filtered_region(const float* img, int w, int h, int pitch, int mode, float width, box_t reg) {
+  imgf_t o = crop_const_f(img, w, h, pitch, reg);
+  if (mode == VWO_PREFILTER_NONE) return o;
+  float k[512];
+  int n = gaussian_kernel((double)width, k, 512);
+  if (mode == VWO_PREFILTER_MEANSUB) {
+    if (n <= 0) { for (size_t i = 0; i < (size_t)o.w * o.h; ++i) o.d[i] = o.d[i] - o.d[i]; return o; }
+    box_t big = { reg.x0 - n, reg.y0 - n, reg.x1 + n, reg.y1 + n };
+    imgf_t e = crop_const_f(img, w, h, pitch, big);
+    float* g = (float*)malloc((size_t)e.w * e.h * sizeof(float));
+    vwo_separable_convolve(e.d, e.w, e.h, e.w, k, n, k, n, 0, g);
+    for (int y = 0; y < o.h; ++y)
+      for (int x = 0; x < o.w; ++x) o.d[(size_t)y * o.w + x] = o.d[(size_t)y * o.w + x] - g[(size_t)(y + n) * e.w + (x + n)];
+    free(g); free(e.d);
+    return o;
+  }
+  /* LOG */
+  box_t need = { clampi(reg.x0 - 1, 0, w - 1), clampi(reg.y0 - 1, 0, h - 1), clampi(reg.x1, 0, w - 1) + 1, clampi(reg.y1, 0, h - 1) + 1 };
+  int m = n > 0 ? n : 0;
+  box_t big = { need.x0 - m, need.y0 - m, need.x1 + m, need.y1 + m };
+  imgf_t e = crop_const_f(img, w, h, pitch, big);
+  float* g = (float*)malloc((size_t)e.w * e.h * sizeof(float));
+  if (n > 0) vwo_separable_convolve(e.d, e.w, e.h, e.w, k, n, k, n, 0, g);
+  else memcpy(g, e.d, (size_t)e.w * e.h * sizeof(float));
+#define GAT(X, Y) g[(size_t)(clampi((Y), 0, h - 1) - big.y0) * e.w + (clampi((X), 0, w - 1) - big.x0)]
+  for (int y = 0; y < o.h; ++y)
+    for (int x = 0; x < o.w; ++x) {
+      int gx = reg.x0 + x, gy = reg.y0 + y;
+      float r = 0.0f;
+      r = r + 1.0f * GAT(gx, gy - 1);
+      r = r + 1.0f * GAT(gx - 1, gy);
+      r = r + -4.0f * GAT(gx, gy);
+      r = r + 1.0f * GAT(gx + 1, gy);
+      r = r + 1.0f * GAT(gx, gy + 1);
+      o.d[(size_t)y * o.w + x] = r;
+    }
+#undef GAT
+  free(g); free(e.d);
+  return o;
+}
+
+/* ParabolaSubpixelView::prerasterize + evaluate (Stereo/ParabolaSubpixelView.cc:31-330).
+ * disp: cols x rows x {dx,dy,valid} floats (the integer disparity as PixelMask<Vector2f>); out: bbox-sized. */
+int vwo_parabola_subpixel(const float* disp, int cols, int rows, const float* left, int lpitch,
+                          const float* right, int rcols, int rrows, int rpitch,
+                          int kx, int ky, int prefilter_mode, float prefilter_width,
+                          int bx0, int by0, int bx1, int by1, float* out) {
+  const int bw = bx1 - bx0, bh = by1 - by0;
+  if (bw <= 0 || bh <= 0 || bx0 < 0 || by0 < 0 || bx1 > cols || by1 > rows) return -1;
+  if (kx % 2 != 1 || ky % 2 != 1) return -2;
+  /* integer_disparity = crop(m_disparity, bbox) as PixelMask<Vector2i>: float -> int truncation (:292) */
+  vwo_disp_t* id = (vwo_disp_t*)malloc((size_t)bw * bh * sizeof(vwo_disp_t));
+  int mnx = 0, mny = 0, mxx = 0, mxy = 0, any = 0;
+  for (int y = 0; y < bh; ++y)
+    for (int x = 0; x < bw; ++x) {
+      const float* p = disp + ((size_t)(by0 + y) * cols + (bx0 + x)) * 3;
+      vwo_disp_t v = { (int)p[0], (int)p[1], p[2] != 0.0f };
+      id[(size_t)y * bw + x] = v;
+      if (v.valid) {      /* get_disparity_range (DisparityMap.h:52-66) */
+        if (!any) { mnx = mxx = v.dx; mny = mxy = v.dy; any = 1; }
+        if (v.dx < mnx) mnx = v.dx; if (v.dx > mxx) mxx = v.dx;
+        if (v.dy < mny) mny = v.dy; if (v.dy > mxy) mxy = v.dy;
+      }
+    }
+  /* entire_search_range: max += 1; expand(1)  (:296-299) */
+  box_t sr = { mnx, mny, mxx + 1, mxy + 1 };
+  sr = box_expand(sr, 1, 1);
+  const int hkx = kx / 2, hky = ky / 2;
+  box_t lreg = { bx0 - hkx, by0 - hky, bx1 + hkx, by1 + hky };                                   /* :302-305 */
+  box_t rreg = { lreg.x0 + sr.x0, lreg.y0 + sr.y0, lreg.x1 + sr.x0 + (sr.x1 - sr.x0), lreg.y1 + sr.y0 + (sr.y1 - sr.y0) };
+  imgf_t L = filtered_region(left, cols, rows, lpitch, prefilter_mode, prefilter_width, lreg);
+  imgf_t R = filtered_region(right, rcols, rrows, rpitch, prefilter_mode, prefilter_width, rreg);
+  float* patch = (float*)calloc((size_t)bw * bh * 9, sizeof(float));
+  /* zones (:74-104) */
+  zlist_t big = { 0, 0, 0 }, zones = { 0, 0, 0 };
+  subdivide(id, bw, bh, box_xywh(0, 0, bw, bh), &big, kx, ky, 0);
+  for (int zi = 0; zi < big.n; ++zi) {
+    zone_t z = big.z[zi];
+    double len1 = (double)box_area(z.img), len2 = (double)box_area(z.disp);
+    if (len2 / len1 < 1.0) { zpush(&zones, z.img, z.disp); continue; }
+    for (int x = z.img.x0; x < z.img.x1; ++x)
+      for (int y = z.img.y0; y < z.img.y1; ++y) {
+        vwo_disp_t v = id[(size_t)y * bw + x];
+        if (!v.valid) continue;
+        box_t d = { v.dx, v.dy, v.dx + 1, v.dy + 1 };
+        zpush(&zones, box_xywh(x, y, 1, 1), d);
+      }
+  }
+  for (int zi = 0; zi < zones.n; ++zi) {                                                         /* :107-224 */
+    zone_t z = zones.z[zi];
+    z.disp = box_expand(z.disp, 1, 1);
+    const int zw = z.img.x1 - z.img.x0, zh = z.img.y1 - z.img.y0;
+    const int cw = zw + kx - 1, ch = zh + ky - 1;
+    double* applied = (double*)malloc((size_t)cw * ch * sizeof(double));
+    double* metric = (double*)malloc((size_t)zw * zh * sizeof(double));
+    for (int ddx = 0; ddx < z.disp.x1 - z.disp.x0; ++ddx)
+      for (int ddy = 0; ddy < z.disp.y1 - z.disp.y0; ++ddy) {
+        const int ax = ddx + z.disp.x0, ay = ddy + z.disp.y0;
+        for (int y = 0; y < ch; ++y)
+          for (int x = 0; x < cw; ++x) {
+            float a = L.d[(size_t)(z.img.y0 + y) * L.w + (z.img.x0 + x)];
+            float b = R.d[(size_t)(z.img.y0 + y + ay - sr.y0) * R.w + (z.img.x0 + x + ax - sr.x0)];
+            applied[(size_t)y * cw + x] = (double)fabsf(a - b);
+          }
+        vwo_fast_box_sum(applied, cw, ch, cw, kx, ky, metric);
+        for (int y = 0; y < zh; ++y)
+          for (int x = 0; x < zw; ++x) {
+            const vwo_disp_t v = id[(size_t)(z.img.y0 + y) * bw + (z.img.x0 + x)];
+            const int ex = ax - v.dx, ey = ay - v.dy;
+            if (ex >= -1 && ex <= 1 && ey >= -1 && ey <= 1)
+              patch[((size_t)(z.img.y0 + y) * bw + (z.img.x0 + x)) * 9 + (ey + 1) * 3 + (ex + 1)] = (float)metric[(size_t)y * zw + x];
+          }
+      }
+    free(applied); free(metric);
+  }
+  /* pinvA (ParabolaSubpixelView.h:82-88), float */
+  static const double pd[54] = {
+     1.0/6, -1.0/3,  1.0/6,  1.0/6, -1.0/3,  1.0/6,   1.0/6, -1.0/3,  1.0/6,
+     1.0/6,  1.0/6,  1.0/6, -1.0/3, -1.0/3, -1.0/3,   1.0/6,  1.0/6,  1.0/6,
+     1.0/4,    0.0, -1.0/4,    0.0,    0.0,    0.0,  -1.0/4,    0.0,  1.0/4,
+    -1.0/6,    0.0,  1.0/6, -1.0/6,    0.0,  1.0/6,  -1.0/6,    0.0,  1.0/6,
+    -1.0/6, -1.0/6, -1.0/6,    0.0,    0.0,    0.0,   1.0/6,  1.0/6,  1.0/6,
+    -1.0/9,  2.0/9, -1.0/9,  2.0/9,   5.0/9, 2.0/9,  -1.0/9,  2.0/9, -1.0/9 };
+  float pinv[54];
+  for (int i = 0; i < 54; ++i) pinv[i] = (float)pd[i];
+  for (int y = 0; y < bh; ++y)                                                                      /* :230-275 */
+    for (int x = 0; x < bw; ++x) {
+      const vwo_disp_t v = id[(size_t)y * bw + x];
+      float* o = out + ((size_t)y * bw + x) * 3;
+      const float* c = patch + ((size_t)y * bw + x) * 9;
+      if (!v.valid) { o[0] = o[1] = o[2] = 0.0f; continue; }
+      o[0] = (float)v.dx; o[1] = (float)v.dy; o[2] = 1.0f;
+      int alleq = 1;
+      for (int k = 1; k < 9; ++k) if (c[k] != c[k - 1]) alleq = 0;     /* std::equal(begin+1,end,begin) */
+      if (alleq) continue;
+      float xs[6];
+      for (int r = 0; r < 6; ++r) { float acc = 0.0f; for (int k = 0; k < 9; ++k) { float pr = pinv[r * 9 + k] * c[k]; acc = acc + pr; } xs[r] = acc; }
+      float t1 = 4 * xs[0]; t1 = t1 * xs[1];
+      float t2 = xs[2] * xs[2];
+      float denom = t1 - t2;
+      float n1a = xs[2] * xs[4], n1b = 2 * xs[1]; n1b = n1b * xs[3];
+      float n2a = xs[2] * xs[3], n2b = 2 * xs[0]; n2b = n2b * xs[4];
+      float ox = (n1a - n1b) / denom, oy = (n2a - n2b) / denom;
+      double nn = 0.0; { float q = ox * ox; nn += q; q = oy * oy; nn += q; }
+      nn = (double)(float)nn;
+      if (sqrt(nn) < 5.0) { o[0] = (float)v.dx + ox; o[1] = (float)v.dy + oy; }
+    }
+  free(big.z); free(zones.z); free(patch); free(L.d); free(R.d); free(id);
+  return 0;
+}
+
 static int zone_cmp(const void* a, const void* b) {                                /* Correlation.h:87-91 */
   const zone_t *A = (const zone_t*)a, *B = (const zone_t*)b;
   double va = (double)box_w(A->img) * (double)box_h(A->img) * (double)box_w(A->disp) * (double)box_h(A->disp);

@@ -120,6 +120,13 @@ int vwo_build_pyramids(const vwo_corr_params* p, const vwo_corr_inputs* in,
                        int32_t* dims /* 8 ints per level: lw,lh,rw,rh,lmw,lmh,rmw,rmh */);
 void vwo_free(void* p);
 
+/* vw::stereo::ParabolaSubpixelView (Stereo/ParabolaSubpixelView.h:27-117, .cc:31-330): disp is the integer
+ * disparity as cols x rows PixelMask<Vector2f> triples; out is the bbox-sized refined disparity. */
+int vwo_parabola_subpixel(const float* disp, int cols, int rows, const float* left, int lpitch,
+                          const float* right, int rcols, int rrows, int rpitch,
+                          int kx, int ky, int prefilter_mode, float prefilter_width,
+                          int bx0, int by0, int bx1, int by1, float* out);
+
 /* number of pyramid levels prerasterize would use for this bbox (CorrelationView.cc:301-310,
  * CorrelationView.h:99-105) */
 int vwo_num_levels(const vwo_corr_params* p, int bw, int bh);

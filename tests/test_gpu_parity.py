@@ -275,3 +275,52 @@ def test_view_with_prefilter(vwb, oracle, mode):
                            filter_half_kernel=3, max_pyramid_levels=3)
     ref = oracle.pyramid_correlate(p, left, right, lm, rm)
     _assert_disp_equal(got, ref, f"prefilter {mode}")
+
+
+def _subpixel_case(rng, W=120, H=90, stretch=0.95):
+    base = np.floor(rng.random((H, W + 20)) * 1024).astype(np.float32)
+    base = np.floor((base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, -1, 0) + np.roll(base, -1, 1)) / 5)
+    left = np.ascontiguousarray(base[:, :W])
+    xs = np.arange(W) * stretch
+    x0 = np.floor(xs).astype(int)
+    f = (xs - x0).astype(np.float32)
+    right = np.floor(base[:, np.clip(x0, 0, W + 18)] * (1 - f) + base[:, np.clip(x0 + 1, 0, W + 18)] * f).astype(np.float32)
+    true = np.arange(W) / stretch - np.arange(W)
+    disp = np.zeros((H, W, 3), np.float32)
+    disp[..., 0] = np.rint(true)[None, :]
+    disp[..., 1] = rng.integers(-1, 2, (H, W))
+    disp[..., 2] = rng.random((H, W)) > 0.1
+    return disp, left, right
+
+
+@pytest.mark.parametrize("mode,width", [(0, 0.0), (1, 1.4), (2, 1.4)])
+def test_parabola_subpixel(vwb, oracle, mode, width):
+    """Stereo/ParabolaSubpixelView.cc:31-330 (a11).  north_star: sub-pixel floats agree within 1e-5; validity and
+    the untouched integer parts are exact.  bboxes touch the image border (edge-extended prefilter semantics)."""
+    rng = np.random.default_rng(51)
+    disp, left, right = _subpixel_case(rng)
+    view = vwb.parabola_subpixel(disp, left, right, mode, width, (7, 7))
+    for bbox in [(0, 0, 120, 90), (10, 5, 70, 60), (64, 32, 120, 90)]:
+        got = view.rasterize(None, bbox)
+        ref = oracle.parabola_subpixel(disp, left, right, (7, 7), mode, width, bbox)
+        assert np.array_equal(got[..., 2], ref[..., 2])
+        np.testing.assert_allclose(got[..., :2], ref[..., :2], rtol=0, atol=1e-5)
+    with pytest.raises(vwb.NoImplErr):
+        view(0, 0)
+
+
+def test_parabola_subpixel_reference_kat(vwb):
+    """Stereo/tests/TestSubPixel.cxx:95-139: constant images leave (1,1) untouched; a 95 % stretch is recovered with
+    mean error well below the integer rounding error (< 0.6 px in the reference test)."""
+    const = np.full((50, 50), 7.0, np.float32)
+    d = np.zeros((50, 50, 3), np.float32)
+    d[..., 0] = 1; d[..., 1] = 1; d[..., 2] = 1
+    o = vwb.parabola_subpixel(d, const, const, 0, 0.0, (7, 7)).rasterize()
+    assert np.abs(o[..., :2] - 1).max() <= 0.1 and (o[..., 2] == 1).all()
+    rng = np.random.default_rng(52)
+    disp, left, right = _subpixel_case(rng)
+    disp[..., 1] = 0; disp[..., 2] = 1
+    o = vwb.parabola_subpixel(disp, left, right, 0, 0.0, (7, 7)).rasterize()
+    true = np.arange(120) / 0.95 - np.arange(120)
+    err = np.abs(o[10:80, 10:100, 0] - true[None, 10:100]).mean()
+    assert err < 0.6 and err < np.abs(np.rint(true) - true)[10:100].mean()

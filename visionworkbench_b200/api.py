@@ -89,6 +89,7 @@ def lib():
         L.vwb200_pyramid_down.argtypes = [P, I, I, Z, P, Z, I, P]
         L.vwb200_subsample_mask_by_two.argtypes = [P, I, I, Z, P, Z, I, P]
         L.vwb200_prefilter.argtypes = [P, I, I, Z, I, F, P, Z, I, P]
+        L.vwb200_parabola_subpixel.argtypes = [P, I, I, P, Z, P, I, I, Z, I, I, I, F, I, I, I, I, P, Z, I, P]
         L.vwb200_cross_corr_consistency_check.argtypes = [P, I, I, Z, P, I, I, Z, F, I, P]
         L.vwb200_rm_outliers_using_thresh.argtypes = [P, I, I, I, I, D, D, P, I, P]
         L.vwb200_disparity_cleanup_using_thresh.argtypes = [P, I, I, I, I, D, D, P, I, P]
@@ -233,6 +234,48 @@ def disparity_mask(disparity_map, left_mask, right_mask):
     _check(lib().vwb200_disparity_mask(a.ctypes.data, a.shape[1], a.shape[0], lm.ctypes.data, rm.ctypes.data,
                                        rm.shape[1], rm.shape[0], out.ctypes.data, 0, None))
     return out
+
+
+class ParabolaSubpixelView:
+    """vw::stereo::ParabolaSubpixelView (Stereo/ParabolaSubpixelView.h:27-117): lazy view refining an integer
+    disparity (PixelMask<Vector2f> triples, same size as the left image) by a 2-D parabola fit."""
+
+    def __init__(self, disparity, left_image, right_image, prefilter_mode, prefilter_width, kernel_size):
+        self._d = _np(disparity, np.float32)
+        self._l, self._r = _np(left_image, np.float32), _np(right_image, np.float32)
+        if self._d.shape[:2] != self._l.shape:
+            raise ArgumentErr("SubpixelView: Disparity image must match left image.")
+        self._mode, self._width, self._k = int(prefilter_mode), float(prefilter_width), (int(kernel_size[0]), int(kernel_size[1]))
+
+    def cols(self):
+        return self._l.shape[1]
+
+    def rows(self):
+        return self._l.shape[0]
+
+    def planes(self):
+        return 1
+
+    def __call__(self, i, j, p=0):
+        raise NoImplErr("SubpixelView:operator() has not been implemented.")
+
+    def rasterize(self, dest=None, bbox=None):
+        b = _bbox(bbox) if bbox is not None else (0, 0, self.cols(), self.rows())
+        w, h = b[2] - b[0], b[3] - b[1]
+        if dest is None:
+            dest = np.empty((h, w, 3), np.float32)
+        _check(lib().vwb200_parabola_subpixel(self._d.ctypes.data, self.cols(), self.rows(), self._l.ctypes.data, self._l.shape[1],
+                                              self._r.ctypes.data, self._r.shape[1], self._r.shape[0], self._r.shape[1],
+                                              self._k[0], self._k[1], self._mode, self._width, b[0], b[1], b[2], b[3],
+                                              dest.ctypes.data, dest.strides[0] // 12, 0, None))
+        return dest
+
+    prerasterize = rasterize
+
+
+def parabola_subpixel(disparity, left_image, right_image, prefilter_mode, prefilter_width, kernel_size):
+    """vw::stereo::parabola_subpixel (Stereo/ParabolaSubpixelView.h:111-117)."""
+    return ParabolaSubpixelView(disparity, left_image, right_image, prefilter_mode, prefilter_width, kernel_size)
 
 
 class BBox2i:

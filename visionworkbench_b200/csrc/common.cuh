@@ -109,6 +109,13 @@ int disparity_mask_launch(const vwb200_dispi* in, int w, int h, ImgB lmask, ImgB
 int finalize_launch(const vwb200_dispi* in, int w, int h, int ax, int ay, float* out, ptrdiff_t opitch_px,
                     int ox, int oy, int ow, int oh, cudaStream_t st);
 
+// ---- a11 ParabolaSubpixelView -------------------------------------------------------------------------
+int disp_range_launch(const float* disp, int cols, int bx0, int by0, int bw, int bh, int* d_r5, cudaStream_t st);
+int meansub_region_launch(const float* e, const float* g, int ew, int m, int w, int h, float* out, cudaStream_t st);
+int log_region_launch(const float* g, int gw, int gx0, int gy0, int iw, int ih, int rx0, int ry0, int w, int h, float* out, cudaStream_t st);
+int parabola_launch(const float* disp, int cols, int bx0, int by0, int bw, int bh, const float* L, int lw, const float* R, int rw,
+                    int srx0, int sry0, int kx, int ky, float* out, cudaStream_t st);
+
 // ---- host-side restatement-free logic -----------------------------------------------------------
 struct Box { int x0, y0, x1, y1; };
 struct HostZone { Box img; Box disp; };

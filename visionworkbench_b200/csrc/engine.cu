@@ -278,6 +278,37 @@ static int prefilter_inplace(float* img, int w, int h, int mode, float width, Ar
   return VWB200_OK;
 }
 
+// prefilter.filter(image) over an arbitrary region of the lazily edge-extended view (what
+// crop(prefilter.filter(img), region) yields in ParabolaSubpixelView::prerasterize, .cc:296-327).
+static int filtered_region(ImgF img, int mode, float width, Box reg, float** out, Arena& ar, cudaStream_t st) {
+  const int w = reg.x1 - reg.x0, h = reg.y1 - reg.y0;
+  float* o;
+  VWB_TRY(ar.alloc(&o, (size_t)w * h));
+  *out = o;
+  if (mode == VWB200_PREFILTER_NONE) return crop_extend_f32_launch(img, reg.x0, reg.y0, w, h, o, w, st);
+  if (mode != VWB200_PREFILTER_LOG && mode != VWB200_PREFILTER_MEANSUB) { set_error("unknown prefilter mode %d", mode); return VWB200_EARG; }
+  const std::vector<float> taps = gaussian_taps((double)width);
+  const int n = (int)taps.size();
+  float* d_taps;
+  VWB_TRY(ar.alloc(&d_taps, taps.size() + 1));
+  if (n) { VWB_CUDA(cudaMemcpyAsync(d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice, st)); VWB_CUDA(cudaStreamSynchronize(st)); }
+  auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+  Box big;
+  if (mode == VWB200_PREFILTER_MEANSUB) big = Box{reg.x0 - n, reg.y0 - n, reg.x1 + n, reg.y1 + n};
+  else {
+    const Box need{clampi(reg.x0 - 1, 0, img.w - 1), clampi(reg.y0 - 1, 0, img.h - 1), clampi(reg.x1, 0, img.w - 1) + 1, clampi(reg.y1, 0, img.h - 1) + 1};
+    big = Box{need.x0 - n, need.y0 - n, need.x1 + n, need.y1 + n};
+  }
+  const int ew = big.x1 - big.x0, eh = big.y1 - big.y0;
+  float *e, *g, *work;
+  VWB_TRY(ar.alloc(&e, (size_t)ew * eh)); VWB_TRY(ar.alloc(&g, (size_t)ew * eh)); VWB_TRY(ar.alloc(&work, (size_t)ew * eh));
+  VWB_TRY(crop_extend_f32_launch(img, big.x0, big.y0, ew, eh, e, ew, st));
+  if (n) VWB_TRY(sepconv_launch(ImgF{e, ew, eh, ew}, d_taps, n, work, g, st));
+  else VWB_CUDA(cudaMemcpyAsync(g, e, (size_t)ew * eh * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (mode == VWB200_PREFILTER_MEANSUB) return meansub_region_launch(e, g, ew, n, w, h, o, st);
+  return log_region_launch(g, ew, big.x0, big.y0, img.w, img.h, reg.x0, reg.y0, w, h, o, st);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // the view handle
 // ---------------------------------------------------------------------------------------------------
@@ -597,6 +628,48 @@ int vwb200_prefilter(const float* in, int w, int h, ptrdiff_t pitch, int mode, f
     VWB_CUDA(cudaMemcpy2DAsync(buf, (size_t)w * 4, in, (size_t)pitch * 4, (size_t)w * 4, h, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     VWB_TRY(prefilter_inplace(buf, w, h, mode, width, ar, st));
     VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch * 4, buf, (size_t)w * 4, (size_t)w * 4, h, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    VWB_CUDA(cudaStreamSynchronize(st));
+  }
+  return VWB200_OK;
+}
+
+int vwb200_parabola_subpixel(const float* disparity, int cols, int rows, const float* left, ptrdiff_t lpitch,
+                             const float* right, int rcols, int rrows, ptrdiff_t rpitch, int kx, int ky,
+                             int prefilter_mode, float prefilter_width, int x0, int y0, int x1, int y1,
+                             float* dest, ptrdiff_t dest_pitch, int on_device, void* stream) {
+  if (!disparity || !left || !right || !dest) { set_error("parabola_subpixel: null pointer"); return VWB200_EARG; }
+  if (x1 <= x0 || y1 <= y0 || x0 < 0 || y0 < 0 || x1 > cols || y1 > rows) { set_error("parabola_subpixel: bbox outside the disparity image"); return VWB200_EARG; }
+  if (kx % 2 != 1 || ky % 2 != 1 || kx < 1 || ky < 1) { set_error("parabola_subpixel: kernel size must be odd"); return VWB200_EARG; }
+  VWB_TRY(ensure_device());
+  StreamGuard sg; VWB_TRY(sg.init(stream));
+  cudaStream_t st = sg.st;
+  {
+    Arena ar(st);
+    const int bw = x1 - x0, bh = y1 - y0;
+    const float *dd, *dl, *dr; ptrdiff_t p0, p1, p2;
+    VWB_TRY(stage_in(disparity, cols * 3, rows, (ptrdiff_t)cols * 3, on_device, ar, st, &dd, &p0));
+    VWB_TRY(stage_in(left, cols, rows, lpitch, on_device, ar, st, &dl, &p1));
+    VWB_TRY(stage_in(right, rcols, rrows, rpitch, on_device, ar, st, &dr, &p2));
+    int* d_r; int hr[5];
+    VWB_TRY(ar.alloc(&d_r, 5));
+    VWB_TRY(disp_range_launch(dd, cols, x0, y0, bw, bh, d_r, st));
+    VWB_CUDA(cudaMemcpyAsync(hr, d_r, sizeof(hr), cudaMemcpyDeviceToHost, st));
+    VWB_CUDA(cudaStreamSynchronize(st));
+    if (!hr[4]) { hr[0] = hr[1] = hr[2] = hr[3] = 0; }
+    // entire_search_range: max += 1, expand(1)  (ParabolaSubpixelView.cc:296-299)
+    const Box sr{hr[0] - 1, hr[1] - 1, hr[2] + 2, hr[3] + 2};
+    const int hkx = kx / 2, hky = ky / 2;
+    const Box lreg{x0 - hkx, y0 - hky, x1 + hkx, y1 + hky};
+    const Box rreg{lreg.x0 + sr.x0, lreg.y0 + sr.y0, lreg.x1 + sr.x0 + (sr.x1 - sr.x0), lreg.y1 + sr.y0 + (sr.y1 - sr.y0)};
+    float *Lf, *Rf;
+    VWB_TRY(filtered_region(ImgF{dl, cols, rows, p1}, prefilter_mode, prefilter_width, lreg, &Lf, ar, st));
+    VWB_TRY(filtered_region(ImgF{dr, rcols, rrows, p2}, prefilter_mode, prefilter_width, rreg, &Rf, ar, st));
+    float* dout = dest;
+    if (!on_device || dest_pitch != bw) VWB_TRY(ar.alloc(&dout, (size_t)bw * bh * 3));
+    VWB_TRY(parabola_launch(dd, cols, x0, y0, bw, bh, Lf, lreg.x1 - lreg.x0, Rf, rreg.x1 - rreg.x0, sr.x0, sr.y0, kx, ky, dout, st));
+    if (dout != dest)
+      VWB_CUDA(cudaMemcpy2DAsync(dest, (size_t)dest_pitch * 12, dout, (size_t)bw * 12, (size_t)bw * 12, bh,
+                                 on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
     VWB_CUDA(cudaStreamSynchronize(st));
   }
   return VWB200_OK;

@@ -191,4 +191,133 @@ int finalize_launch(const vwb200_dispi* in, int w, int h, int ax, int ay, float*
   return VWB200_OK;
 }
 
+
+// ====================================================================================================
+// a11: ParabolaSubpixelView (Stereo/ParabolaSubpixelView.cc:31-330)
+// ====================================================================================================
+// min / max of the truncated integer disparity over the valid pixels of a bbox crop (get_disparity_range,
+// Stereo/DisparityMap.h:52-66).  r[0..3] = minx, miny, maxx, maxy ; r[4] = any valid
+__global__ void disp_range_kernel(const float* __restrict__ disp, int cols, int bx0, int by0, int bw, int bh, int* __restrict__ r) {
+  int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN, any = 0;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < (long long)bw * bh; k += (long long)gridDim.x * blockDim.x) {
+    const float* p = disp + ((ptrdiff_t)(by0 + (int)(k / bw)) * cols + bx0 + (int)(k % bw)) * 3;
+    if (p[2] != 0.0f) { const int dx = (int)p[0], dy = (int)p[1]; mnx = min(mnx, dx); mxx = max(mxx, dx); mny = min(mny, dy); mxy = max(mxy, dy); any = 1; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    any |= __shfl_xor_sync(0xffffffffu, any, o);
+  }
+  if ((threadIdx.x & 31) == 0 && any) { atomicMin(r + 0, mnx); atomicMin(r + 1, mny); atomicMax(r + 2, mxx); atomicMax(r + 3, mxy); atomicExch(r + 4, 1); }
+}
+int disp_range_launch(const float* disp, int cols, int bx0, int by0, int bw, int bh, int* d_r5, cudaStream_t st) {
+  const int init[5] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN, 0};
+  VWB_CUDA(cudaMemcpyAsync(d_r5, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  VWB_CUDA(cudaStreamSynchronize(st));
+  disp_range_kernel<<<148, 256, 0, st>>>(disp, cols, bx0, by0, bw, bh, d_r5);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
+// out(x,y) = e(x+m, y+m) - g(x+m, y+m): SubtractedMean over a region of the replicate-extended image
+__global__ void meansub_region_kernel(const float* __restrict__ e, const float* __restrict__ g, int ew, int m, int w, int h, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const ptrdiff_t k = (ptrdiff_t)(y + m) * ew + (x + m);
+  out[(ptrdiff_t)y * w + x] = __fsub_rn(e[k], g[k]);
+}
+// LoG over a region: Laplacian stencil over the in-image gaussian read at clamped image coordinates
+__global__ void log_region_kernel(const float* __restrict__ g, int gw, int gx0, int gy0, int iw, int ih, int rx0, int ry0, int w, int h, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int cx = rx0 + x, cy = ry0 + y;
+#define GAT(X, Y) g[(ptrdiff_t)(clampi3((Y), 0, ih - 1) - gy0) * gw + (clampi3((X), 0, iw - 1) - gx0)]
+  float r = __fadd_rn(0.0f, __fmul_rn(1.0f, GAT(cx, cy - 1)));
+  r = __fadd_rn(r, __fmul_rn(1.0f, GAT(cx - 1, cy)));
+  r = __fadd_rn(r, __fmul_rn(-4.0f, GAT(cx, cy)));
+  r = __fadd_rn(r, __fmul_rn(1.0f, GAT(cx + 1, cy)));
+  r = __fadd_rn(r, __fmul_rn(1.0f, GAT(cx, cy + 1)));
+#undef GAT
+  out[(ptrdiff_t)y * w + x] = r;
+}
+int meansub_region_launch(const float* e, const float* g, int ew, int m, int w, int h, float* out, cudaStream_t st) {
+  dim3 b(32, 8), gr((w + 31) / 32, (h + 7) / 8);
+  meansub_region_kernel<<<gr, b, 0, st>>>(e, g, ew, m, w, h, out);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+int log_region_launch(const float* g, int gw, int gx0, int gy0, int iw, int ih, int rx0, int ry0, int w, int h, float* out, cudaStream_t st) {
+  dim3 b(32, 8), gr((w + 31) / 32, (h + 7) / 8);
+  log_region_kernel<<<gr, b, 0, st>>>(g, gw, gx0, gy0, iw, ih, rx0, ry0, w, h, out);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
+// One thread per pixel: the 9 AbsoluteCost window sums around the integer disparity (double accumulation of float
+// |a-b|, exactly the values the reference's per-zone fast_box_sum produces when sums are exact), the 6x9 float
+// pseudo-inverse fit with the reference's operation order, offset kept if its norm is below 5
+// (ParabolaSubpixelView.h:82-88, .cc:230-275).
+__constant__ float c_pinv[54];
+__global__ void parabola_kernel(const float* __restrict__ disp, int cols, int bx0, int by0, int bw, int bh,
+                                const float* __restrict__ L, int lw, const float* __restrict__ R, int rw,
+                                int srx0, int sry0, int kx, int ky, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= bw || y >= bh) return;
+  const float* p = disp + ((ptrdiff_t)(by0 + y) * cols + bx0 + x) * 3;
+  float* o = out + ((ptrdiff_t)y * bw + x) * 3;
+  if (p[2] == 0.0f) { o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f; return; }
+  const int dx = (int)p[0], dy = (int)p[1];
+  float c[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int ex = k % 3 - 1, ey = k / 3 - 1;
+    // L raster origin = bbox.min - half kernel: window of pixel (x,y) starts at (x,y); R raster origin adds sr.min
+    const float* lp = L + (ptrdiff_t)y * lw + x;
+    const float* rp = R + (ptrdiff_t)(y + dy + ey - sry0) * rw + (x + dx + ex - srx0);
+    double s = 0.0;
+    for (int j = 0; j < ky; ++j)
+      for (int i = 0; i < kx; ++i) s += (double)fabsf(__fsub_rn(lp[(ptrdiff_t)j * lw + i], rp[(ptrdiff_t)j * rw + i]));
+    c[k] = (float)s;
+  }
+  o[0] = (float)dx; o[1] = (float)dy; o[2] = 1.0f;
+  bool alleq = true;
+#pragma unroll
+  for (int k = 1; k < 9; ++k) alleq = alleq && (c[k] == c[k - 1]);
+  if (alleq) return;
+  float xs[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc = __fadd_rn(acc, __fmul_rn(c_pinv[r * 9 + k], c[k]));
+    xs[r] = acc;
+  }
+  const float denom = __fsub_rn(__fmul_rn(__fmul_rn(4.0f, xs[0]), xs[1]), __fmul_rn(xs[2], xs[2]));
+  const float ox = __fdiv_rn(__fsub_rn(__fmul_rn(xs[2], xs[4]), __fmul_rn(__fmul_rn(2.0f, xs[1]), xs[3])), denom);
+  const float oy = __fdiv_rn(__fsub_rn(__fmul_rn(xs[2], xs[3]), __fmul_rn(__fmul_rn(2.0f, xs[0]), xs[4])), denom);
+  double nn = 0.0;
+  nn += (double)__fmul_rn(ox, ox);
+  nn += (double)__fmul_rn(oy, oy);
+  nn = (double)(float)nn;
+  if (sqrt(nn) < 5.0) { o[0] = __fadd_rn((float)dx, ox); o[1] = __fadd_rn((float)dy, oy); }
+}
+int parabola_launch(const float* disp, int cols, int bx0, int by0, int bw, int bh, const float* L, int lw, const float* R, int rw,
+                    int srx0, int sry0, int kx, int ky, float* out, cudaStream_t st) {
+  static const double pd[54] = {
+     1.0/6, -1.0/3,  1.0/6,  1.0/6, -1.0/3,  1.0/6,   1.0/6, -1.0/3,  1.0/6,
+     1.0/6,  1.0/6,  1.0/6, -1.0/3, -1.0/3, -1.0/3,   1.0/6,  1.0/6,  1.0/6,
+     1.0/4,    0.0, -1.0/4,    0.0,    0.0,    0.0,  -1.0/4,    0.0,  1.0/4,
+    -1.0/6,    0.0,  1.0/6, -1.0/6,    0.0,  1.0/6,  -1.0/6,    0.0,  1.0/6,
+    -1.0/6, -1.0/6, -1.0/6,    0.0,    0.0,    0.0,   1.0/6,  1.0/6,  1.0/6,
+    -1.0/9,  2.0/9, -1.0/9,  2.0/9,   5.0/9, 2.0/9,  -1.0/9,  2.0/9, -1.0/9 };
+  float pf[54];
+  for (int i = 0; i < 54; ++i) pf[i] = (float)pd[i];
+  VWB_CUDA(cudaMemcpyToSymbolAsync(c_pinv, pf, sizeof(pf), 0, cudaMemcpyHostToDevice, st));
+  VWB_CUDA(cudaStreamSynchronize(st));
+  dim3 b(32, 8), g((bw + 31) / 32, (bh + 7) / 8);
+  parabola_kernel<<<g, b, 0, st>>>(disp, cols, bx0, by0, bw, bh, L, lw, R, rw, srx0, sry0, kx, ky, out);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
 }  // namespace vwb200
