@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <algorithm>
@@ -52,7 +53,7 @@ int ensure_device() {
 }
 
 int zone_post_launch(const Tile* d_tiles, int ntiles, const Zone* d_zones, const Zone* d_rlzones, const int2* d_post_add,
-                     vwb200_dispi* disp, const vwb200_dispi* rl, float thr, int tile, cudaStream_t st);
+                     vwb200_dispi* disp, const vwb200_dispi* rl, float thr, int tile_w, int tile_h, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------
 // small RAII helpers: stream-ordered device buffers, an owned-or-borrowed stream
@@ -82,11 +83,11 @@ struct StreamGuard {
   ~StreamGuard() { if (own && st) cudaStreamDestroy(st); }
 };
 
-static void make_tiles(const std::vector<Zone>& zones, int tile, std::vector<Tile>& tiles) {
+static void make_tiles(const std::vector<Zone>& zones, int tile_w, int tile_h, std::vector<Tile>& tiles) {
   tiles.clear();
   for (size_t zi = 0; zi < zones.size(); ++zi)
-    for (int ty = 0; ty < zones[zi].h; ty += tile)
-      for (int tx = 0; tx < zones[zi].w; tx += tile) tiles.push_back(Tile{(int)zi, tx, ty, 0});
+    for (int ty = 0; ty < zones[zi].h; ty += tile_h)
+      for (int tx = 0; tx < zones[zi].w; tx += tile_w) tiles.push_back(Tile{(int)zi, tx, ty, 0});
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -98,7 +99,7 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, const std::vector<Zone>
                         const Tile** d_tiles_out = nullptr, int* ntiles_out = nullptr, const KEvents* ev = nullptr) {
   if (zones.empty()) { if (ntiles_out) *ntiles_out = 0; return VWB200_OK; }
   std::vector<Tile> tiles;
-  make_tiles(zones, k1_generic_tile_w(kx), tiles);
+  make_tiles(zones, k1_generic_tile_w(kx), k1_generic_tile_h(ky), tiles);
   Zone* d_zones; Tile* d_tiles;
   VWB_TRY(ar.alloc(&d_zones, zones.size()));
   VWB_TRY(ar.alloc(&d_tiles, tiles.size()));
@@ -418,7 +419,7 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
   zones.push_back(HostZone{Box{0, 0, py[levels].lmw, py[levels].lmh}, Box{0, 0, ssx / up + 1, ssy / up + 1}});   // :338-342
   vwb200_dispi* disp = nullptr;
   std::vector<vwb200_dispi> hdisp;
-  const int tile = k1_generic_tile_w(kx);
+  const int tile_w = k1_generic_tile_w(kx), tile_h = k1_generic_tile_h(ky);
   for (int level = levels; level >= 0; --level) {
     const LevelImgs& lv = py[level];
     const int scaling = 1 << level;
@@ -451,6 +452,11 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
         zr.push_back(q);
       }
     }
+    if (getenv("VWB200_DEBUG")) {
+      long long evals = 0, maxd = 0, big = 0; int nbig = 0;
+      for (const Zone& z : zl) { long long e = (long long)z.w * z.h * z.sx * z.sy; evals += e; if ((long long)z.sx * z.sy > maxd) maxd = (long long)z.sx * z.sy; if ((long long)z.sx * z.sy > 400) { ++nbig; big += e; } }
+      fprintf(stderr, "[vwb200] level %d: %zu zones, %lld evals, max search %lld, %d zones with >400 disparities (%lld evals)\n", level, zl.size(), evals, maxd, nbig, big);
+    }
     const ImgF Ll{lv.l, lv.lw, lv.lh, lv.lw}, Rl{lv.r, lv.rw, lv.rh, lv.rw};
     const Zone* d_zl = nullptr; const Tile* d_tl = nullptr; int ntl = 0;
     VWB_TRY(run_k1_zones(p.cost_type, Ll, Rl, zl, kx, ky, disp, ar, st, &d_zl, &d_tl, &ntl));
@@ -463,7 +469,7 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
       int2* d_post;
       VWB_TRY(ar.alloc(&d_post, post.size()));
       VWB_CUDA(cudaMemcpyAsync(d_post, post.data(), post.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-      VWB_TRY(zone_post_launch(d_tl, ntl, d_zl, d_zr, d_post, disp, rl, p.consistency_threshold, tile, st));
+      VWB_TRY(zone_post_launch(d_tl, ntl, d_zl, d_zr, d_post, disp, rl, p.consistency_threshold, tile_w, tile_h, st));
     }
     if (p.filter_half_kernel > 0) {   // :713-744
       const int fh = p.filter_half_kernel;

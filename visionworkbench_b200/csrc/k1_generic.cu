@@ -30,8 +30,8 @@ static constexpr int IDX_MASK = 0x0fffffff;
 static constexpr int FLAG_DIFF = 0x40000000;
 static constexpr int FLAG_NAN = 0x20000000;
 
-int k1_generic_tile_w(int kx) { (void)kx; return K1G_TILE; }
-int k1_generic_tile_h(int ky) { (void)ky; return K1G_TILE; }
+int k1_generic_tile_w(int kx) { (void)kx; return 32; }
+int k1_generic_tile_h(int ky) { (void)ky; return 16; }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -50,6 +50,13 @@ __device__ __forceinline__ float ld_clamped(const ImgF& im, int x, int y) {
   return __ldg(im.p + (ptrdiff_t)clampi(y, 0, im.h - 1) * im.pitch + clampi(x, 0, im.w - 1));
 }
 
+// Zone kernel.  One CTA per ZT_W x ZT_H tile of a zone; the 8 warps work on different disparities at the same
+// time (d = warp, warp + 8, ...) with only warp-level synchronisation inside the disparity loop:
+//   phase 1  lane = padded column: vertical sliding sum of the per-pixel cost down the tile's rows -> V[warp][y][x']
+//   phase 2  lane = (row, half row): horizontal sliding sum over V, compare with the warp's private running best
+// After the loop the warps' private bests are merged (cost, then raster index: first disparity wins ties).
+static constexpr int ZT_W = 32, ZT_H = 16, ZWARPS = 8;
+
 template <int COST>
 __global__ void __launch_bounds__(K1G_THREADS)
 k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __restrict__ tiles,
@@ -57,94 +64,101 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Tile t = tiles[blockIdx.x];
   const Zone z = zones[t.zone];
-  const int tw = min(K1G_TILE, z.w - t.tx), th = min(K1G_TILE, z.h - t.ty);
+  const int tw = min(ZT_W, z.w - t.tx), th = min(ZT_H, z.h - t.ty);
   const int pw = tw + kx - 1;
-  const int vp = pw | 1;                                   // odd pitch: conflict-free row walking
-  double* V = reinterpret_cast<double*>(smem_raw);         // [th][vp]
-  double* best = V + (size_t)K1G_TILE * ((K1G_TILE + kx - 1) | 1);   // [th*tw]
-  int* bidx = reinterpret_cast<int*>(best + K1G_TILE * K1G_TILE);    // [th*tw]
-  const int tid = threadIdx.x, nth = blockDim.x;
-
-  // work decomposition
-  int S = nth / pw; if (S < 1) S = 1; { int m = th / 8; if (m < 1) m = 1; if (S > m) S = m; }
-  const int rps = (th + S - 1) / S;
-  int C = nth / th; if (C < 1) C = 1; { int m = tw / 8; if (m < 1) m = 1; if (C > m) C = m; }
-  const int cw = (tw + C - 1) / C;
-
-  const int lx0 = z.lx + t.tx, ly0 = z.ly + t.ty;          // left coords of the tile's padded origin
+  const int vp = (ZT_W + kx - 1) | 1;                         // odd pitch: conflict-free when lanes walk rows
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* Vall = reinterpret_cast<double*>(smem_raw);          // [ZWARPS][ZT_H][vp]
+  double* bestall = Vall + (size_t)ZWARPS * ZT_H * vp;         // [ZWARPS][ZT_H*ZT_W]
+  int* bidxall = reinterpret_cast<int*>(bestall + (size_t)ZWARPS * ZT_H * ZT_W);
+  double* V = Vall + (size_t)warp * ZT_H * vp;
+  double* best = bestall + (size_t)warp * ZT_H * ZT_W;
+  int* bidx = bidxall + (size_t)warp * ZT_H * ZT_W;
+  const int lx0 = z.lx + t.tx, ly0 = z.ly + t.ty;
   const int rx0 = z.rx + t.tx, ry0 = z.ry + t.ty;
-
-  for (int dy = 0; dy < z.sy; ++dy) {
-    for (int dx = 0; dx < z.sx; ++dx) {
-      // ---- phase 1: vertical sliding sums -------------------------------------------------------
-      for (int item = tid; item < pw * S; item += nth) {
-        const int xp = item % pw, s = item / pw;
-        const int yb = s * rps, ye = min(th, yb + rps);
-        if (yb < ye) {
-          const int gl = lx0 + xp, gr = rx0 + xp + dx;
-          double v = 0.0;
-          for (int j = 0; j < ky; ++j)
-            v += pix_cost<COST>(ld_clamped(L, gl, ly0 + yb + j), ld_clamped(R, gr, ry0 + yb + j + dy));
-          V[yb * vp + xp] = v;
-          for (int y = yb + 1; y < ye; ++y) {
-            v += pix_cost<COST>(ld_clamped(L, gl, ly0 + y + ky - 1), ld_clamped(R, gr, ry0 + y + ky - 1 + dy));
-            v -= pix_cost<COST>(ld_clamped(L, gl, ly0 + y - 1), ld_clamped(R, gr, ry0 + y - 1 + dy));
-            V[y * vp + xp] = v;
-          }
-        }
+  const int nd = z.sx * z.sy;
+  // phase-2 work split: lane -> (row, half)
+  const int halves = (2 * th <= 32) ? 2 : 1;
+  const int cw = (tw + halves - 1) / halves;
+  const int prow = lane / halves, phalf = lane % halves;
+  bool first = true;
+  for (int d = warp; d < nd; d += ZWARPS) {
+    const int dy = d / z.sx, dx = d - dy * z.sx;
+    // ---- phase 1 ----
+    for (int xp = lane; xp < pw; xp += 32) {
+      const int gl = lx0 + xp, gr = rx0 + xp + dx;
+      double v = 0.0;
+      for (int j = 0; j < ky; ++j) v += pix_cost<COST>(ld_clamped(L, gl, ly0 + j), ld_clamped(R, gr, ry0 + j + dy));
+      V[xp] = v;
+      for (int y = 1; y < th; ++y) {
+        v += pix_cost<COST>(ld_clamped(L, gl, ly0 + y + ky - 1), ld_clamped(R, gr, ry0 + y + ky - 1 + dy));
+        v -= pix_cost<COST>(ld_clamped(L, gl, ly0 + y - 1), ld_clamped(R, gr, ry0 + y - 1 + dy));
+        V[y * vp + xp] = v;
       }
-      __syncthreads();
-      // ---- phase 2: horizontal sliding sums + running best ---------------------------------------
-      const int d = dy * z.sx + dx;
-      for (int item = tid; item < th * C; item += nth) {
-        const int y = item % th, c = item / th;
-        const int xb = c * cw, xe = min(tw, xb + cw);
-        if (xb < xe) {
-          const double* vr = V + y * vp;
-          double h = 0.0;
-          for (int i = 0; i < kx; ++i) h += vr[xb + i];
-          for (int x = xb; x < xe; ++x) {
-            double cost = h;
-            if (COST == VWB200_CROSS_CORRELATION) {
-              const double lp = ncc.inv_l[(ptrdiff_t)(ly0 + y - ncc.l_oy) * ncc.l_w + (lx0 + x - ncc.l_ox)];
-              const double rp = ncc.inv_r[(ptrdiff_t)(ry0 + y + dy - ncc.r_oy) * ncc.r_w + (rx0 + x + dx - ncc.r_ox)];
-              cost = __dmul_rn(h, sqrt(__dmul_rn(lp, rp)));
-            }
-            const int k = y * tw + x;
-            if (d == 0) {
-              best[k] = cost;
-              bidx[k] = (cost != cost) ? FLAG_NAN : 0;
-            } else {
-              const double b = best[k];
-              int bi = bidx[k];
-              if (cost != b) bi |= FLAG_DIFF;
-              if (cost != cost) bi |= FLAG_NAN;
-              if (better<COST>(cost, b)) { best[k] = cost; bi = (bi & ~IDX_MASK) | d; }
-              bidx[k] = bi;
-            }
-            if (x + 1 < xe) h += vr[x + kx] - vr[x];
-          }
-        }
-      }
-      __syncthreads();
     }
+    __syncwarp();
+    // ---- phase 2 ----
+    if (prow < th) {
+      const int xb = phalf * cw, xe = min(tw, xb + cw);
+      if (xb < xe) {
+        const double* vr = V + prow * vp;
+        double h = 0.0;
+        for (int i = 0; i < kx; ++i) h += vr[xb + i];
+        for (int x = xb; x < xe; ++x) {
+          double cost = h;
+          if (COST == VWB200_CROSS_CORRELATION) {
+            const double lp = ncc.inv_l[(ptrdiff_t)(ly0 + prow - ncc.l_oy) * ncc.l_w + (lx0 + x - ncc.l_ox)];
+            const double rp = ncc.inv_r[(ptrdiff_t)(ry0 + prow + dy - ncc.r_oy) * ncc.r_w + (rx0 + x + dx - ncc.r_ox)];
+            cost = __dmul_rn(h, sqrt(__dmul_rn(lp, rp)));
+          }
+          const int k = prow * ZT_W + x;
+          if (first) {
+            best[k] = cost;
+            bidx[k] = d | ((cost != cost) ? FLAG_NAN : 0);
+          } else {
+            const double b = best[k];
+            int bi = bidx[k];
+            if (cost != b) bi |= FLAG_DIFF;
+            if (cost != cost) bi |= FLAG_NAN;
+            if (better<COST>(cost, b)) { best[k] = cost; bi = (bi & ~IDX_MASK) | d; }
+            bidx[k] = bi;
+          }
+          if (x + 1 < xe) h += vr[x + kx] - vr[x];
+        }
+      }
+    }
+    first = false;
+    __syncwarp();
   }
-  // ---- epilogue: coalesced-ish 12-byte pixel writes -------------------------------------------------
-  for (int k = tid; k < tw * th; k += nth) {
-    const int y = k / tw, x = k % tw;
-    const int bi = bidx[k];
-    const int d = bi & IDX_MASK;
+  __syncthreads();
+  // ---- merge the warps' private bests; epilogue: 12-byte pixel writes ----
+  const int nw = nd < ZWARPS ? nd : ZWARPS;
+  for (int k = threadIdx.x; k < tw * th; k += blockDim.x) {
+    const int y = k / tw, x = k - y * tw;
+    const int kk = y * ZT_W + x;
+    double b = bestall[kk];
+    int bi = bidxall[kk];
+    int flags = bi & (FLAG_DIFF | FLAG_NAN);
+    int d = bi & IDX_MASK;
+    for (int w = 1; w < nw; ++w) {
+      const double c = bestall[(size_t)w * ZT_H * ZT_W + kk];
+      const int ci = bidxall[(size_t)w * ZT_H * ZT_W + kk];
+      flags |= ci & (FLAG_DIFF | FLAG_NAN);
+      if (c != b) flags |= FLAG_DIFF;
+      const int cd = ci & IDX_MASK;
+      if (better<COST>(c, b) || (c == b && cd < d)) { b = c; d = cd; }
+    }
     vwb200_dispi o;
     o.dx = d % z.sx + z.addx;
     o.dy = d / z.sx + z.addy;
-    o.valid = (bi & FLAG_NAN) ? 2 : ((bi & FLAG_DIFF) ? 1 : 0);
+    o.valid = (flags & FLAG_NAN) ? 2 : ((flags & FLAG_DIFF) ? 1 : 0);
     out[z.obase + (ptrdiff_t)(t.ty + y) * z.opitch + (t.tx + x)] = o;
   }
 }
 
 static size_t k1g_smem_bytes(int kx) {
-  size_t vp = (size_t)((K1G_TILE + kx - 1) | 1);
-  return (size_t)K1G_TILE * vp * sizeof(double) + (size_t)K1G_TILE * K1G_TILE * (sizeof(double) + sizeof(int));
+  const size_t vp = (size_t)((ZT_W + kx - 1) | 1);
+  return (size_t)ZWARPS * ZT_H * vp * sizeof(double) + (size_t)ZWARPS * ZT_H * ZT_W * (sizeof(double) + sizeof(int));
 }
 
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
@@ -165,6 +179,7 @@ int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, cons
   if (ev && ev->e1) cudaEventRecord(ev->e1, st);
   return VWB200_OK;
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // 1 / boxsum(v*v): NCCCost's left_precision / right_precision (Stereo/CostFunctions.h:214-219).

@@ -41,10 +41,10 @@ int consistency_launch(vwb200_dispi* l2r, int lw, int lh, ptrdiff_t lpitch, cons
 // image, then "+= zone.disparity_range().min()" (CorrelationView.cc:691-698).  One launch per level.
 __global__ void zone_post_kernel(const Tile* __restrict__ tiles, const Zone* __restrict__ zones, const Zone* __restrict__ rlzones,
                                  const int2* __restrict__ post_add, vwb200_dispi* __restrict__ disp,
-                                 const vwb200_dispi* __restrict__ rl, float thr, int tile) {
+                                 const vwb200_dispi* __restrict__ rl, float thr, int tile_w, int tile_h) {
   const Tile t = tiles[blockIdx.x];
   const Zone z = zones[t.zone];
-  const int tw = min(tile, z.w - t.tx), th = min(tile, z.h - t.ty);
+  const int tw = min(tile_w, z.w - t.tx), th = min(tile_h, z.h - t.ty);
   const int2 add = post_add[t.zone];
   for (int k = threadIdx.x; k < tw * th; k += blockDim.x) {
     const int x = t.tx + k % tw, y = t.ty + k / tw;
@@ -58,9 +58,9 @@ __global__ void zone_post_kernel(const Tile* __restrict__ tiles, const Zone* __r
   }
 }
 int zone_post_launch(const Tile* d_tiles, int ntiles, const Zone* d_zones, const Zone* d_rlzones, const int2* d_post_add,
-                     vwb200_dispi* disp, const vwb200_dispi* rl, float thr, int tile, cudaStream_t st) {
+                     vwb200_dispi* disp, const vwb200_dispi* rl, float thr, int tile_w, int tile_h, cudaStream_t st) {
   if (ntiles <= 0) return VWB200_OK;
-  zone_post_kernel<<<ntiles, 256, 0, st>>>(d_tiles, d_zones, d_rlzones, d_post_add, disp, rl, thr, tile);
+  zone_post_kernel<<<ntiles, 128, 0, st>>>(d_tiles, d_zones, d_rlzones, d_post_add, disp, rl, thr, tile_w, tile_h);
   VWB_LAUNCH_CHECK();
   return VWB200_OK;
 }
