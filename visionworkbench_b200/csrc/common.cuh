@@ -54,9 +54,12 @@ struct Zone {
   int rx, ry;        // right_region.min in right image coordinates
   int sx, sy;        // search volume
   int addx, addy;    // constant added to the children by the K1 epilogue (R->L pass: -search size)
+  int nchunks;       // > 1: the disparity range is split over several CTAs (K1G_DCHUNK disparities each)
+  int pad0;
+  long long sbase;   // element offset of this zone's partial results in the scratch planes [chunk][h][w]
 };
-// One unit of work of the generic kernel: a TW x TH tile of a zone.
-struct Tile { int zone; int tx, ty; int pad; };
+// One unit of work of the generic kernel: a TW x TH tile of a zone (x one chunk of its disparity range).
+struct Tile { int zone; int tx, ty; int chunk; };
 
 // ---- K1 generic (fp64, any float input, zones) --------------------------------------------
 // cost: VWB200_* cost type.  inv_l / inv_r: for NCC, 1/boxsum(v^2) maps whose (0,0) sits at window
@@ -65,7 +68,12 @@ struct NccMaps { const double* inv_l; int l_ox, l_oy, l_w, l_h; const double* in
 // optional event pair recorded around the dominant kernel (kernel-only timing for the roofline)
 struct KEvents { cudaEvent_t e0 = nullptr, e1 = nullptr; };
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
-                      int kx, int ky, NccMaps ncc, vwb200_dispi* out, cudaStream_t st, const KEvents* ev = nullptr);
+                      int kx, int ky, NccMaps ncc, vwb200_dispi* out, double* scratch_cost, int* scratch_idx, bool clamp_reads,
+                      cudaStream_t st, const KEvents* ev = nullptr);
+static constexpr int K1G_DCHUNK = 256;
+// merge the per-chunk partial results of split zones (zone indices in d_split)
+int k1_generic_merge_launch(int cost, const Zone* d_zones, const int* d_split, int nsplit, const double* scratch_cost,
+                            const int* scratch_idx, vwb200_dispi* out, cudaStream_t st);
 int k1_generic_tile_w(int kx);
 int k1_generic_tile_h(int ky);
 // 1/boxsum(v*v) over window origins [ox0,ox0+ow) x [oy0,oy0+oh) with clamped (constant edge) reads.

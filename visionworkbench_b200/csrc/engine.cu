@@ -83,24 +83,46 @@ struct StreamGuard {
   ~StreamGuard() { if (own && st) cudaStreamDestroy(st); }
 };
 
-static void make_tiles(const std::vector<Zone>& zones, int tile_w, int tile_h, std::vector<Tile>& tiles) {
+static void make_tiles(const std::vector<Zone>& zones, int tile_w, int tile_h, std::vector<Tile>& tiles, bool with_chunks) {
   tiles.clear();
   for (size_t zi = 0; zi < zones.size(); ++zi)
-    for (int ty = 0; ty < zones[zi].h; ty += tile_h)
-      for (int tx = 0; tx < zones[zi].w; tx += tile_w) tiles.push_back(Tile{(int)zi, tx, ty, 0});
+    for (int c = 0; c < (with_chunks ? zones[zi].nchunks : 1); ++c)
+      for (int ty = 0; ty < zones[zi].h; ty += tile_h)
+        for (int tx = 0; tx < zones[zi].w; tx += tile_w) tiles.push_back(Tile{(int)zi, tx, ty, c});
 }
 
 // ---------------------------------------------------------------------------------------------------
 // K1 dispatch for one batch of zones (generic path).  NCC maps are built over the bounding domain of
 // the window origins the zones touch.
 // ---------------------------------------------------------------------------------------------------
-static int run_k1_zones(int cost, ImgF left, ImgF right, const std::vector<Zone>& zones, int kx, int ky,
+static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones, int kx, int ky,
                         vwb200_dispi* d_out, Arena& ar, cudaStream_t st, const Zone** d_zones_out = nullptr,
                         const Tile** d_tiles_out = nullptr, int* ntiles_out = nullptr, const KEvents* ev = nullptr) {
   if (zones.empty()) { if (ntiles_out) *ntiles_out = 0; return VWB200_OK; }
-  std::vector<Tile> tiles;
-  make_tiles(zones, k1_generic_tile_w(kx), k1_generic_tile_h(ky), tiles);
+  // split the disparity range of zones with many disparities over several CTAs (load balance: a zone whose
+  // range was reset to the full search window would otherwise be one CTA's serial loop)
+  std::vector<int> split;
+  long long scratch_elems = 0;
+  bool clamp_reads = false;
+  for (size_t zi = 0; zi < zones.size(); ++zi) {
+    Zone& z = zones[zi];
+    const int nd = z.sx * z.sy;
+    z.nchunks = (nd + K1G_DCHUNK - 1) / K1G_DCHUNK;
+    z.sbase = 0;
+    if (z.nchunks > 1 && (long long)z.w * z.h * z.nchunks < (1ll << 26)) {
+      z.sbase = scratch_elems; scratch_elems += (long long)z.nchunks * z.w * z.h; split.push_back((int)zi);
+    } else z.nchunks = 1;
+    if (z.lx < 0 || z.ly < 0 || z.lx + z.w + kx - 1 > left.w || z.ly + z.h + ky - 1 > left.h ||
+        z.rx < 0 || z.ry < 0 || z.rx + z.w + kx - 1 + z.sx - 1 > right.w || z.ry + z.h + ky - 1 + z.sy - 1 > right.h) clamp_reads = true;
+  }
+  std::vector<Tile> tiles, tiles_post;
+  make_tiles(zones, k1_generic_tile_w(kx), k1_generic_tile_h(ky), tiles, true);
   Zone* d_zones; Tile* d_tiles;
+  double* d_sc = nullptr; int* d_si = nullptr; int* d_split = nullptr;
+  if (!split.empty()) {
+    VWB_TRY(ar.alloc(&d_sc, (size_t)scratch_elems)); VWB_TRY(ar.alloc(&d_si, (size_t)scratch_elems)); VWB_TRY(ar.alloc(&d_split, split.size()));
+    VWB_CUDA(cudaMemcpyAsync(d_split, split.data(), split.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
   VWB_TRY(ar.alloc(&d_zones, zones.size()));
   VWB_TRY(ar.alloc(&d_tiles, tiles.size()));
   VWB_CUDA(cudaMemcpyAsync(d_zones, zones.data(), zones.size() * sizeof(Zone), cudaMemcpyHostToDevice, st));
@@ -120,12 +142,21 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, const std::vector<Zone>
     VWB_TRY(box_sq_inv_launch(right, kx, ky, rx0, ry0, rx1 - rx0, ry1 - ry0, ir, st));
     ncc = NccMaps{il, lx0, ly0, lx1 - lx0, ly1 - ly0, ir, rx0, ry0, rx1 - rx0, ry1 - ry0};
   }
-  VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles, (int)tiles.size(), kx, ky, ncc, d_out, st, ev));
+  VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles, (int)tiles.size(), kx, ky, ncc, d_out, d_sc, d_si, clamp_reads, st, ev));
+  VWB_TRY(k1_generic_merge_launch(cost, d_zones, d_split, (int)split.size(), d_sc, d_si, d_out, st));
   if (cost == VWB200_CROSS_CORRELATION)
     VWB_TRY(k1_nan_fixup_launch(cost, left, right, d_zones, (int)zones.size(), kx, ky, ncc, d_out, st));
   if (d_zones_out) *d_zones_out = d_zones;
-  if (d_tiles_out) *d_tiles_out = d_tiles;
-  if (ntiles_out) *ntiles_out = (int)tiles.size();
+  if (d_tiles_out) {          // chunk-free tile table for the per-pixel post pass
+    make_tiles(zones, k1_generic_tile_w(kx), k1_generic_tile_h(ky), tiles_post, false);
+    Tile* d_tp;
+    VWB_TRY(ar.alloc(&d_tp, tiles_post.size()));
+    VWB_CUDA(cudaMemcpyAsync(d_tp, tiles_post.data(), tiles_post.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    VWB_CUDA(cudaStreamSynchronize(st));      // tiles_post is a local
+    *d_tiles_out = d_tp;
+    if (ntiles_out) *ntiles_out = (int)tiles_post.size();
+  } else if (ntiles_out) *ntiles_out = (int)tiles.size();
+  VWB_CUDA(cudaStreamSynchronize(st));        // zones / tiles / split are locals of this frame
   return VWB200_OK;
 }
 

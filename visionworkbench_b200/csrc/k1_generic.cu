@@ -49,6 +49,11 @@ __device__ __forceinline__ bool better(double c, double q) {
 __device__ __forceinline__ float ld_clamped(const ImgF& im, int x, int y) {
   return __ldg(im.p + (ptrdiff_t)clampi(y, 0, im.h - 1) * im.pitch + clampi(x, 0, im.w - 1));
 }
+template <bool CLAMP>
+__device__ __forceinline__ float ld_img(const ImgF& im, int x, int y) {
+  if (CLAMP) return ld_clamped(im, x, y);
+  return __ldg(im.p + (ptrdiff_t)y * im.pitch + x);
+}
 
 // Zone kernel.  One CTA per ZT_W x ZT_H tile of a zone; the 8 warps work on different disparities at the same
 // time (d = warp, warp + 8, ...) with only warp-level synchronisation inside the disparity loop:
@@ -57,10 +62,11 @@ __device__ __forceinline__ float ld_clamped(const ImgF& im, int x, int y) {
 // After the loop the warps' private bests are merged (cost, then raster index: first disparity wins ties).
 static constexpr int ZT_W = 32, ZT_H = 16, ZWARPS = 8;
 
-template <int COST>
+template <int COST, bool CLAMP>
 __global__ void __launch_bounds__(K1G_THREADS)
 k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __restrict__ tiles,
-                  int kx, int ky, NccMaps ncc, vwb200_dispi* __restrict__ out) {
+                  int kx, int ky, NccMaps ncc, vwb200_dispi* __restrict__ out, double* __restrict__ scratch_cost,
+                  int* __restrict__ scratch_idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Tile t = tiles[blockIdx.x];
   const Zone z = zones[t.zone];
@@ -76,23 +82,25 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
   int* bidx = bidxall + (size_t)warp * ZT_H * ZT_W;
   const int lx0 = z.lx + t.tx, ly0 = z.ly + t.ty;
   const int rx0 = z.rx + t.tx, ry0 = z.ry + t.ty;
-  const int nd = z.sx * z.sy;
+  const int nd_all = z.sx * z.sy;
+  const int d_begin = t.chunk * K1G_DCHUNK;
+  const int nd = min(nd_all, d_begin + K1G_DCHUNK);             // this CTA covers [d_begin, nd)
   // phase-2 work split: lane -> (row, half)
   const int halves = (2 * th <= 32) ? 2 : 1;
   const int cw = (tw + halves - 1) / halves;
   const int prow = lane / halves, phalf = lane % halves;
   bool first = true;
-  for (int d = warp; d < nd; d += ZWARPS) {
+  for (int d = d_begin + warp; d < nd; d += ZWARPS) {
     const int dy = d / z.sx, dx = d - dy * z.sx;
     // ---- phase 1 ----
     for (int xp = lane; xp < pw; xp += 32) {
       const int gl = lx0 + xp, gr = rx0 + xp + dx;
       double v = 0.0;
-      for (int j = 0; j < ky; ++j) v += pix_cost<COST>(ld_clamped(L, gl, ly0 + j), ld_clamped(R, gr, ry0 + j + dy));
+      for (int j = 0; j < ky; ++j) v += pix_cost<COST>(ld_img<CLAMP>(L, gl, ly0 + j), ld_img<CLAMP>(R, gr, ry0 + j + dy));
       V[xp] = v;
       for (int y = 1; y < th; ++y) {
-        v += pix_cost<COST>(ld_clamped(L, gl, ly0 + y + ky - 1), ld_clamped(R, gr, ry0 + y + ky - 1 + dy));
-        v -= pix_cost<COST>(ld_clamped(L, gl, ly0 + y - 1), ld_clamped(R, gr, ry0 + y - 1 + dy));
+        v += pix_cost<COST>(ld_img<CLAMP>(L, gl, ly0 + y + ky - 1), ld_img<CLAMP>(R, gr, ry0 + y + ky - 1 + dy));
+        v -= pix_cost<COST>(ld_img<CLAMP>(L, gl, ly0 + y - 1), ld_img<CLAMP>(R, gr, ry0 + y - 1 + dy));
         V[y * vp + xp] = v;
       }
     }
@@ -132,7 +140,7 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
   }
   __syncthreads();
   // ---- merge the warps' private bests; epilogue: 12-byte pixel writes ----
-  const int nw = nd < ZWARPS ? nd : ZWARPS;
+  const int nw = (nd - d_begin) < ZWARPS ? (nd - d_begin) : ZWARPS;
   for (int k = threadIdx.x; k < tw * th; k += blockDim.x) {
     const int y = k / tw, x = k - y * tw;
     const int kk = y * ZT_W + x;
@@ -148,6 +156,12 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
       const int cd = ci & IDX_MASK;
       if (better<COST>(c, b) || (c == b && cd < d)) { b = c; d = cd; }
     }
+    if (z.nchunks > 1) {        // partial result of this disparity chunk; k1_generic_merge_kernel finishes the pixel
+      const long long s = z.sbase + ((long long)t.chunk * z.h + (t.ty + y)) * z.w + (t.tx + x);
+      scratch_cost[s] = b;
+      scratch_idx[s] = d | flags;
+      continue;
+    }
     vwb200_dispi o;
     o.dx = d % z.sx + z.addx;
     o.dy = d / z.sx + z.addy;
@@ -156,25 +170,59 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
   }
 }
 
+// merge of disparity chunks (ascending chunk order = ascending raster order of the disparities)
+template <int COST>
+__global__ void k1_generic_merge_kernel(const Zone* __restrict__ zones, const int* __restrict__ split, const double* __restrict__ sc,
+                                        const int* __restrict__ si, vwb200_dispi* __restrict__ out) {
+  const Zone z = zones[split[blockIdx.y]];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < z.w * z.h; k += gridDim.x * blockDim.x) {
+    double b = sc[z.sbase + k];
+    int bi = si[z.sbase + k];
+    int flags = bi & (FLAG_DIFF | FLAG_NAN), d = bi & IDX_MASK;
+    for (int c = 1; c < z.nchunks; ++c) {
+      const double cc = sc[z.sbase + (long long)c * z.w * z.h + k];
+      const int ci = si[z.sbase + (long long)c * z.w * z.h + k];
+      flags |= ci & (FLAG_DIFF | FLAG_NAN);
+      if (cc != b) flags |= FLAG_DIFF;
+      if (better<COST>(cc, b)) { b = cc; d = ci & IDX_MASK; }     // equal cost: the earlier chunk (smaller d) stays
+    }
+    vwb200_dispi o;
+    o.dx = d % z.sx + z.addx;
+    o.dy = d / z.sx + z.addy;
+    o.valid = (flags & FLAG_NAN) ? 2 : ((flags & FLAG_DIFF) ? 1 : 0);
+    out[z.obase + (ptrdiff_t)(k / z.w) * z.opitch + (k % z.w)] = o;
+  }
+}
+int k1_generic_merge_launch(int cost, const Zone* d_zones, const int* d_split, int nsplit, const double* scratch_cost,
+                            const int* scratch_idx, vwb200_dispi* out, cudaStream_t st) {
+  if (nsplit <= 0) return VWB200_OK;
+  dim3 grid(16, nsplit);
+  if (cost == VWB200_CROSS_CORRELATION) k1_generic_merge_kernel<VWB200_CROSS_CORRELATION><<<grid, 256, 0, st>>>(d_zones, d_split, scratch_cost, scratch_idx, out);
+  else k1_generic_merge_kernel<VWB200_ABSOLUTE_DIFFERENCE><<<grid, 256, 0, st>>>(d_zones, d_split, scratch_cost, scratch_idx, out);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
 static size_t k1g_smem_bytes(int kx) {
   const size_t vp = (size_t)((ZT_W + kx - 1) | 1);
   return (size_t)ZWARPS * ZT_H * vp * sizeof(double) + (size_t)ZWARPS * ZT_H * ZT_W * (sizeof(double) + sizeof(int));
 }
 
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
-                      int kx, int ky, NccMaps ncc, vwb200_dispi* out, cudaStream_t st, const KEvents* ev) {
+                      int kx, int ky, NccMaps ncc, vwb200_dispi* out, double* scratch_cost, int* scratch_idx, bool clamp_reads,
+                      cudaStream_t st, const KEvents* ev) {
   if (ntiles <= 0) return VWB200_OK;
   if (kx > 129 || ky > 129) { set_error("kernel size %dx%d exceeds the supported 129", kx, ky); return VWB200_ENOIMPL; }
   const size_t smem = k1g_smem_bytes(kx);
-  void (*kern)(ImgF, ImgF, const Zone*, const Tile*, int, int, NccMaps, vwb200_dispi*);
+  void (*kern)(ImgF, ImgF, const Zone*, const Tile*, int, int, NccMaps, vwb200_dispi*, double*, int*);
   switch (cost) {
-    case VWB200_SQUARED_DIFFERENCE: kern = k1_generic_kernel<VWB200_SQUARED_DIFFERENCE>; break;
-    case VWB200_CROSS_CORRELATION:  kern = k1_generic_kernel<VWB200_CROSS_CORRELATION>; break;
-    default:                        kern = k1_generic_kernel<VWB200_ABSOLUTE_DIFFERENCE>; break;
+    case VWB200_SQUARED_DIFFERENCE: kern = clamp_reads ? k1_generic_kernel<VWB200_SQUARED_DIFFERENCE, true> : k1_generic_kernel<VWB200_SQUARED_DIFFERENCE, false>; break;
+    case VWB200_CROSS_CORRELATION:  kern = clamp_reads ? k1_generic_kernel<VWB200_CROSS_CORRELATION, true> : k1_generic_kernel<VWB200_CROSS_CORRELATION, false>; break;
+    default:                        kern = clamp_reads ? k1_generic_kernel<VWB200_ABSOLUTE_DIFFERENCE, true> : k1_generic_kernel<VWB200_ABSOLUTE_DIFFERENCE, false>; break;
   }
   VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ev && ev->e0) cudaEventRecord(ev->e0, st);
-  kern<<<ntiles, K1G_THREADS, smem, st>>>(left, right, d_zones, d_tiles, kx, ky, ncc, out);
+  kern<<<ntiles, K1G_THREADS, smem, st>>>(left, right, d_zones, d_tiles, kx, ky, ncc, out, scratch_cost, scratch_idx);
   VWB_LAUNCH_CHECK();
   if (ev && ev->e1) cudaEventRecord(ev->e1, st);
   return VWB200_OK;
