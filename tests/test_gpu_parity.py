@@ -324,3 +324,15 @@ def test_parabola_subpixel_reference_kat(vwb):
     true = np.arange(120) / 0.95 - np.arange(120)
     err = np.abs(o[10:80, 10:100, 0] - true[None, 10:100]).mean()
     assert err < 0.6 and err < np.abs(np.rint(true) - true)[10:100].mean()
+
+
+def test_generic_kernel_unsplit_large_search(vwb, oracle, monkeypatch):
+    """A zone whose partial-result scratch would be too large is NOT split over disparity chunks: the single CTA
+    loop must then cover the whole search range (regression: it covered only the first 256 disparities)."""
+    from visionworkbench_b200.synth import make_rasters
+    W, H, search, kernel = 40, 24, (40, 30), (5, 5)       # 1200 disparities, SquaredCost -> generic kernel
+    left, right = make_rasters(W, H, search, kernel, seed=77)
+    got = vwb.calc_disparity(1, left, right, search, kernel)
+    ref = oracle.calc_disparity(1, left, right, search, kernel)
+    _assert_disp_equal(got, ref)
+    assert (ref[..., 0] + ref[..., 1] * 40).max() > 256     # the true matches lie beyond the first chunk

@@ -84,7 +84,7 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
   const int rx0 = z.rx + t.tx, ry0 = z.ry + t.ty;
   const int nd_all = z.sx * z.sy;
   const int d_begin = t.chunk * K1G_DCHUNK;
-  const int nd = min(nd_all, d_begin + K1G_DCHUNK);             // this CTA covers [d_begin, nd)
+  const int nd = z.nchunks > 1 ? min(nd_all, d_begin + K1G_DCHUNK) : nd_all;   // this CTA covers [d_begin, nd)
   // phase-2 work split: lane -> (row, half)
   const int halves = (2 * th <= 32) ? 2 : 1;
   const int cw = (tw + halves - 1) / halves;
