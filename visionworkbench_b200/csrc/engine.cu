@@ -117,6 +117,10 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
   }
   std::vector<Tile> tiles, tiles_post;
   make_tiles(zones, k1_generic_tile_w(kx), k1_generic_tile_h(ky), tiles, true);
+  // tiles whose right search patch fits in shared memory first (staged kernel), the rest after (L1 reads)
+  std::stable_partition(tiles.begin(), tiles.end(), [&](const Tile& t) { return k1_generic_can_stage(kx, ky, zones[t.zone].sx, zones[t.zone].sy); });
+  int n_staged = 0;
+  for (const Tile& t : tiles) if (k1_generic_can_stage(kx, ky, zones[t.zone].sx, zones[t.zone].sy)) ++n_staged;
   Zone* d_zones; Tile* d_tiles;
   double* d_sc = nullptr; int* d_si = nullptr; int* d_split = nullptr;
   if (!split.empty()) {
@@ -142,7 +146,9 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
     VWB_TRY(box_sq_inv_launch(right, kx, ky, rx0, ry0, rx1 - rx0, ry1 - ry0, ir, st));
     ncc = NccMaps{il, lx0, ly0, lx1 - lx0, ly1 - ly0, ir, rx0, ry0, rx1 - rx0, ry1 - ry0};
   }
-  VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles, (int)tiles.size(), kx, ky, ncc, d_out, d_sc, d_si, clamp_reads, st, ev));
+  VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles, n_staged, kx, ky, ncc, d_out, d_sc, d_si, clamp_reads, true, st, ev));
+  VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles + n_staged, (int)tiles.size() - n_staged, kx, ky, ncc, d_out, d_sc, d_si,
+                            clamp_reads, false, st, n_staged ? nullptr : ev));
   VWB_TRY(k1_generic_merge_launch(cost, d_zones, d_split, (int)split.size(), d_sc, d_si, d_out, st));
   if (cost == VWB200_CROSS_CORRELATION)
     VWB_TRY(k1_nan_fixup_launch(cost, left, right, d_zones, (int)zones.size(), kx, ky, ncc, d_out, st));

@@ -62,7 +62,13 @@ __device__ __forceinline__ float ld_img(const ImgF& im, int x, int y) {
 // After the loop the warps' private bests are merged (cost, then raster index: first disparity wins ties).
 static constexpr int ZT_W = 32, ZT_H = 16, ZWARPS = 8;
 
-template <int COST, bool CLAMP>
+// STAGE: the tile's left patch and right search patch are copied once into shared memory (as floats, with the
+// constant-edge clamping applied during the copy), so the disparity loop touches no global memory.  Used whenever
+// the right patch fits (ZR_MAX floats); otherwise the loop reads global memory through L1.
+static constexpr int ZR_MAX = 12288;          // 48 KB of right patch
+static constexpr int ZCW = 16;                // max columns per phase-2 lane (ZT_W / 2 halves)
+
+template <int COST, bool CLAMP, bool STAGE>
 __global__ void __launch_bounds__(K1G_THREADS)
 k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __restrict__ tiles,
                   int kx, int ky, NccMaps ncc, vwb200_dispi* __restrict__ out, double* __restrict__ scratch_cost,
@@ -71,76 +77,108 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
   const Tile t = tiles[blockIdx.x];
   const Zone z = zones[t.zone];
   const int tw = min(ZT_W, z.w - t.tx), th = min(ZT_H, z.h - t.ty);
-  const int pw = tw + kx - 1;
+  const int pw = tw + kx - 1, ph = th + ky - 1;
   const int vp = (ZT_W + kx - 1) | 1;                         // odd pitch: conflict-free when lanes walk rows
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* Vall = reinterpret_cast<double*>(smem_raw);          // [ZWARPS][ZT_H][vp]
-  double* bestall = Vall + (size_t)ZWARPS * ZT_H * vp;         // [ZWARPS][ZT_H*ZT_W]
+  double* bestall = Vall + (size_t)ZWARPS * ZT_H * vp;         // [ZWARPS][ZT_H*ZT_W]   (merge only)
   int* bidxall = reinterpret_cast<int*>(bestall + (size_t)ZWARPS * ZT_H * ZT_W);
+  float* sL = reinterpret_cast<float*>(bidxall + (size_t)ZWARPS * ZT_H * ZT_W);   // [ph][pw]      (STAGE)
+  float* sR = sL + (size_t)(ZT_H + ky - 1) * (ZT_W + kx - 1);                      // [ph+sy-1][pw+sx-1]
   double* V = Vall + (size_t)warp * ZT_H * vp;
-  double* best = bestall + (size_t)warp * ZT_H * ZT_W;
-  int* bidx = bidxall + (size_t)warp * ZT_H * ZT_W;
   const int lx0 = z.lx + t.tx, ly0 = z.ly + t.ty;
   const int rx0 = z.rx + t.tx, ry0 = z.ry + t.ty;
   const int nd_all = z.sx * z.sy;
   const int d_begin = t.chunk * K1G_DCHUNK;
   const int nd = z.nchunks > 1 ? min(nd_all, d_begin + K1G_DCHUNK) : nd_all;   // this CTA covers [d_begin, nd)
-  // phase-2 work split: lane -> (row, half)
+  const int rpw = pw + z.sx - 1;
+  if (STAGE) {
+    const int rph = ph + z.sy - 1;
+    for (int k = threadIdx.x; k < pw * ph; k += blockDim.x) sL[k] = ld_clamped(L, lx0 + k % pw, ly0 + k / pw);
+    for (int k = threadIdx.x; k < rpw * rph; k += blockDim.x) sR[k] = ld_clamped(R, rx0 + k % rpw, ry0 + k / rpw);
+    __syncthreads();
+  }
+  // phase-2 work split: lane -> (row, half); each lane keeps the running best of its <= ZCW pixels in registers
   const int halves = (2 * th <= 32) ? 2 : 1;
   const int cw = (tw + halves - 1) / halves;
   const int prow = lane / halves, phalf = lane % halves;
+  const int xb = phalf * cw, xe = min(tw, xb + cw);
+  const bool p2 = prow < th && xb < xe;
+  double rbest[ZCW];
+  int ridx[ZCW];
+#pragma unroll
+  for (int i = 0; i < ZCW; ++i) { rbest[i] = 0.0; ridx[i] = 0; }
   bool first = true;
   for (int d = d_begin + warp; d < nd; d += ZWARPS) {
     const int dy = d / z.sx, dx = d - dy * z.sx;
-    // ---- phase 1 ----
+    // ---- phase 1: vertical sliding sums ----
     for (int xp = lane; xp < pw; xp += 32) {
-      const int gl = lx0 + xp, gr = rx0 + xp + dx;
       double v = 0.0;
-      for (int j = 0; j < ky; ++j) v += pix_cost<COST>(ld_img<CLAMP>(L, gl, ly0 + j), ld_img<CLAMP>(R, gr, ry0 + j + dy));
-      V[xp] = v;
-      for (int y = 1; y < th; ++y) {
-        v += pix_cost<COST>(ld_img<CLAMP>(L, gl, ly0 + y + ky - 1), ld_img<CLAMP>(R, gr, ry0 + y + ky - 1 + dy));
-        v -= pix_cost<COST>(ld_img<CLAMP>(L, gl, ly0 + y - 1), ld_img<CLAMP>(R, gr, ry0 + y - 1 + dy));
-        V[y * vp + xp] = v;
+      if (STAGE) {
+        const float* lp = sL + xp;
+        const float* rp = sR + dy * rpw + xp + dx;
+        for (int j = 0; j < ky; ++j) v += pix_cost<COST>(lp[j * pw], rp[j * rpw]);
+        V[xp] = v;
+        for (int y = 1; y < th; ++y) {
+          v += pix_cost<COST>(lp[(y + ky - 1) * pw], rp[(y + ky - 1) * rpw]);
+          v -= pix_cost<COST>(lp[(y - 1) * pw], rp[(y - 1) * rpw]);
+          V[y * vp + xp] = v;
+        }
+      } else {
+        const int gl = lx0 + xp, gr = rx0 + xp + dx;
+        for (int j = 0; j < ky; ++j) v += pix_cost<COST>(ld_img<CLAMP>(L, gl, ly0 + j), ld_img<CLAMP>(R, gr, ry0 + j + dy));
+        V[xp] = v;
+        for (int y = 1; y < th; ++y) {
+          v += pix_cost<COST>(ld_img<CLAMP>(L, gl, ly0 + y + ky - 1), ld_img<CLAMP>(R, gr, ry0 + y + ky - 1 + dy));
+          v -= pix_cost<COST>(ld_img<CLAMP>(L, gl, ly0 + y - 1), ld_img<CLAMP>(R, gr, ry0 + y - 1 + dy));
+          V[y * vp + xp] = v;
+        }
       }
     }
     __syncwarp();
-    // ---- phase 2 ----
-    if (prow < th) {
-      const int xb = phalf * cw, xe = min(tw, xb + cw);
-      if (xb < xe) {
-        const double* vr = V + prow * vp;
-        double h = 0.0;
-        for (int i = 0; i < kx; ++i) h += vr[xb + i];
-        for (int x = xb; x < xe; ++x) {
+    // ---- phase 2: horizontal sliding sums + running best in registers ----
+    if (p2) {
+      const double* vr = V + prow * vp + xb;
+      double h = 0.0;
+      for (int i = 0; i < kx; ++i) h += vr[i];
+#pragma unroll
+      for (int xi = 0; xi < ZCW; ++xi) {
+        if (xi < xe - xb) {
           double cost = h;
           if (COST == VWB200_CROSS_CORRELATION) {
+            const int x = xb + xi;
             const double lp = ncc.inv_l[(ptrdiff_t)(ly0 + prow - ncc.l_oy) * ncc.l_w + (lx0 + x - ncc.l_ox)];
             const double rp = ncc.inv_r[(ptrdiff_t)(ry0 + prow + dy - ncc.r_oy) * ncc.r_w + (rx0 + x + dx - ncc.r_ox)];
             cost = __dmul_rn(h, sqrt(__dmul_rn(lp, rp)));
           }
-          const int k = prow * ZT_W + x;
           if (first) {
-            best[k] = cost;
-            bidx[k] = d | ((cost != cost) ? FLAG_NAN : 0);
+            rbest[xi] = cost;
+            ridx[xi] = d | ((cost != cost) ? FLAG_NAN : 0);
           } else {
-            const double b = best[k];
-            int bi = bidx[k];
-            if (cost != b) bi |= FLAG_DIFF;
+            int bi = ridx[xi];
+            if (cost != rbest[xi]) bi |= FLAG_DIFF;
             if (cost != cost) bi |= FLAG_NAN;
-            if (better<COST>(cost, b)) { best[k] = cost; bi = (bi & ~IDX_MASK) | d; }
-            bidx[k] = bi;
+            if (better<COST>(cost, rbest[xi])) { rbest[xi] = cost; bi = (bi & ~IDX_MASK) | d; }
+            ridx[xi] = bi;
           }
-          if (x + 1 < xe) h += vr[x + kx] - vr[x];
+          if (xi + 1 < xe - xb) h += vr[xi + kx] - vr[xi];
         }
       }
     }
     first = false;
     __syncwarp();
   }
-  __syncthreads();
-  // ---- merge the warps' private bests; epilogue: 12-byte pixel writes ----
+  // ---- publish the warp's private bests, merge across warps; epilogue: 12-byte pixel writes ----
   const int nw = (nd - d_begin) < ZWARPS ? (nd - d_begin) : ZWARPS;
+  if (p2 && warp < nw) {
+#pragma unroll
+    for (int xi = 0; xi < ZCW; ++xi)
+      if (xi < xe - xb) {
+        bestall[(size_t)warp * ZT_H * ZT_W + prow * ZT_W + xb + xi] = rbest[xi];
+        bidxall[(size_t)warp * ZT_H * ZT_W + prow * ZT_W + xb + xi] = ridx[xi];
+      }
+  }
+  __syncthreads();
   for (int k = threadIdx.x; k < tw * th; k += blockDim.x) {
     const int y = k / tw, x = k - y * tw;
     const int kk = y * ZT_W + x;
@@ -203,23 +241,30 @@ int k1_generic_merge_launch(int cost, const Zone* d_zones, const int* d_split, i
   return VWB200_OK;
 }
 
-static size_t k1g_smem_bytes(int kx) {
+static size_t k1g_smem_bytes(int kx, int ky, bool stage) {
   const size_t vp = (size_t)((ZT_W + kx - 1) | 1);
-  return (size_t)ZWARPS * ZT_H * vp * sizeof(double) + (size_t)ZWARPS * ZT_H * ZT_W * (sizeof(double) + sizeof(int));
+  size_t b = (size_t)ZWARPS * ZT_H * vp * sizeof(double) + (size_t)ZWARPS * ZT_H * ZT_W * (sizeof(double) + sizeof(int));
+  if (stage) b += ((size_t)(ZT_H + ky - 1) * (ZT_W + kx - 1) + ZR_MAX) * sizeof(float);
+  return b;
+}
+bool k1_generic_can_stage(int kx, int ky, int sx, int sy) {
+  return (long long)(ZT_W + kx - 1 + sx - 1) * (ZT_H + ky - 1 + sy - 1) <= ZR_MAX;
 }
 
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
                       int kx, int ky, NccMaps ncc, vwb200_dispi* out, double* scratch_cost, int* scratch_idx, bool clamp_reads,
-                      cudaStream_t st, const KEvents* ev) {
+                      bool stage, cudaStream_t st, const KEvents* ev) {
   if (ntiles <= 0) return VWB200_OK;
   if (kx > 129 || ky > 129) { set_error("kernel size %dx%d exceeds the supported 129", kx, ky); return VWB200_ENOIMPL; }
-  const size_t smem = k1g_smem_bytes(kx);
+  const size_t smem = k1g_smem_bytes(kx, ky, stage);
   void (*kern)(ImgF, ImgF, const Zone*, const Tile*, int, int, NccMaps, vwb200_dispi*, double*, int*);
+#define KSEL(C) (stage ? k1_generic_kernel<C, true, true> : (clamp_reads ? k1_generic_kernel<C, true, false> : k1_generic_kernel<C, false, false>))
   switch (cost) {
-    case VWB200_SQUARED_DIFFERENCE: kern = clamp_reads ? k1_generic_kernel<VWB200_SQUARED_DIFFERENCE, true> : k1_generic_kernel<VWB200_SQUARED_DIFFERENCE, false>; break;
-    case VWB200_CROSS_CORRELATION:  kern = clamp_reads ? k1_generic_kernel<VWB200_CROSS_CORRELATION, true> : k1_generic_kernel<VWB200_CROSS_CORRELATION, false>; break;
-    default:                        kern = clamp_reads ? k1_generic_kernel<VWB200_ABSOLUTE_DIFFERENCE, true> : k1_generic_kernel<VWB200_ABSOLUTE_DIFFERENCE, false>; break;
+    case VWB200_SQUARED_DIFFERENCE: kern = KSEL(VWB200_SQUARED_DIFFERENCE); break;
+    case VWB200_CROSS_CORRELATION:  kern = KSEL(VWB200_CROSS_CORRELATION); break;
+    default:                        kern = KSEL(VWB200_ABSOLUTE_DIFFERENCE); break;
   }
+#undef KSEL
   VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ev && ev->e0) cudaEventRecord(ev->e0, st);
   kern<<<ntiles, K1G_THREADS, smem, st>>>(left, right, d_zones, d_tiles, kx, ky, ncc, out, scratch_cost, scratch_idx);
