@@ -336,3 +336,20 @@ def test_generic_kernel_unsplit_large_search(vwb, oracle, monkeypatch):
     ref = oracle.calc_disparity(1, left, right, search, kernel)
     _assert_disp_equal(got, ref)
     assert (ref[..., 0] + ref[..., 1] * 40).max() > 256     # the true matches lie beyond the first chunk
+
+
+@pytest.mark.parametrize("consistency", [-1.0, 2.0])
+def test_view_single_level_uses_fast_kernel(vwb, oracle, consistency):
+    """pyramid_correlate(max_pyramid_levels=0) on integer imagery: one big zone with a (search+1)^2 window
+    (CorrelationView.cc:338-342) -> exact-integer fast kernel incl. the partial last dx octet, the R->L pass with
+    edge-extended reads and the output offsets; masked pixels keep the tile on the general kernel."""
+    from visionworkbench_b200.synth import make_pair
+    search, kernel = (-20, -7, 12, 9), (9, 9)        # 33 x 17 window after the +1: not a multiple of 8
+    left, right, lm, rm, _ = make_pair(420, 300, search, 61, dropout=0.0)
+    view = vwb.pyramid_correlate(left, right, lm, rm, 0, 0.0, search, kernel, 0, 0, 0.0, consistency, 0, 3, 0)
+    p = oracle.make_params(search, kernel, cost=0, consistency_threshold=consistency, filter_half_kernel=3, max_pyramid_levels=0)
+    for bbox in [(0, 0, 420, 300), (100, 60, 400, 290)]:
+        n0 = vwb.kernel_launches()
+        got = view.rasterize(None, bbox)
+        ref = oracle.pyramid_correlate(p, left, right, lm, rm, bbox=bbox)
+        _assert_disp_equal(got, ref, f"single level fast {bbox}")

@@ -83,12 +83,15 @@ int box_sq_inv_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh
 int k1_nan_fixup_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, int nzones, int kx, int ky,
                         NccMaps ncc, vwb200_dispi* out, cudaStream_t st);
 
+// left/right are whole images; the logical rasters start at (lox,loy) / (rox,roy) (constant edge extension outside),
+// (addx,addy) is added to every output disparity (R->L pass of the level loop)
+struct FastOrigin { int lox, loy, rox, roy, addx, addy; };
 // ---- K1 fast (exact-integer path, single big zone) -------------------------------------------
 // Returns VWB200_ENOIMPL if the configuration is outside what the fast path handles.
 int k1_fast_supported(int cost, int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued);
 int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
                    vwb200_dispi* out, ptrdiff_t opitch, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                   const KEvents* ev = nullptr);
+                   const KEvents* ev = nullptr, const struct FastOrigin* org = nullptr);
 size_t k1_fast_workspace_bytes(int W, int H, int sx, int sy, int kx, int ky);
 // min / max / integer-valuedness of an image (device reduction); result[0]=min,[1]=max,[2]=all-integers(1/0)
 int image_stats_launch(ImgF img, float* d_result3, cudaStream_t st);

@@ -97,7 +97,8 @@ static void make_tiles(const std::vector<Zone>& zones, int tile_w, int tile_h, s
 // ---------------------------------------------------------------------------------------------------
 static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones, int kx, int ky,
                         vwb200_dispi* d_out, Arena& ar, cudaStream_t st, const Zone** d_zones_out = nullptr,
-                        const Tile** d_tiles_out = nullptr, int* ntiles_out = nullptr, const KEvents* ev = nullptr) {
+                        const Tile** d_tiles_out = nullptr, int* ntiles_out = nullptr, const KEvents* ev = nullptr,
+                        const std::vector<char>* skip = nullptr) {
   if (zones.empty()) { if (ntiles_out) *ntiles_out = 0; return VWB200_OK; }
   // split the disparity range of zones with many disparities over several CTAs (load balance: a zone whose
   // range was reset to the full search window would otherwise be one CTA's serial loop)
@@ -117,6 +118,7 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
   }
   std::vector<Tile> tiles, tiles_post;
   make_tiles(zones, k1_generic_tile_w(kx), k1_generic_tile_h(ky), tiles, true);
+  if (skip) tiles.erase(std::remove_if(tiles.begin(), tiles.end(), [&](const Tile& t) { return (*skip)[t.zone] != 0; }), tiles.end());
   // tiles whose right search patch fits in shared memory first (staged kernel), the rest after (L1 reads)
   std::stable_partition(tiles.begin(), tiles.end(), [&](const Tile& t) { return k1_generic_can_stage(kx, ky, zones[t.zone].sx, zones[t.zone].sy); });
   int n_staged = 0;
@@ -425,6 +427,19 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
     VWB_TRY(mean_fill_launch(b0.l, b0.lw, b0.lh, b0.lw, ImgB{lmb, b0.lw, b0.lh, b0.lw}, acc, st));
     VWB_TRY(mean_fill_launch(b0.r, b0.rw, b0.rh, b0.rw, ImgB{rmb, b0.rw, b0.rh, b0.rw}, acc_r, st));
   }
+  // level-0 imagery statistics (after the mean fill): integer valued with a small range -> the exact-integer fast
+  // kernel can take the large zones of level 0
+  float hstats[6] = {0, 0, 0, 0, 0, 0};
+  if (p.cost_type == VWB200_ABSOLUTE_DIFFERENCE) {
+    float* d_stats;
+    VWB_TRY(ar.alloc(&d_stats, 6));
+    VWB_TRY(image_stats_launch(ImgF{b0.l, b0.lw, b0.lh, b0.lw}, d_stats, st));
+    VWB_TRY(image_stats_launch(ImgF{b0.r, b0.rw, b0.rh, b0.rw}, d_stats + 3, st));
+    VWB_CUDA(cudaMemcpyAsync(hstats, d_stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
+    VWB_CUDA(cudaStreamSynchronize(st));
+  }
+  const float tile_vmin = std::min(hstats[0], hstats[3]), tile_vmax = std::max(hstats[1], hstats[4]);
+  const bool tile_integer = hstats[2] != 0.0f && hstats[5] != 0.0f && p.prefilter_mode == VWB200_PREFILTER_NONE;
   // final masks: zero edge extension, no kernel padding (:192-197)
   b0.lmw = bw; b0.lmh = bh; b0.rmw = bw + ssx; b0.rmh = bh + ssy;
   VWB_TRY(ar.alloc(&b0.lm, (size_t)b0.lmw * b0.lmh));
@@ -495,13 +510,29 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
       fprintf(stderr, "[vwb200] level %d: %zu zones, %lld evals, max search %lld, %d zones with >400 disparities (%lld evals)\n", level, zl.size(), evals, maxd, nbig, big);
     }
     const ImgF Ll{lv.l, lv.lw, lv.lh, lv.lw}, Rl{lv.r, lv.rw, lv.rh, lv.rw};
-    const Zone* d_zl = nullptr; const Tile* d_tl = nullptr; int ntl = 0;
-    VWB_TRY(run_k1_zones(p.cost_type, Ll, Rl, zl, kx, ky, disp, ar, st, &d_zl, &d_tl, &ntl));
-    vwb200_dispi* rl = nullptr; const Zone* d_zr = nullptr;
-    if (check && !zr.empty()) {
-      VWB_TRY(ar.alloc(&rl, (size_t)rl_elems));
-      VWB_TRY(run_k1_zones(p.cost_type, Rl, Ll, zr, kx, ky, rl, ar, st, &d_zr));
+    vwb200_dispi* rl = nullptr;
+    if (check && !zr.empty()) VWB_TRY(ar.alloc(&rl, (size_t)rl_elems));
+    // large level-0 zones of integer imagery go to the exact-integer fast kernel, everything else to the zone kernel
+    std::vector<char> fast_l(zl.size(), 0), fast_r(zr.size(), 0);
+    if (level == 0 && tile_integer) {
+      auto try_fast = [&](const Zone& z, ImgF a, ImgF b, vwb200_dispi* dst, char& flag) -> int {
+        if ((long long)z.w * z.h < 128 * 128 || (long long)z.sx * z.sy < 256) return VWB200_OK;
+        if (k1_fast_supported(p.cost_type, kx, ky, z.sx, z.sy, tile_vmin, tile_vmax, true) != VWB200_OK) return VWB200_OK;
+        const size_t wb = k1_fast_workspace_bytes(z.w, z.h, z.sx, z.sy, kx, ky);
+        unsigned char* ws;
+        VWB_TRY(ar.alloc(&ws, wb));
+        const FastOrigin org{z.lx, z.ly, z.rx, z.ry, z.addx, z.addy};
+        VWB_TRY(k1_fast_launch(p.cost_type, a, b, z.w, z.h, z.sx, z.sy, kx, ky, tile_vmin, tile_vmax, dst + z.obase, z.opitch, ws, wb, st, nullptr, &org));
+        flag = 1;
+        return VWB200_OK;
+      };
+      for (size_t i = 0; i < zl.size(); ++i) VWB_TRY(try_fast(zl[i], Ll, Rl, disp, fast_l[i]));
+      for (size_t i = 0; i < zr.size(); ++i) VWB_TRY(try_fast(zr[i], Rl, Ll, rl, fast_r[i]));
     }
+    const Zone* d_zl = nullptr; const Tile* d_tl = nullptr; int ntl = 0;
+    VWB_TRY(run_k1_zones(p.cost_type, Ll, Rl, zl, kx, ky, disp, ar, st, &d_zl, &d_tl, &ntl, nullptr, &fast_l));
+    const Zone* d_zr = nullptr;
+    if (check && !zr.empty()) VWB_TRY(run_k1_zones(p.cost_type, Rl, Ll, zr, kx, ky, rl, ar, st, &d_zr, nullptr, nullptr, nullptr, &fast_r));
     if (!zl.empty()) {
       int2* d_post;
       VWB_TRY(ar.alloc(&d_post, post.size()));

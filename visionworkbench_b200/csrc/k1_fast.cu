@@ -88,6 +88,8 @@ struct FastGeom {
   int ltile_rows;    // F_TH + ky - 1
   int ring_slots;    // F_TH + ky
   int rw;            // u16 per packed right row = 256 + sx (multiple of 8)
+  int lox, loy, rox, roy;   // origin of the (logical) left / right rasters inside the images passed to the pack kernels
+  int addx, addy;           // constant added to the output disparities
 };
 static FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
   FastGeom g;
@@ -99,7 +101,8 @@ static FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
   g.ring_slots = F_TH + ky;
   g.lrows = g.NB * F_TH + ky - 1;
   g.rrows = g.NB * F_TH + ky - 1 + sy;
-  g.rw = ((F_COLS + sx + 7) / 8) * 8;
+  g.rw = ((F_COLS + sx + 7) / 8) * 8 + 8;
+  g.lox = g.loy = g.rox = g.roy = 0; g.addx = g.addy = 0;
   return g;
 }
 static size_t fast_smem_bytes(const FastGeom& g) {
@@ -111,7 +114,7 @@ int k1_fast_supported(int cost, int kx, int ky, int sx, int sy, float vmin, floa
   if (!integer_valued) return VWB200_ENOIMPL;
   if (!(vmax - vmin <= 8191.0f) || !(fabsf(vmin) < 1.0e6f) || !(fabsf(vmax) < 1.0e6f)) return VWB200_ENOIMPL;
   if (kx < 3 || kx > 31 || ky < 1 || ky > 41) return VWB200_ENOIMPL;
-  if (sx % F_B != 0 || sx < F_B || sx > 512 || sy < 1) return VWB200_ENOIMPL;
+  if (sx < F_B || sx > 512 || sy < 1) return VWB200_ENOIMPL;
   if ((long long)sx * sy > 65536) return VWB200_ENOIMPL;
   if ((long long)sx * sy < 64) return VWB200_ENOIMPL;      // tiny searches: the generic kernel is as good
   FastGeom g = make_geom(256, 32, sx, sy, kx, ky);
@@ -134,8 +137,11 @@ __global__ void pack_left_kernel(ImgF img, float vmin, FastGeom g, uint16_t* __r
   uint16_t* o = out + ((size_t)strip * g.lrows + row) * F_COLS;
   for (int c = threadIdx.x; c < F_COLS; c += blockDim.x) {      // c = strip-relative padded column (coalesced reads)
     const int gx = s0 + c;
-    uint16_t v = 0;
-    if (row < img.h && gx < img.w) v = (uint16_t)((int)(img.p[(ptrdiff_t)row * img.pitch + gx] - vmin) * F_B);
+    uint16_t v = 0;      // logical raster = (W+kx-1) x (H+ky-1) at (lox,loy); constant edge extension of the image beyond it
+    if (row < g.H + g.ky - 1 && gx < g.W + g.kx - 1) {
+      const int iy = min(max(g.loy + row, 0), img.h - 1), ix = min(max(g.lox + gx, 0), img.w - 1);
+      v = (uint16_t)((int)(img.p[(ptrdiff_t)iy * img.pitch + ix] - vmin) * F_B);
+    }
     o[c] = v;
   }
 }
@@ -146,7 +152,10 @@ __global__ void pack_right_kernel(ImgF img, float vmin, FastGeom g, uint16_t* __
   for (int c = threadIdx.x; c < g.rw; c += blockDim.x) {
     const int gx = s0 + c;
     uint16_t v = 0;
-    if (row < img.h && gx < img.w) v = (uint16_t)((int)(img.p[(ptrdiff_t)row * img.pitch + gx] - vmin) * F_B);
+    if (row < g.H + g.ky - 1 + g.sy - 1 && gx < g.W + g.kx - 1 + g.sx - 1) {
+      const int iy = min(max(g.roy + row, 0), img.h - 1), ix = min(max(g.rox + gx, 0), img.w - 1);
+      v = (uint16_t)((int)(img.p[(ptrdiff_t)iy * img.pitch + ix] - vmin) * F_B);
+    }
     o[c] = v;
   }
 }
@@ -238,7 +247,7 @@ __device__ __forceinline__ void load_row_f(const uint16_t* lrow, const uint16_t*
 template <int KX, bool FSEED>
 __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, const uint16_t* __restrict__ rring,
                                           uint32_t* __restrict__ state, uint16_t* __restrict__ idxp,
-                                          int lane, int g, int ky, int ring_slots, int rw, int ring_base, int idx_base, int row0) {
+                                          int lane, int g, int ky, int ring_slots, int rw, int ring_base, int idx_base, int row0, int nb) {
   int V[8][F_B];
   const uint16_t* lp = ltile + row0 * F_COLS + 8 * lane;       // + row*256            (16-byte aligned)
   const uint16_t* rp = rring + 8 * (lane + g);                 // + slot*rw            (16-byte aligned)
@@ -305,6 +314,7 @@ __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, co
     int m[8];
 #pragma unroll
     for (int b = 0; b < F_B; ++b) {
+      if (b >= nb) break;               // last octet of a search width that is not a multiple of 8 (warp uniform)
       int p[8], o[8];
       p[0] = V[0][b];
 #pragma unroll
@@ -445,7 +455,7 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
   uint64_t* bars = reinterpret_cast<uint64_t*>(rring + (size_t)G.ring_slots * G.rw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int sub = w & (F_SUBSETS - 1), half = w / F_SUBSETS, row0 = half * F_RH;
-  const int ngroups = G.sx / F_B;
+  const int ngroups = (G.sx + F_B - 1) / F_B;
   uint16_t* idxp_block = idx_scratch + (size_t)blockIdx.x * F_SUBSETS * F_TH * F_COLS;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
@@ -476,7 +486,8 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
       }
       for (int g = sub; g < ngroups; g += F_SUBSETS) {
         if (FLT) fast_pass_f<KX>(ltile, rring, reinterpret_cast<float*>(wstate), widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, dy * G.sx + F_B * g, row0);
-        else     fast_pass<KX, FSEED>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, dy * G.sx + F_B * g, row0);
+        else     fast_pass<KX, FSEED>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, dy * G.sx + F_B * g, row0,
+                                      min(F_B, G.sx - F_B * g));
       }
       if (dy + 1 < G.sy) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
       __syncthreads();
@@ -497,7 +508,7 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
         if (c < best || (c == best && i < bidx)) { best = c; bidx = i; }
       }
       vwb200_dispi o;
-      o.dx = bidx % G.sx; o.dy = bidx / G.sx; o.valid = 1;
+      o.dx = bidx % G.sx + G.addx; o.dy = bidx / G.sx + G.addy; o.valid = 1;
       out[(ptrdiff_t)gy * opitch + gx] = o;
     }
     __syncthreads();
@@ -505,22 +516,24 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
 }
 
 // ---- "every disparity gave the same cost" fix-up for pixels whose arg-best is (0,0) --------------------------
-__global__ void k1_fast_allequal_fixup(ImgF L, ImgF R, int W, int H, int sx, int sy, int kx, int ky,
-                                       vwb200_dispi* __restrict__ out, ptrdiff_t opitch) {
+__global__ void k1_fast_allequal_fixup(ImgF L, ImgF R, FastGeom g, vwb200_dispi* __restrict__ out, ptrdiff_t opitch) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= W || y >= H) return;
+  if (x >= g.W || y >= g.H) return;
   vwb200_dispi* o = out + (ptrdiff_t)y * opitch + x;
-  if (o->dx != 0 || o->dy != 0) return;
-  // arg-best (0,0): valid iff some disparity has a different (necessarily larger) cost
-  long long c0 = 0;   // integer-valued inputs: exact integer arithmetic
-  for (int j = 0; j < ky; ++j)
-    for (int i = 0; i < kx; ++i) c0 += abs((int)L.p[(ptrdiff_t)(y + j) * L.pitch + x + i] - (int)R.p[(ptrdiff_t)(y + j) * R.pitch + x + i]);
-  for (int dy = 0; dy < sy; ++dy)
-    for (int dx = 0; dx < sx; ++dx) {
+  if (o->dx != g.addx || o->dy != g.addy) return;
+  // arg-best (0,0): valid iff some disparity has a different (necessarily larger) cost.  Integer-valued inputs:
+  // exact integer arithmetic.  Reads follow the pack kernels (constant edge extension around the logical rasters).
+  auto lv = [&](int xx, int yy) { return (int)L.p[(ptrdiff_t)min(max(g.loy + yy, 0), L.h - 1) * L.pitch + min(max(g.lox + xx, 0), L.w - 1)]; };
+  auto rv = [&](int xx, int yy) { return (int)R.p[(ptrdiff_t)min(max(g.roy + yy, 0), R.h - 1) * R.pitch + min(max(g.rox + xx, 0), R.w - 1)]; };
+  long long c0 = 0;
+  for (int j = 0; j < g.ky; ++j)
+    for (int i = 0; i < g.kx; ++i) c0 += abs(lv(x + i, y + j) - rv(x + i, y + j));
+  for (int dy = 0; dy < g.sy; ++dy)
+    for (int dx = 0; dx < g.sx; ++dx) {
       if (dx == 0 && dy == 0) continue;
       long long c = 0;
-      for (int j = 0; j < ky; ++j)
-        for (int i = 0; i < kx; ++i) c += abs((int)L.p[(ptrdiff_t)(y + j) * L.pitch + x + i] - (int)R.p[(ptrdiff_t)(y + j + dy) * R.pitch + x + i + dx]);
+      for (int j = 0; j < g.ky; ++j)
+        for (int i = 0; i < g.kx; ++i) c += abs(lv(x + i, y + j) - rv(x + i + dx, y + j + dy));
       if (c != c0) return;      // not all equal -> stays valid
     }
   o->valid = 0;
@@ -528,9 +541,10 @@ __global__ void k1_fast_allequal_fixup(ImgF L, ImgF R, int W, int H, int sx, int
 
 int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
                    vwb200_dispi* out, ptrdiff_t opitch, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                   const KEvents* ev) {
+                   const KEvents* ev, const FastOrigin* org) {
   (void)cost; (void)workspace_bytes;
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
+  if (org) { g.lox = org->lox; g.loy = org->loy; g.rox = org->rox; g.roy = org->roy; g.addx = org->addx; g.addy = org->addy; }
   // fp32 carries the integers exactly while every window sum * 8 (+7) stays below 2^24
   // variants: all-int (default, ALU-pipe bound), int with fp32 seeding (VWB200_K1_FAST=fseed), all-fp32 on the FMA
   // pipes (VWB200_K1_FAST=float; issue-bound).  All three are exact; profiles/k1_fast_variants_r01.md has the numbers.
@@ -570,7 +584,7 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
   VWB_LAUNCH_CHECK();
   if (ev && ev->e1) cudaEventRecord(ev->e1, st);
   dim3 b(32, 8), gg((W + 31) / 32, (H + 7) / 8);
-  k1_fast_allequal_fixup<<<gg, b, 0, st>>>(left, right, W, H, sx, sy, kx, ky, out, opitch);
+  k1_fast_allequal_fixup<<<gg, b, 0, st>>>(left, right, g, out, opitch);
   VWB_LAUNCH_CHECK();
   return VWB200_OK;
 }
