@@ -9,7 +9,7 @@ S, T, LV, cost, k, s = [int(a) for a in sys.argv[1:7]]
 check = len(sys.argv) > 7
 search = (-s // 2, -s // 2, s // 2, s // 2)
 t0 = time.time()
-left, right, lm, rm, _ = make_pair(S, S, search, 103)
+left, right, lm, rm, _ = make_pair(S, S, search, 103, dropout=0.0 if os.environ.get("NODROP") else 0.03)
 print(f"generated in {time.time()-t0:.1f}s")
 dl, dr, dlm, drm = [torch.from_numpy(a).cuda() for a in (left, right, lm, rm)]
 view = v.pyramid_correlate(dl, dr, dlm, drm, 0, 0.0, search, (k, k), cost, 0, 0.0, 2.0, 0, 5, LV)

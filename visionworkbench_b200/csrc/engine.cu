@@ -108,7 +108,7 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
   for (size_t zi = 0; zi < zones.size(); ++zi) {
     Zone& z = zones[zi];
     const int nd = z.sx * z.sy;
-    z.nchunks = (nd + K1G_DCHUNK - 1) / K1G_DCHUNK;
+    z.nchunks = (skip && (*skip)[zi]) ? 1 : (nd + K1G_DCHUNK - 1) / K1G_DCHUNK;     // zones the fast kernel took are not ours
     z.sbase = 0;
     if (z.nchunks > 1 && (long long)z.w * z.h * z.nchunks < (1ll << 26)) {
       z.sbase = scratch_elems; scratch_elems += (long long)z.nchunks * z.w * z.h; split.push_back((int)zi);
