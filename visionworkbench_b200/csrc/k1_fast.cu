@@ -88,6 +88,7 @@ struct FastGeom {
   int ltile_rows;    // F_TH + ky - 1
   int ring_slots;    // F_TH + ky
   int rw;            // u16 per packed right row = 256 + sx (multiple of 8)
+  int J, dy_per;            // the dy range is split into J chunks of dy_per rows (more, smaller work items for small rasters)
   int lox, loy, rox, roy;   // origin of the (logical) left / right rasters inside the images passed to the pack kernels
   int addx, addy;           // constant added to the output disparities
 };
@@ -103,6 +104,12 @@ static FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
   g.rrows = g.NB * F_TH + ky - 1 + sy;
   g.rw = ((F_COLS + sx + 7) / 8) * 8 + 8;
   g.lox = g.loy = g.rox = g.roy = 0; g.addx = g.addy = 0;
+  // enough work items to fill 148 persistent CTAs several times over: split the dy range when the raster is small
+  g.J = 1;
+  const int items = g.NS * g.NB;
+  if (items < 6 * 148) { g.J = (6 * 148 + items - 1) / items; if (g.J > 8) g.J = 8; if (g.J > (sy + 7) / 8) g.J = (sy + 7) / 8; if (g.J < 1) g.J = 1; }
+  g.dy_per = (sy + g.J - 1) / g.J;
+  g.J = (sy + g.dy_per - 1) / g.dy_per;
   return g;
 }
 static size_t fast_smem_bytes(const FastGeom& g) {
@@ -127,7 +134,8 @@ size_t k1_fast_workspace_bytes(int W, int H, int sx, int sy, int kx, int ky) {
   size_t l = (size_t)g.NS * g.lrows * F_COLS * 2;
   size_t r = (size_t)g.NS * g.rrows * g.rw * 2;
   size_t idx = (size_t)1024 * F_SUBSETS * F_TH * F_COLS * 2;    // per-CTA index planes (<= 1024 CTAs)
-  return l + r + idx + 256;
+  size_t part = g.J > 1 ? (size_t)g.J * W * H * 6 + 64 : 0;      // per-dy-chunk partial (cost u32, index u16)
+  return l + r + idx + part + 512;
 }
 
 // ---- pack kernels: float raster -> u16 (v - vmin) * 4 in the lane-transposed strip layout ------------
@@ -447,7 +455,8 @@ __device__ __forceinline__ void fast_pass_f(const uint16_t* __restrict__ ltile, 
 template <int KX, bool FLT, bool FSEED>
 __global__ void __launch_bounds__(F_THREADS, 1)
 k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict__ R16, FastGeom G,
-                   uint16_t* __restrict__ idx_scratch, vwb200_dispi* __restrict__ out, ptrdiff_t opitch) {
+                   uint16_t* __restrict__ idx_scratch, vwb200_dispi* __restrict__ out, ptrdiff_t opitch,
+                   uint32_t* __restrict__ part_cost, uint16_t* __restrict__ part_idx) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint32_t* state = reinterpret_cast<uint32_t*>(smem);                                  // [4][32][8][32]
   uint16_t* ltile = reinterpret_cast<uint16_t*>(smem + (size_t)F_SUBSETS * F_TH * F_COLS * 4);
@@ -461,11 +470,13 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
   __syncthreads();
   uint32_t ph0 = 0, ph1 = 0;
   const uint32_t lbytes = (uint32_t)G.ltile_rows * F_COLS * 2, rrow_bytes = (uint32_t)G.rw * 2;
-  for (int item = blockIdx.x; item < G.NS * G.NB; item += gridDim.x) {
-    const int strip = item % G.NS, band = item / G.NS;
+  for (int item = blockIdx.x; item < G.NS * G.NB * G.J; item += gridDim.x) {
+    const int chunk = item % G.J, rest = item / G.J;
+    const int strip = rest % G.NS, band = rest / G.NS;
     const int y0 = band * F_TH;
+    const int dy0 = chunk * G.dy_per, ndy = min(G.sy, dy0 + G.dy_per) - dy0;
     const uint16_t* lsrc = L16 + ((size_t)strip * G.lrows + y0) * F_COLS;
-    const uint16_t* rsrc = R16 + ((size_t)strip * G.rrows + y0) * G.rw;
+    const uint16_t* rsrc = R16 + ((size_t)strip * G.rrows + y0 + dy0) * G.rw;
     if (tid == 0) {
       fence_proxy_async();
       mbar_expect_tx(&bars[0], lbytes + (uint32_t)G.ltile_rows * rrow_bytes);
@@ -477,19 +488,19 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
     mbar_wait(&bars[0], ph0); ph0 ^= 1;
     uint32_t* wstate = state + ((size_t)sub * F_TH + row0) * F_COLS;       // this warp's rows of its subset plane
     uint16_t* widx = idxp_block + ((size_t)sub * F_TH + row0) * F_COLS;
-    for (int dy = 0; dy < G.sy; ++dy) {
+    for (int dy = 0; dy < ndy; ++dy) {         // dy relative to the chunk's first row dy0
       const int ring_base = (dy + row0) % G.ring_slots;
-      if (tid == 0 && dy + 1 < G.sy) {       // prefetch the row iteration dy+1 adds, into the slot iteration dy-1 freed
+      if (tid == 0 && dy + 1 < ndy) {        // prefetch the row iteration dy+1 adds, into the slot iteration dy-1 freed
         fence_proxy_async();
         mbar_expect_tx(&bars[1], rrow_bytes);
         tma_load_1d(rring + (size_t)((dy + G.ltile_rows) % G.ring_slots) * G.rw, rsrc + (size_t)(dy + G.ltile_rows) * G.rw, rrow_bytes, &bars[1]);
       }
       for (int g = sub; g < ngroups; g += F_SUBSETS) {
-        if (FLT) fast_pass_f<KX>(ltile, rring, reinterpret_cast<float*>(wstate), widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, dy * G.sx + F_B * g, row0);
-        else     fast_pass<KX, FSEED>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, dy * G.sx + F_B * g, row0,
+        if (FLT) fast_pass_f<KX>(ltile, rring, reinterpret_cast<float*>(wstate), widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0);
+        else     fast_pass<KX, FSEED>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0,
                                       min(F_B, G.sx - F_B * g));
       }
-      if (dy + 1 < G.sy) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
+      if (dy + 1 < ndy) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
       __syncthreads();
     }
     // ---- merge the 4 warps' private bests and write {dx, dy, valid} ----
@@ -507,12 +518,34 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
         const int i = idxp_block[(size_t)ww * F_TH * F_COLS + off];
         if (c < best || (c == best && i < bidx)) { best = c; bidx = i; }
       }
+      if (G.J > 1) {             // partial result of this dy chunk; k1_fast_merge_kernel finishes the pixel
+        const size_t pk = ((size_t)chunk * G.H + gy) * G.W + gx;
+        part_cost[pk] = best; part_idx[pk] = (uint16_t)bidx;
+        continue;
+      }
       vwb200_dispi o;
       o.dx = bidx % G.sx + G.addx; o.dy = bidx / G.sx + G.addy; o.valid = 1;
       out[(ptrdiff_t)gy * opitch + gx] = o;
     }
     __syncthreads();
   }
+}
+
+// merge of the dy chunks (ascending chunk = ascending raster order: an equal cost keeps the earlier chunk)
+__global__ void k1_fast_merge_kernel(FastGeom G, const uint32_t* __restrict__ part_cost, const uint16_t* __restrict__ part_idx,
+                                     vwb200_dispi* __restrict__ out, ptrdiff_t opitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= G.W || y >= G.H) return;
+  const size_t plane = (size_t)G.W * G.H, k = (size_t)y * G.W + x;
+  uint32_t best = part_cost[k];
+  int bidx = part_idx[k];
+  for (int c = 1; c < G.J; ++c) {
+    const uint32_t cc = part_cost[c * plane + k];
+    if (cc < best) { best = cc; bidx = part_idx[c * plane + k]; }
+  }
+  vwb200_dispi o;
+  o.dx = bidx % G.sx + G.addx; o.dy = bidx / G.sx + G.addy; o.valid = 1;
+  out[(ptrdiff_t)y * opitch + x] = o;
 }
 
 // ---- "every disparity gave the same cost" fix-up for pixels whose arg-best is (0,0) --------------------------
@@ -557,6 +590,8 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
   uint16_t* L16 = reinterpret_cast<uint16_t*>(ws);
   uint16_t* R16 = L16 + (size_t)g.NS * g.lrows * F_COLS;
   uint16_t* idx = R16 + (size_t)g.NS * g.rrows * g.rw;
+  uint32_t* part_cost = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(idx + (size_t)1024 * F_SUBSETS * F_TH * F_COLS + 31) & ~(uintptr_t)63);
+  uint16_t* part_idx = reinterpret_cast<uint16_t*>(part_cost + (size_t)g.J * W * H);
   {
     dim3 gl(g.lrows, g.NS), gr(g.rrows, g.NS);
     pack_left_kernel<<<gl, 256, 0, st>>>(left, vmin, g, L16);
@@ -567,10 +602,10 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
   int dev = 0, nsm = 148;
   VWB_CUDA(cudaGetDevice(&dev));
   VWB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  const int items = g.NS * g.NB;
+  const int items = g.NS * g.NB * g.J;
   const int grid = items < nsm ? items : nsm;
   const size_t smem = fast_smem_bytes(g);
-  void (*kern)(const uint16_t*, const uint16_t*, FastGeom, uint16_t*, vwb200_dispi*, ptrdiff_t) = nullptr;
+  void (*kern)(const uint16_t*, const uint16_t*, FastGeom, uint16_t*, vwb200_dispi*, ptrdiff_t, uint32_t*, uint16_t*) = nullptr;
   switch (kx) {
 #define KCASE(K) case K: kern = use_float ? k1_fast_abs_kernel<K, true, false> : (float_seed ? k1_fast_abs_kernel<K, false, true> : k1_fast_abs_kernel<K, false, false>); break;
     KCASE(3) KCASE(5) KCASE(7) KCASE(9) KCASE(11) KCASE(13) KCASE(15) KCASE(17) KCASE(19) KCASE(21) KCASE(23) KCASE(25)
@@ -580,9 +615,14 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
   }
   VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ev && ev->e0) cudaEventRecord(ev->e0, st);
-  kern<<<grid, F_THREADS, smem, st>>>(L16, R16, g, idx, out, opitch);
+  kern<<<grid, F_THREADS, smem, st>>>(L16, R16, g, idx, out, opitch, part_cost, part_idx);
   VWB_LAUNCH_CHECK();
   if (ev && ev->e1) cudaEventRecord(ev->e1, st);
+  if (g.J > 1) {
+    dim3 mb(32, 8), mg((W + 31) / 32, (H + 7) / 8);
+    k1_fast_merge_kernel<<<mg, mb, 0, st>>>(g, part_cost, part_idx, out, opitch);
+    VWB_LAUNCH_CHECK();
+  }
   dim3 b(32, 8), gg((W + 31) / 32, (H + 7) / 8);
   k1_fast_allequal_fixup<<<gg, b, 0, st>>>(left, right, g, out, opitch);
   VWB_LAUNCH_CHECK();
