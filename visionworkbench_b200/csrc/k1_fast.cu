@@ -107,7 +107,7 @@ static FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
   // enough work items to fill 148 persistent CTAs several times over: split the dy range when the raster is small
   g.J = 1;
   const int items = g.NS * g.NB;
-  if (items < 6 * 148) { g.J = (6 * 148 + items - 1) / items; if (g.J > 8) g.J = 8; if (g.J > (sy + 7) / 8) g.J = (sy + 7) / 8; if (g.J < 1) g.J = 1; }
+  if (items < 3 * 148) { g.J = (6 * 148 + items - 1) / items; if (g.J > 8) g.J = 8; if (g.J > (sy + 7) / 8) g.J = (sy + 7) / 8; if (g.J < 1) g.J = 1; }
   g.dy_per = (sy + g.J - 1) / g.J;
   g.J = (sy + g.dy_per - 1) / g.dy_per;
   return g;
