@@ -353,3 +353,20 @@ def test_view_single_level_uses_fast_kernel(vwb, oracle, consistency):
         got = view.rasterize(None, bbox)
         ref = oracle.pyramid_correlate(p, left, right, lm, rm, bbox=bbox)
         _assert_disp_equal(got, ref, f"single level fast {bbox}")
+
+
+@pytest.mark.parametrize("shape", [((300, 70), (16, 8), (21, 21)), ((260, 100), (33, 5), (7, 7)), ((473, 65), (24, 11), (15, 9))])
+def test_calc_disparity_exact_int_fast_path_squared(vwb, oracle, shape):
+    """SquaredCost on the exact-integer kernel: uint32 window sums, compare/select arg-min."""
+    from visionworkbench_b200.synth import make_rasters
+    (W, H), search, kernel = shape
+    left, right = make_rasters(W, H, search, kernel, seed=17 + W)
+    got = vwb.calc_disparity(1, left, right, search, kernel)
+    assert vwb.last_k1_stats()["path"] == "exact-int"
+    _assert_disp_equal(got, oracle.calc_disparity(1, left, right, search, kernel), f"fast sq {shape}")
+    # range too large for uint32 sums -> general kernel, same answer
+    big = left * 16.0
+    bigr = right * 16.0
+    got = vwb.calc_disparity(1, big, bigr, search, kernel)
+    assert vwb.last_k1_stats()["path"] == "general-fp64"
+    _assert_disp_equal(got, oracle.calc_disparity(1, big, bigr, search, kernel), f"generic sq {shape}")

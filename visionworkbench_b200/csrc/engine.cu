@@ -430,7 +430,7 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
   // level-0 imagery statistics (after the mean fill): integer valued with a small range -> the exact-integer fast
   // kernel can take the large zones of level 0
   float hstats[6] = {0, 0, 0, 0, 0, 0};
-  if (p.cost_type == VWB200_ABSOLUTE_DIFFERENCE) {
+  if (p.cost_type == VWB200_ABSOLUTE_DIFFERENCE || p.cost_type == VWB200_SQUARED_DIFFERENCE) {
     float* d_stats;
     VWB_TRY(ar.alloc(&d_stats, 6));
     VWB_TRY(image_stats_launch(ImgF{b0.l, b0.lw, b0.lh, b0.lw}, d_stats, st));

@@ -88,6 +88,7 @@ struct FastGeom {
   int ltile_rows;    // F_TH + ky - 1
   int ring_slots;    // F_TH + ky
   int rw;            // u16 per packed right row = 256 + sx (multiple of 8)
+  int scale;                // values are packed as (v - vmin) * scale: 8 for AbsoluteCost (keys = cost*8+b), 1 for SquaredCost
   int J, dy_per;            // the dy range is split into J chunks of dy_per rows (more, smaller work items for small rasters)
   int lox, loy, rox, roy;   // origin of the (logical) left / right rasters inside the images passed to the pack kernels
   int addx, addy;           // constant added to the output disparities
@@ -103,7 +104,7 @@ static FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
   g.lrows = g.NB * F_TH + ky - 1;
   g.rrows = g.NB * F_TH + ky - 1 + sy;
   g.rw = ((F_COLS + sx + 7) / 8) * 8 + 8;
-  g.lox = g.loy = g.rox = g.roy = 0; g.addx = g.addy = 0;
+  g.lox = g.loy = g.rox = g.roy = 0; g.addx = g.addy = 0; g.scale = F_B;
   // enough work items to fill 148 persistent CTAs several times over: split the dy range when the raster is small
   g.J = 1;
   const int items = g.NS * g.NB;
@@ -117,9 +118,15 @@ static size_t fast_smem_bytes(const FastGeom& g) {
 }
 
 int k1_fast_supported(int cost, int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued) {
-  if (cost != VWB200_ABSOLUTE_DIFFERENCE) return VWB200_ENOIMPL;
+  if (cost != VWB200_ABSOLUTE_DIFFERENCE && cost != VWB200_SQUARED_DIFFERENCE) return VWB200_ENOIMPL;
   if (!integer_valued) return VWB200_ENOIMPL;
-  if (!(vmax - vmin <= 8191.0f) || !(fabsf(vmin) < 1.0e6f) || !(fabsf(vmax) < 1.0e6f)) return VWB200_ENOIMPL;
+  if (cost == VWB200_SQUARED_DIFFERENCE) {        // window sums of (a-b)^2 must fit uint32
+    const double r = (double)vmax - (double)vmin;
+    // |a-b| <= 4095 keeps the reference's FLOAT (a-b)*(a-b) exact (< 2^24); beyond that it rounds and only the
+    // general kernel (which issues the same float multiply) reproduces it
+    if (!(r <= 4095.0) || !(r * r * kx * ky < 4294967295.0)) return VWB200_ENOIMPL;
+  } else if (!(vmax - vmin <= 8191.0f)) return VWB200_ENOIMPL;
+  if ( !(fabsf(vmin) < 1.0e6f) || !(fabsf(vmax) < 1.0e6f)) return VWB200_ENOIMPL;
   if (kx < 3 || kx > 31 || ky < 1 || ky > 41) return VWB200_ENOIMPL;
   if (sx < F_B || sx > 512 || sy < 1) return VWB200_ENOIMPL;
   if ((long long)sx * sy > 65536) return VWB200_ENOIMPL;
@@ -148,7 +155,7 @@ __global__ void pack_left_kernel(ImgF img, float vmin, FastGeom g, uint16_t* __r
     uint16_t v = 0;      // logical raster = (W+kx-1) x (H+ky-1) at (lox,loy); constant edge extension of the image beyond it
     if (row < g.H + g.ky - 1 && gx < g.W + g.kx - 1) {
       const int iy = min(max(g.loy + row, 0), img.h - 1), ix = min(max(g.lox + gx, 0), img.w - 1);
-      v = (uint16_t)((int)(img.p[(ptrdiff_t)iy * img.pitch + ix] - vmin) * F_B);
+      v = (uint16_t)((int)(img.p[(ptrdiff_t)iy * img.pitch + ix] - vmin) * g.scale);
     }
     o[c] = v;
   }
@@ -162,7 +169,7 @@ __global__ void pack_right_kernel(ImgF img, float vmin, FastGeom g, uint16_t* __
     uint16_t v = 0;
     if (row < g.H + g.ky - 1 + g.sy - 1 && gx < g.W + g.kx - 1 + g.sx - 1) {
       const int iy = min(max(g.roy + row, 0), img.h - 1), ix = min(max(g.rox + gx, 0), img.w - 1);
-      v = (uint16_t)((int)(img.p[(ptrdiff_t)iy * img.pitch + ix] - vmin) * F_B);
+      v = (uint16_t)((int)(img.p[(ptrdiff_t)iy * img.pitch + ix] - vmin) * g.scale);
     }
     o[c] = v;
   }
@@ -349,6 +356,81 @@ __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, co
   }
 }
 
+// ---- SquaredCost variant of the integer pass ----------------------------------------------------------------
+// (a-b)^2 of integer imagery is an exact integer in the reference's float arithmetic as long as |a-b| < 4096, and
+// the double window sums are exact; here they are uint32 (the host checks kx*ky*range^2 < 2^32).  Costs do not
+// leave room for the key trick, so the arg-min over the octet is tracked with compare/select.
+template <int KX>
+__device__ __forceinline__ void fast_pass_sq(const uint16_t* __restrict__ ltile, const uint16_t* __restrict__ rring,
+                                             uint32_t* __restrict__ state, uint16_t* __restrict__ idxp,
+                                             int lane, int g, int ky, int ring_slots, int rw, int ring_base, int idx_base, int row0, int nb) {
+  int V[8][F_B];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < F_B; ++b) V[a][b] = 0;
+  const uint16_t* lp = ltile + row0 * F_COLS + 8 * lane;
+  const uint16_t* rp = rring + 8 * (lane + g);
+  int slot_new = ring_base;
+  for (int t = 0; t < ky; ++t) {
+    int Lv[8], Rv[16];
+    load_row(lp + t * F_COLS, rp + slot_new * rw, Lv, Rv);
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < F_B; ++b) { const int d = Lv[a] - Rv[a + b]; V[a][b] += d * d; }
+    if (++slot_new == ring_slots) slot_new = 0;
+  }
+  int slot_old = ring_base;
+  for (int y = 0; y < F_RH; ++y) {
+    if (y > 0) {
+      {
+        int Lv[8], Rv[16];
+        load_row(lp + (y + ky - 1) * F_COLS, rp + slot_new * rw, Lv, Rv);
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int b = 0; b < F_B; ++b) { const int d = Lv[a] - Rv[a + b]; V[a][b] += d * d; }
+      }
+      {
+        int Lo[8], Ro[16];
+        load_row(lp + (y - 1) * F_COLS, rp + slot_old * rw, Lo, Ro);
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int b = 0; b < F_B; ++b) { const int d = Lo[a] - Ro[a + b]; V[a][b] -= d * d; }
+      }
+      if (++slot_new == ring_slots) slot_new = 0;
+      if (++slot_old == ring_slots) slot_old = 0;
+    }
+    uint32_t m[8];
+    int mb[8];
+#pragma unroll
+    for (int b = 0; b < F_B; ++b) {
+      if (b >= nb) break;
+      int p[8], o[8];
+      p[0] = V[0][b];
+#pragma unroll
+      for (int a = 1; a < 8; ++a) p[a] = p[a - 1] + V[a][b];     // wraps mod 2^32 like the uint32 sums they stand for
+      window_sums<KX>(p, o);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t c = (uint32_t)o[r];
+        if (b == 0) { m[r] = c; mb[r] = 0; }
+        else if (c < m[r]) { m[r] = c; mb[r] = b; }
+      }
+    }
+    uint32_t* srow = state + y * F_COLS + lane;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (m[r] < srow[r * 32]) {
+        srow[r * 32] = m[r];
+        idxp[y * F_COLS + r * 32 + lane] = (uint16_t)(idx_base + mb[r]);
+      }
+    }
+  }
+}
+
 // ---- float variant of the pass: the same exact integers carried in fp32 ----------------------------------
 // The ALU pipe (VABSDIFF, integer min, unpack) is the bound of the integer pass; FADD runs on the FMA
 // pipes at twice the ALU rate.  Unpacking u16 -> "2^23 + x" biased floats is a single PRMT, differences
@@ -452,7 +534,7 @@ __device__ __forceinline__ void fast_pass_f(const uint16_t* __restrict__ ltile, 
   }
 }
 
-template <int KX, bool FLT, bool FSEED>
+template <int KX, bool FLT, bool FSEED, bool SQ = false>
 __global__ void __launch_bounds__(F_THREADS, 1)
 k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict__ R16, FastGeom G,
                    uint16_t* __restrict__ idx_scratch, vwb200_dispi* __restrict__ out, ptrdiff_t opitch,
@@ -483,7 +565,7 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
       tma_load_1d(ltile, lsrc, lbytes, &bars[0]);
       tma_load_1d(rring, rsrc, (uint32_t)G.ltile_rows * rrow_bytes, &bars[0]);     // right rows y0 .. y0+ltile_rows-1 -> slots 0..
     }
-    for (int k = tid; k < F_SUBSETS * F_TH * F_COLS; k += F_THREADS) state[k] = FLT ? 0x7f000000u : S_INIT;     // 1.7e38f as float bits / max key
+    for (int k = tid; k < F_SUBSETS * F_TH * F_COLS; k += F_THREADS) state[k] = SQ ? 0xffffffffu : (FLT ? 0x7f000000u : S_INIT);     // 1.7e38f as float bits / max key
     __syncthreads();
     mbar_wait(&bars[0], ph0); ph0 ^= 1;
     uint32_t* wstate = state + ((size_t)sub * F_TH + row0) * F_COLS;       // this warp's rows of its subset plane
@@ -496,7 +578,9 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
         tma_load_1d(rring + (size_t)((dy + G.ltile_rows) % G.ring_slots) * G.rw, rsrc + (size_t)(dy + G.ltile_rows) * G.rw, rrow_bytes, &bars[1]);
       }
       for (int g = sub; g < ngroups; g += F_SUBSETS) {
-        if (FLT) fast_pass_f<KX>(ltile, rring, reinterpret_cast<float*>(wstate), widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0);
+        if (SQ) fast_pass_sq<KX>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0,
+                                 min(F_B, G.sx - F_B * g));
+        else if (FLT) fast_pass_f<KX>(ltile, rring, reinterpret_cast<float*>(wstate), widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0);
         else     fast_pass<KX, FSEED>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0,
                                       min(F_B, G.sx - F_B * g));
       }
@@ -560,13 +644,13 @@ __global__ void k1_fast_allequal_fixup(ImgF L, ImgF R, FastGeom g, vwb200_dispi*
   auto rv = [&](int xx, int yy) { return (int)R.p[(ptrdiff_t)min(max(g.roy + yy, 0), R.h - 1) * R.pitch + min(max(g.rox + xx, 0), R.w - 1)]; };
   long long c0 = 0;
   for (int j = 0; j < g.ky; ++j)
-    for (int i = 0; i < g.kx; ++i) c0 += abs(lv(x + i, y + j) - rv(x + i, y + j));
+    for (int i = 0; i < g.kx; ++i) { const long long d = lv(x + i, y + j) - rv(x + i, y + j); c0 += g.scale == 1 ? d * d : (d < 0 ? -d : d); }
   for (int dy = 0; dy < g.sy; ++dy)
     for (int dx = 0; dx < g.sx; ++dx) {
       if (dx == 0 && dy == 0) continue;
       long long c = 0;
       for (int j = 0; j < g.ky; ++j)
-        for (int i = 0; i < g.kx; ++i) c += abs(lv(x + i, y + j) - rv(x + i + dx, y + j + dy));
+        for (int i = 0; i < g.kx; ++i) { const long long d = lv(x + i, y + j) - rv(x + i + dx, y + j + dy); c += g.scale == 1 ? d * d : (d < 0 ? -d : d); }
       if (c != c0) return;      // not all equal -> stays valid
     }
   o->valid = 0;
@@ -575,8 +659,10 @@ __global__ void k1_fast_allequal_fixup(ImgF L, ImgF R, FastGeom g, vwb200_dispi*
 int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
                    vwb200_dispi* out, ptrdiff_t opitch, void* workspace, size_t workspace_bytes, cudaStream_t st,
                    const KEvents* ev, const FastOrigin* org) {
-  (void)cost; (void)workspace_bytes;
+  (void)workspace_bytes;
+  const bool sq = cost == VWB200_SQUARED_DIFFERENCE;
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
+  g.scale = sq ? 1 : F_B;
   if (org) { g.lox = org->lox; g.loy = org->loy; g.rox = org->rox; g.roy = org->roy; g.addx = org->addx; g.addy = org->addy; }
   // fp32 carries the integers exactly while every window sum * 8 (+7) stays below 2^24
   // variants: all-int (default, ALU-pipe bound), int with fp32 seeding (VWB200_K1_FAST=fseed), all-fp32 on the FMA
@@ -607,7 +693,7 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
   const size_t smem = fast_smem_bytes(g);
   void (*kern)(const uint16_t*, const uint16_t*, FastGeom, uint16_t*, vwb200_dispi*, ptrdiff_t, uint32_t*, uint16_t*) = nullptr;
   switch (kx) {
-#define KCASE(K) case K: kern = use_float ? k1_fast_abs_kernel<K, true, false> : (float_seed ? k1_fast_abs_kernel<K, false, true> : k1_fast_abs_kernel<K, false, false>); break;
+#define KCASE(K) case K: kern = sq ? k1_fast_abs_kernel<K, false, false, true> : (use_float ? k1_fast_abs_kernel<K, true, false> : (float_seed ? k1_fast_abs_kernel<K, false, true> : k1_fast_abs_kernel<K, false, false>)); break;
     KCASE(3) KCASE(5) KCASE(7) KCASE(9) KCASE(11) KCASE(13) KCASE(15) KCASE(17) KCASE(19) KCASE(21) KCASE(23) KCASE(25)
     KCASE(27) KCASE(29) KCASE(31)
 #undef KCASE
