@@ -259,7 +259,7 @@ __device__ __forceinline__ void load_row_f(const uint16_t* lrow, const uint16_t*
 #pragma unroll
   for (int i = 0; i < 8; ++i) Rv[8 + i] = t[i];
 }
-template <int KX, bool FSEED>
+template <int KX, bool FSEED, bool FULL>
 __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, const uint16_t* __restrict__ rring,
                                           uint32_t* __restrict__ state, uint16_t* __restrict__ idxp,
                                           int lane, int g, int ky, int ring_slots, int rw, int ring_base, int idx_base, int row0, int nb) {
@@ -329,7 +329,7 @@ __device__ __forceinline__ void fast_pass(const uint16_t* __restrict__ ltile, co
     int m[8];
 #pragma unroll
     for (int b = 0; b < F_B; ++b) {
-      if (b >= nb) break;               // last octet of a search width that is not a multiple of 8 (warp uniform)
+      if (!FULL && b >= nb) break;      // last octet of a search width that is not a multiple of 8 (warp uniform)
       int p[8], o[8];
       p[0] = V[0][b];
 #pragma unroll
@@ -581,8 +581,11 @@ k1_fast_abs_kernel(const uint16_t* __restrict__ L16, const uint16_t* __restrict_
         if (SQ) fast_pass_sq<KX>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0,
                                  min(F_B, G.sx - F_B * g));
         else if (FLT) fast_pass_f<KX>(ltile, rring, reinterpret_cast<float*>(wstate), widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0);
-        else     fast_pass<KX, FSEED>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0,
-                                      min(F_B, G.sx - F_B * g));
+        else if (G.sx - F_B * g >= F_B)
+          fast_pass<KX, FSEED, true>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0, F_B);
+        else
+          fast_pass<KX, FSEED, false>(ltile, rring, wstate, widx, lane, g, G.ky, G.ring_slots, G.rw, ring_base, (dy0 + dy) * G.sx + F_B * g, row0,
+                                      G.sx - F_B * g);
       }
       if (dy + 1 < ndy) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
       __syncthreads();
