@@ -110,7 +110,7 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
     const int nd = z.sx * z.sy;
     z.nchunks = (skip && (*skip)[zi]) ? 1 : (nd + K1G_DCHUNK - 1) / K1G_DCHUNK;     // zones the fast kernel took are not ours
     z.sbase = 0;
-    if (z.nchunks > 1 && (long long)z.w * z.h * z.nchunks < (1ll << 26)) {
+    if (z.nchunks > 1 && (long long)z.w * z.h * z.nchunks < (1ll << 29)) {
       z.sbase = scratch_elems; scratch_elems += (long long)z.nchunks * z.w * z.h; split.push_back((int)zi);
     } else z.nchunks = 1;
     if (z.lx < 0 || z.ly < 0 || z.lx + z.w + kx - 1 > left.w || z.ly + z.h + ky - 1 > left.h ||
@@ -120,9 +120,9 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
   make_tiles(zones, k1_generic_tile_w(kx), k1_generic_tile_h(ky), tiles, true);
   if (skip) tiles.erase(std::remove_if(tiles.begin(), tiles.end(), [&](const Tile& t) { return (*skip)[t.zone] != 0; }), tiles.end());
   // tiles whose right search patch fits in shared memory first (staged kernel), the rest after (L1 reads)
-  std::stable_partition(tiles.begin(), tiles.end(), [&](const Tile& t) { return k1_generic_can_stage(kx, ky, zones[t.zone].sx, zones[t.zone].sy); });
+  std::stable_partition(tiles.begin(), tiles.end(), [&](const Tile& t) { return k1_generic_can_stage(kx, ky, zones[t.zone].sx, zones[t.zone].sy, zones[t.zone].nchunks); });
   int n_staged = 0;
-  for (const Tile& t : tiles) if (k1_generic_can_stage(kx, ky, zones[t.zone].sx, zones[t.zone].sy)) ++n_staged;
+  for (const Tile& t : tiles) if (k1_generic_can_stage(kx, ky, zones[t.zone].sx, zones[t.zone].sy, zones[t.zone].nchunks)) ++n_staged;
   Zone* d_zones; Tile* d_tiles;
   double* d_sc = nullptr; int* d_si = nullptr; int* d_split = nullptr;
   if (!split.empty()) {

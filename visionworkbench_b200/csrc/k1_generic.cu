@@ -21,6 +21,7 @@
 // whenever the cost terms are multiples of 2^-32 below 2^21 (see DESIGN.md "exactness").
 #include "common.cuh"
 #include <vector>
+#include <algorithm>
 
 namespace vwb200 {
 
@@ -92,10 +93,12 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
   const int d_begin = t.chunk * K1G_DCHUNK;
   const int nd = z.nchunks > 1 ? min(nd_all, d_begin + K1G_DCHUNK) : nd_all;   // this CTA covers [d_begin, nd)
   const int rpw = pw + z.sx - 1;
+  const int dy_lo = d_begin / z.sx;                              // first search row this CTA touches
   if (STAGE) {
-    const int rph = ph + z.sy - 1;
+    const int dy_hi = (nd - 1) / z.sx;
+    const int rph = ph + (dy_hi - dy_lo);
     for (int k = threadIdx.x; k < pw * ph; k += blockDim.x) sL[k] = ld_clamped(L, lx0 + k % pw, ly0 + k / pw);
-    for (int k = threadIdx.x; k < rpw * rph; k += blockDim.x) sR[k] = ld_clamped(R, rx0 + k % rpw, ry0 + k / rpw);
+    for (int k = threadIdx.x; k < rpw * rph; k += blockDim.x) sR[k] = ld_clamped(R, rx0 + k % rpw, ry0 + dy_lo + k / rpw);
     __syncthreads();
   }
   // phase-2 work split: lane -> (row, half); each lane keeps the running best of its <= ZCW pixels in registers
@@ -116,7 +119,7 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
       double v = 0.0;
       if (STAGE) {
         const float* lp = sL + xp;
-        const float* rp = sR + dy * rpw + xp + dx;
+        const float* rp = sR + (dy - dy_lo) * rpw + xp + dx;
         for (int j = 0; j < ky; ++j) v += pix_cost<COST>(lp[j * pw], rp[j * rpw]);
         V[xp] = v;
         for (int y = 1; y < th; ++y) {
@@ -247,8 +250,10 @@ static size_t k1g_smem_bytes(int kx, int ky, bool stage) {
   if (stage) b += ((size_t)(ZT_H + ky - 1) * (ZT_W + kx - 1) + ZR_MAX) * sizeof(float);
   return b;
 }
-bool k1_generic_can_stage(int kx, int ky, int sx, int sy) {
-  return (long long)(ZT_W + kx - 1 + sx - 1) * (ZT_H + ky - 1 + sy - 1) <= ZR_MAX;
+bool k1_generic_can_stage(int kx, int ky, int sx, int sy, int nchunks) {
+  // a CTA of a split zone only touches the search rows of its K1G_DCHUNK disparities
+  const int span = nchunks > 1 ? std::min(sy, (K1G_DCHUNK + sx - 1) / sx + 1) : sy;
+  return (long long)(ZT_W + kx - 1 + sx - 1) * (ZT_H + ky - 1 + span - 1) <= ZR_MAX;
 }
 
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
