@@ -370,3 +370,34 @@ def test_calc_disparity_exact_int_fast_path_squared(vwb, oracle, shape):
     got = vwb.calc_disparity(1, big, bigr, search, kernel)
     assert vwb.last_k1_stats()["path"] == "general-fp64"
     _assert_disp_equal(got, oracle.calc_disparity(1, big, bigr, search, kernel), f"generic sq {shape}")
+
+
+@pytest.mark.parametrize("shape", [((300, 70), (16, 8), (21, 21)), ((260, 100), (33, 5), (7, 7)), ((473, 65), (24, 11), (15, 9)),
+                                   ((64, 64), (8, 8), (3, 5)), ((250, 40), (128, 2), (21, 21))])
+def test_calc_disparity_exact_int_fast_path_ncc(vwb, oracle, shape):
+    """NCC on the exact-integer kernel (k1_fast_ncc): integer numerators, fp32 upper-bound screening, exact double
+    evaluation (reference arithmetic) of the surviving candidates."""
+    from visionworkbench_b200.synth import make_rasters
+    (W, H), search, kernel = shape
+    left, right = make_rasters(W, H, search, kernel, seed=11 + W)
+    got = vwb.calc_disparity(2, left, right, search, kernel)
+    assert vwb.last_k1_stats()["path"] == "exact-int"
+    ref = oracle.calc_disparity(2, left, right, search, kernel)
+    _assert_disp_equal(got, ref, f"fast ncc {shape}")
+
+
+def test_fast_ncc_ties_zero_windows_and_constant_regions(vwb, oracle):
+    """2-bit imagery: exact cost ties (first disparity in raster order wins), zero-energy windows (NaN state machine),
+    flat regions (all-equal -> invalid)."""
+    rng = np.random.default_rng(78)
+    W, H, search, kernel = 280, 70, (16, 8), (7, 7)
+    right = np.floor(rng.random((H + 6 + 7, W + 6 + 15)) * 4).astype(np.float32)
+    right[20:60, 40:120] = 3.0
+    right[10:50, 150:230] = 0.0
+    left = np.ascontiguousarray(right[2:2 + H + 6, 5:5 + W + 6])
+    left[40:70, 10:60] = 0.0
+    got = vwb.calc_disparity(2, left, right, search, kernel)
+    assert vwb.last_k1_stats()["path"] == "exact-int"
+    ref = oracle.calc_disparity(2, left, right, search, kernel)
+    assert (ref[..., 2] == 0).any() and (ref[..., 2] == 1).any()
+    _assert_disp_equal(got, ref, "ncc ties")

@@ -283,8 +283,10 @@ int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, cons
 // 1 / boxsum(v*v): NCCCost's left_precision / right_precision (Stereo/CostFunctions.h:214-219).
 // square() is the float product v*v (Math/Functors.h:316-321), summed in double.
 // ------------------------------------------------------------------------------------------------
+// MODE 0: out = 1 / boxsum(v*v) (double).  MODE 1: out_i = boxsum(v) as int32 (integer-valued imagery: exact).
+template <int MODE>
 __global__ void __launch_bounds__(K1G_THREADS)
-box_sq_inv_kernel(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* __restrict__ out) {
+box_sq_inv_kernel(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* __restrict__ out, int* __restrict__ out_i) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* V = reinterpret_cast<double*>(smem_raw);
   const int tx0 = blockIdx.x * K1G_TILE, ty0 = blockIdx.y * K1G_TILE;
@@ -299,11 +301,11 @@ box_sq_inv_kernel(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, do
     if (yb < ye) {
       const int gx = ox0 + tx0 + xp, gy = oy0 + ty0;
       double v = 0.0;
-      for (int j = 0; j < ky; ++j) { float a = ld_clamped(img, gx, gy + yb + j); v += (double)__fmul_rn(a, a); }
+      for (int j = 0; j < ky; ++j) { float a = ld_clamped(img, gx, gy + yb + j); v += MODE ? (double)a : (double)__fmul_rn(a, a); }
       V[yb * vp + xp] = v;
       for (int y = yb + 1; y < ye; ++y) {
-        float a = ld_clamped(img, gx, gy + y + ky - 1); v += (double)__fmul_rn(a, a);
-        float b = ld_clamped(img, gx, gy + y - 1); v -= (double)__fmul_rn(b, b);
+        float a = ld_clamped(img, gx, gy + y + ky - 1); v += MODE ? (double)a : (double)__fmul_rn(a, a);
+        float b = ld_clamped(img, gx, gy + y - 1); v -= MODE ? (double)b : (double)__fmul_rn(b, b);
         V[y * vp + xp] = v;
       }
     }
@@ -319,7 +321,8 @@ box_sq_inv_kernel(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, do
       double h = 0.0;
       for (int i = 0; i < kx; ++i) h += vr[xb + i];
       for (int x = xb; x < xe; ++x) {
-        out[(ptrdiff_t)(ty0 + y) * ow + (tx0 + x)] = __ddiv_rn(1.0, h);
+        if (MODE) out_i[(ptrdiff_t)(ty0 + y) * ow + (tx0 + x)] = (int)h;
+        else out[(ptrdiff_t)(ty0 + y) * ow + (tx0 + x)] = __ddiv_rn(1.0, h);
         if (x + 1 < xe) h += vr[x + kx] - vr[x];
       }
     }
@@ -329,9 +332,18 @@ box_sq_inv_kernel(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, do
 int box_sq_inv_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* out, cudaStream_t st) {
   if (ow <= 0 || oh <= 0) return VWB200_OK;
   size_t smem = (size_t)K1G_TILE * ((K1G_TILE + kx - 1) | 1) * sizeof(double);
-  VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((ow + K1G_TILE - 1) / K1G_TILE, (oh + K1G_TILE - 1) / K1G_TILE);
-  box_sq_inv_kernel<<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, out);
+  box_sq_inv_kernel<0><<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, out, nullptr);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+int box_sum_i32_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, int* out, cudaStream_t st) {
+  if (ow <= 0 || oh <= 0) return VWB200_OK;
+  size_t smem = (size_t)K1G_TILE * ((K1G_TILE + kx - 1) | 1) * sizeof(double);
+  VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((ow + K1G_TILE - 1) / K1G_TILE, (oh + K1G_TILE - 1) / K1G_TILE);
+  box_sq_inv_kernel<1><<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, nullptr, out);
   VWB_LAUNCH_CHECK();
   return VWB200_OK;
 }
@@ -373,10 +385,10 @@ __global__ void k1_nan_fixup_kernel(ImgF L, ImgF R, const Zone* __restrict__ zon
 }
 
 int k1_nan_fixup_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, int nzones, int kx, int ky,
-                        NccMaps ncc, vwb200_dispi* out, cudaStream_t st) {
+                        NccMaps ncc, vwb200_dispi* out, cudaStream_t st, int gridx) {
   for (int z0 = 0; z0 < nzones; z0 += 32768) {
     const int n = nzones - z0 < 32768 ? nzones - z0 : 32768;
-    dim3 grid(8, n);
+    dim3 grid(gridx, n);
     switch (cost) {
       case VWB200_SQUARED_DIFFERENCE:
         k1_nan_fixup_kernel<VWB200_SQUARED_DIFFERENCE><<<grid, 128, 0, st>>>(left, right, d_zones + z0, kx, ky, ncc, out); break;
