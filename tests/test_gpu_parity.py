@@ -401,3 +401,33 @@ def test_fast_ncc_ties_zero_windows_and_constant_regions(vwb, oracle):
     ref = oracle.calc_disparity(2, left, right, search, kernel)
     assert (ref[..., 2] == 0).any() and (ref[..., 2] == 1).any()
     _assert_disp_equal(got, ref, "ncc ties")
+
+
+@pytest.mark.parametrize("shape", [((300, 70), (16, 8), (21, 21)), ((260, 100), (33, 5), (7, 7)), ((250, 40), (128, 2), (21, 21)),
+                                   ((64, 64), (8, 8), (3, 5))])
+def test_calc_disparity_screened_squared_12bit(vwb, oracle, shape):
+    """SquaredCost whose window sums exceed uint32 (12-bit imagery, 21x21) takes the screened exact-integer kernel
+    (k1_screen): centred int32 numerators, fp32 screening, exact int64 evaluation of the surviving candidates."""
+    from visionworkbench_b200.synth import make_rasters
+    (W, H), search, kernel = shape
+    left, right = make_rasters(W, H, search, kernel, seed=5 + W, bits=12)
+    left = left - 700.0; right = right - 700.0          # SquaredCost only needs a bounded range, not non-negative values
+    got = vwb.calc_disparity(1, left, right, search, kernel)
+    assert vwb.last_k1_stats()["path"] == "exact-int"
+    ref = oracle.calc_disparity(1, left, right, search, kernel)
+    _assert_disp_equal(got, ref, f"screened sq {shape}")
+
+
+@pytest.mark.parametrize("cost", [1, 2])
+def test_screened_kernel_flat_regions_overflow_to_replay(vwb, oracle, cost):
+    """A flat region makes every disparity tie: the candidate lists overflow and the pixels are replayed exactly."""
+    rng = np.random.default_rng(79)
+    W, H, search, kernel = 300, 40, (32, 16), (21, 21)
+    right = np.floor(rng.random((H + 20 + 15, W + 20 + 31)) * 4096).astype(np.float32)
+    right[:, 100:260] = 1000.0
+    left = np.ascontiguousarray(right[3:3 + H + 20, 7:7 + W + 20])
+    got = vwb.calc_disparity(cost, left, right, search, kernel)
+    assert vwb.last_k1_stats()["path"] == "exact-int"
+    ref = oracle.calc_disparity(cost, left, right, search, kernel)
+    assert (ref[..., 2] == 0).any() and (ref[..., 2] == 1).any()
+    _assert_disp_equal(got, ref, "flat")

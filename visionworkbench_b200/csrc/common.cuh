@@ -79,13 +79,14 @@ int k1_generic_tile_w(int kx);
 int k1_generic_tile_h(int ky);
 // 1/boxsum(v*v) over window origins [ox0,ox0+ow) x [oy0,oy0+oh) with clamped (constant edge) reads.
 int box_sq_inv_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* out, cudaStream_t st);
-// boxsum(v) as int32 over the same window-origin domain (integer-valued imagery)
-int box_sum_i32_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, int* out, cudaStream_t st);
-// NCC on the exact-integer fast path (k1_fast_ncc.cu)
-int k1_fast_ncc_supported(int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued);
-size_t k1_fast_ncc_workspace_bytes(int W, int H, int sx, int sy, int kx, int ky);
-int k1_fast_ncc_launch(ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
-                       vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev = nullptr);
+// boxsum(v) (centred == 0) or boxsum((v - c)^2) (centred == 1) as int32 over the same window-origin domain (integer imagery)
+int box_sum_i32_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, int* out, cudaStream_t st, int centred = 0,
+                       float c = 0.0f);
+// NCC / wide-range SquaredCost on the exact-integer path with fp32 screening (k1_screen.cu)
+int k1_screen_supported(int cost, int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued);
+size_t k1_screen_workspace_bytes(int cost, int W, int H, int sx, int sy, int kx, int ky);
+int k1_screen_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
+                     vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev = nullptr);
 // exact sequential re-evaluation of pixels flagged NaN by k1 (NCC zero-energy windows)
 int k1_nan_fixup_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, int nzones, int kx, int ky,
                         NccMaps ncc, vwb200_dispi* out, cudaStream_t st, int gridx = 8);

@@ -643,18 +643,16 @@ int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrd
       VWB_CUDA(cudaStreamSynchronize(st));
       const float vmin = std::min(hs[0], hs[3]), vmax = std::max(hs[1], hs[4]);
       const bool integer = hs[2] != 0.0f && hs[5] != 0.0f;
-      if (cost_type == VWB200_CROSS_CORRELATION) {
-        if (k1_fast_ncc_supported(kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK && !getenv("VWB200_NCC_GENERIC")) {
-          unsigned char* ws;
-          VWB_TRY(ar.alloc(&ws, k1_fast_ncc_workspace_bytes(W, H, sx, sy, kx, ky)));
-          VWB_TRY(k1_fast_ncc_launch(Li, Ri, W, H, sx, sy, kx, ky, vmin, vmax, dout, dop, ws, st, &kev));
-          path = 0;
-        }
-      } else if (k1_fast_supported(cost_type, kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK) {
+      if (k1_fast_supported(cost_type, kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK) {
         const size_t wb = k1_fast_workspace_bytes(W, H, sx, sy, kx, ky);
         unsigned char* ws;
         VWB_TRY(ar.alloc(&ws, wb));
         VWB_TRY(k1_fast_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, vmin, vmax, dout, dop, ws, wb, st, &kev));
+        path = 0;
+      } else if (k1_screen_supported(cost_type, kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK && !getenv("VWB200_K1_GENERIC")) {
+        unsigned char* ws;
+        VWB_TRY(ar.alloc(&ws, k1_screen_workspace_bytes(cost_type, W, H, sx, sy, kx, ky)));
+        VWB_TRY(k1_screen_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, vmin, vmax, dout, dop, ws, st, &kev));
         path = 0;
       }
     }

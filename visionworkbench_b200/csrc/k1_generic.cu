@@ -284,9 +284,17 @@ int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, cons
 // square() is the float product v*v (Math/Functors.h:316-321), summed in double.
 // ------------------------------------------------------------------------------------------------
 // MODE 0: out = 1 / boxsum(v*v) (double).  MODE 1: out_i = boxsum(v) as int32 (integer-valued imagery: exact).
+// MODE 0: v*v (float product, as the reference) -> 1/sum;  MODE 1: v -> int sum;  MODE 2: (v - cen)^2 -> int sum
+template <int MODE>
+__device__ __forceinline__ double box_term(float a, float cen) {
+  if (MODE == 0) return (double)__fmul_rn(a, a);
+  if (MODE == 1) return (double)a;
+  const float d = __fsub_rn(a, cen);
+  return (double)__fmul_rn(d, d);
+}
 template <int MODE>
 __global__ void __launch_bounds__(K1G_THREADS)
-box_sq_inv_kernel(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* __restrict__ out, int* __restrict__ out_i) {
+box_sq_inv_kernel(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* __restrict__ out, int* __restrict__ out_i, float cen) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* V = reinterpret_cast<double*>(smem_raw);
   const int tx0 = blockIdx.x * K1G_TILE, ty0 = blockIdx.y * K1G_TILE;
@@ -301,11 +309,11 @@ box_sq_inv_kernel(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, do
     if (yb < ye) {
       const int gx = ox0 + tx0 + xp, gy = oy0 + ty0;
       double v = 0.0;
-      for (int j = 0; j < ky; ++j) { float a = ld_clamped(img, gx, gy + yb + j); v += MODE ? (double)a : (double)__fmul_rn(a, a); }
+      for (int j = 0; j < ky; ++j) { float a = ld_clamped(img, gx, gy + yb + j); v += box_term<MODE>(a, cen); }
       V[yb * vp + xp] = v;
       for (int y = yb + 1; y < ye; ++y) {
-        float a = ld_clamped(img, gx, gy + y + ky - 1); v += MODE ? (double)a : (double)__fmul_rn(a, a);
-        float b = ld_clamped(img, gx, gy + y - 1); v -= MODE ? (double)b : (double)__fmul_rn(b, b);
+        float a = ld_clamped(img, gx, gy + y + ky - 1); v += box_term<MODE>(a, cen);
+        float b = ld_clamped(img, gx, gy + y - 1); v -= box_term<MODE>(b, cen);
         V[y * vp + xp] = v;
       }
     }
@@ -334,16 +342,21 @@ int box_sq_inv_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh
   size_t smem = (size_t)K1G_TILE * ((K1G_TILE + kx - 1) | 1) * sizeof(double);
   VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((ow + K1G_TILE - 1) / K1G_TILE, (oh + K1G_TILE - 1) / K1G_TILE);
-  box_sq_inv_kernel<0><<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, out, nullptr);
+  box_sq_inv_kernel<0><<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, out, nullptr, 0.0f);
   VWB_LAUNCH_CHECK();
   return VWB200_OK;
 }
-int box_sum_i32_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, int* out, cudaStream_t st) {
+int box_sum_i32_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, int* out, cudaStream_t st, int centred, float c) {
   if (ow <= 0 || oh <= 0) return VWB200_OK;
   size_t smem = (size_t)K1G_TILE * ((K1G_TILE + kx - 1) | 1) * sizeof(double);
-  VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((ow + K1G_TILE - 1) / K1G_TILE, (oh + K1G_TILE - 1) / K1G_TILE);
-  box_sq_inv_kernel<1><<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, nullptr, out);
+  if (centred) {
+    VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    box_sq_inv_kernel<2><<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, nullptr, out, c);
+  } else {
+    VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    box_sq_inv_kernel<1><<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, nullptr, out, 0.0f);
+  }
   VWB_LAUNCH_CHECK();
   return VWB200_OK;
 }
@@ -360,6 +373,11 @@ __global__ void k1_nan_fixup_kernel(ImgF L, ImgF R, const Zone* __restrict__ zon
     const int x = k % z.w, y = k / z.w;
     vwb200_dispi* o = out + z.obase + (ptrdiff_t)y * z.opitch + x;
     if (o->valid != 2) continue;
+    if (COST == VWB200_CROSS_CORRELATION) {
+      // zero-energy LEFT window: every cost is 0 * inf = NaN, so best stays NaN at (0,0) and best == worst is false (:110-133)
+      const double lp = ncc.inv_l[(ptrdiff_t)(z.ly + y - ncc.l_oy) * ncc.l_w + (z.lx + x - ncc.l_ox)];
+      if (isinf(lp)) { o->dx = z.addx; o->dy = z.addy; o->valid = 1; continue; }
+    }
     double best = 0, worst = 0;
     int bd = 0;
     for (int dy = 0; dy < z.sy; ++dy)
