@@ -40,7 +40,7 @@ static constexpr float SQ_SLACK = 8192.0f;
 static size_t screen_smem_bytes(const FastGeom& g, int mode) {
   return (size_t)F_TH * F_COLS * 4                                                   // T
          + (size_t)g.ltile_rows * F_COLS * 2 + (size_t)g.ring_slots * g.rw * 2      // left tile, right ring (int16)
-         + (mode == M_NCC ? 2 : 1) * (size_t)NQ_SLOTS * g.rw * 4 + 64;              // A ring (+ Qi ring)
+         + (mode == M_NCC ? 2 : 1) * (size_t)NQ_SLOTS * g.rw * 4 + 128;              // A ring (+ Qi ring)
 }
 
 static bool screen_params(int mode, int kx, int ky, float vmin, float vmax, int* c_out, double* maxc_out) {
@@ -208,22 +208,40 @@ struct ScreenCtx {           // what the exact evaluation needs
 __device__ unsigned long long g_screen_stats[8];   // candidates, warp events, survivors, overflow, flushes
 #endif
 
+// shared-memory accesses by 32-bit shared-window address (no generic-pointer arithmetic on the rare path)
+__device__ __forceinline__ float lds_volatile_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void atoms_max_s32(uint32_t a, int v) {
+  asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ int atoms_add_s32(uint32_t a, int v) {
+  int old;
+  asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+// per-item constants of the rare path, kept in shared memory so that a call only marshals what changes
+struct CandCtx { uint4* list; unsigned char* nan_band; int cap; int W; int cnt; int next[2]; int pad; };
+
 // One candidate (lane-divergent, ~0.1 % of the evaluations): raise the pixel's threshold to a float lower bound of this
-// disparity's cost and append it to the CTA's list.  pix = y*256 + x inside the band, didx = raster index inside the chunk.
+// disparity's cost and append it to the CTA's list.  key = pix | didx << 13 (pix = y*256 + x inside the band, didx = raster
+// index inside the chunk); t_sa = shared address of the pixel's threshold, c_sa = shared address of the CandCtx.
 template <int MODE>
-__device__ __noinline__ void screen_candidate(float* __restrict__ thr, int* __restrict__ cnt, uint4* __restrict__ list, int cap,
-                                              unsigned char* __restrict__ nan_px, int pix, int didx, int sprime, float f,
-                                              float A, float nB, float Qi) {
+__device__ __noinline__ void screen_candidate(uint32_t t_sa, uint32_t c_sa, uint32_t key, int sprime, float f, float A, float nB, float Qi) {
 #ifdef VWB_SCREEN_STATS
   atomicAdd(&g_screen_stats[0], 1ull);
 #endif
-  const float T = *reinterpret_cast<volatile float*>(thr);
+  const float T = lds_volatile_f32(t_sa);
   if (!(T < INFINITY)) return;                          // pixel closed (outside the raster, or marked for replay)
+  const CandCtx* cc = reinterpret_cast<const CandCtx*>(__cvta_shared_to_generic(c_sa));
+  const int pix = key & 8191;
   float U, L;
   if (MODE == M_NCC) {
     if (Qi <= QI_ZERO) {                                // zero-energy right window: this cost is NaN, the pixel is replayed
-      *nan_px = 1;
-      atomicMax(reinterpret_cast<int*>(thr), 0x7f800000);
+      cc->nan_band[(size_t)(pix >> 8) * cc->W + (pix & 255)] = 1;
+      atoms_max_s32(t_sa, 0x7f800000);
       return;
     }
     const float t = (f + A) - nB;                       // ~ box(l*r) + E, within NCC_SLACK
@@ -236,12 +254,12 @@ __device__ __noinline__ void screen_candidate(float* __restrict__ thr, int* __re
     U = k + SQ_SLACK;
     L = fmaxf(k - SQ_SLACK, 0.0f);
   }
-  atomicMax(reinterpret_cast<int*>(thr), __float_as_int(L));
-  const int slot = atomicAdd(cnt, 1);
-  if (slot < cap) list[slot] = make_uint4((uint32_t)pix | ((uint32_t)didx << 13), (uint32_t)sprime, __float_as_uint(U), 0u);
+  atoms_max_s32(t_sa, __float_as_int(L));
+  const int slot = atoms_add_s32(c_sa + (uint32_t)offsetof(CandCtx, cnt), 1);
+  if (slot < cc->cap) cc->list[slot] = make_uint4(key, (uint32_t)sprime, __float_as_uint(U), 0u);
   else {                                                // list full: replay the pixel instead
-    *nan_px = 1;
-    atomicMax(reinterpret_cast<int*>(thr), 0x7f800000);
+    cc->nan_band[(size_t)(pix >> 8) * cc->W + (pix & 255)] = 1;
+    atoms_max_s32(t_sa, 0x7f800000);
 #ifdef VWB_SCREEN_STATS
     atomicAdd(&g_screen_stats[3], 1ull);
 #endif
@@ -251,8 +269,7 @@ __device__ __noinline__ void screen_candidate(float* __restrict__ thr, int* __re
 template <int KX, bool FULL, int MODE>
 __device__ __forceinline__ void screen_pass(const int16_t* __restrict__ ltile, const int16_t* __restrict__ rring,
                                             const float* __restrict__ qring, const float* __restrict__ aring,
-                                            float* __restrict__ thr, const float* __restrict__ b_band, int* __restrict__ cnt,
-                                            uint4* __restrict__ list, int cap, unsigned char* __restrict__ nan_band, int W,
+                                            float* __restrict__ thr, const float* __restrict__ b_band, uint32_t c_sa,
                                             int lane, int g, int ky, int ring_slots, int rw, int ring_base, int qbase,
                                             int row0, int nb, int sx, int dy_rel) {
   int V[8][F_B];
@@ -343,16 +360,16 @@ __device__ __forceinline__ void screen_pass(const int16_t* __restrict__ ltile, c
 #ifdef VWB_SCREEN_STATS
         if (__ffs(__activemask()) - 1 == lane) atomicAdd(&g_screen_stats[1], 1ull);
 #endif
+        const uint32_t t_sa = smem_u32(trow);
+        const uint32_t key0 = (uint32_t)((row0 + y) * F_COLS + 8 * lane) | ((uint32_t)(dy_rel * sx + F_B * g + b) << 13);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const float t = *reinterpret_cast<volatile float*>(trow + r * 32);      // re-read: keeps these tests out of the hot path
+          const float t = lds_volatile_f32(t_sa + 128u * r);                    // re-read: keeps these tests out of the hot path
           const float rhs = MODE == M_NCC ? __fadd_rd(__fmaf_rd(t, Qv[r + b], Bv[r]), -Av[r + b])
                                           : __fadd_rd(__fmaf_rd(0.5f, t, Bv[r]), Av[r + b]);
           if (!(f[r] < rhs)) {
-            screen_candidate<MODE>(trow + r * 32, cnt, list, cap, nan_band + (size_t)(row0 + y) * W + 8 * lane + r,
-                                   (row0 + y) * F_COLS + 8 * lane + r, dy_rel * sx + F_B * g + b, o[r], f[r], Av[r + b], Bv[r],
-                                   MODE == M_NCC ? Qv[r + b] : 1.0f);
-            const float t2 = *reinterpret_cast<volatile float*>(trow + r * 32);
+            screen_candidate<MODE>(t_sa + 128u * r, c_sa, key0 + r, o[r], f[r], Av[r + b], Bv[r], MODE == M_NCC ? Qv[r + b] : 1.0f);
+            const float t2 = lds_volatile_f32(t_sa + 128u * r);
             Tv[r] = MODE == M_NCC ? t2 : __fmaf_rd(0.5f, t2, Bv[r]);
           }
         }
@@ -431,10 +448,10 @@ k1_screen_kernel(const int16_t* __restrict__ L16, const int16_t* __restrict__ R1
   float* aring = reinterpret_cast<float*>(rring + (size_t)G.ring_slots * G.rw);
   float* qring = aring + (size_t)NQ_SLOTS * G.rw;                                           // NCC only
   uint64_t* bars = reinterpret_cast<uint64_t*>(aring + (size_t)(MODE == M_NCC ? 2 : 1) * NQ_SLOTS * G.rw);
-  int* cnt = reinterpret_cast<int*>(bars + 2);
+  CandCtx* cc = reinterpret_cast<CandCtx*>(bars + 2);
+  const uint32_t c_sa = smem_u32(cc);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int sub = w & (F_SUBSETS - 1), half = w / F_SUBSETS, row0 = half * F_RH;
-  const int ngroups = (G.sx + F_B - 1) / F_B;
+  const int ngroups = (G.sx + F_B - 1) / F_B, nunits = ngroups * F_HALVES;
   unsigned long long* bk = bk_all + (size_t)blockIdx.x * F_TH * F_COLS;
   int* bi = bi_all + (size_t)blockIdx.x * F_TH * F_COLS;
   uint4* list = list_all + (size_t)blockIdx.x * cap;
@@ -461,7 +478,7 @@ k1_screen_kernel(const int16_t* __restrict__ L16, const int16_t* __restrict__ R1
       tma_load_1d(rring, rsrc, (uint32_t)G.ltile_rows * rrow_bytes, &bars[0]);
       tma_load_1d(aring, asrc, (uint32_t)F_TH * qrow_bytes, &bars[0]);       // window-origin rows y0+dy0 .. +31 -> slots 0..31
       if (MODE == M_NCC) tma_load_1d(qring, qsrc, (uint32_t)F_TH * qrow_bytes, &bars[0]);
-      *cnt = 0;
+      cc->list = list; cc->nan_band = nan_band; cc->cap = cap; cc->W = G.W; cc->cnt = 0; cc->next[0] = 0; cc->next[1] = 0;
     }
     // thresholds: 0 for live pixels (every cost key is >= 0), +inf for closed ones (outside the raster / strip; NCC:
     // zero-energy left window = every cost NaN -> replay)
@@ -479,30 +496,40 @@ k1_screen_kernel(const int16_t* __restrict__ L16, const int16_t* __restrict__ R1
     __syncthreads();
     mbar_wait(&bars[0], ph0); ph0 ^= 1;
     for (int dy = 0; dy < ndy; ++dy) {
-      const int ring_base = (dy + row0) % G.ring_slots;
-      const int qbase = (dy + row0) % NQ_SLOTS;
-      if (tid == 0 && dy + 1 < ndy) {
-        fence_proxy_async();
-        mbar_expect_tx(&bars[1], rrow_bytes + NRINGS * qrow_bytes);
-        tma_load_1d(rring + (size_t)((dy + G.ltile_rows) % G.ring_slots) * G.rw, rsrc + (size_t)(dy + G.ltile_rows) * G.rw, rrow_bytes, &bars[1]);
-        tma_load_1d(aring + (size_t)((dy + F_TH) % NQ_SLOTS) * G.rw, asrc + (size_t)(dy + F_TH) * G.rw, qrow_bytes, &bars[1]);
-        if (MODE == M_NCC)
-          tma_load_1d(qring + (size_t)((dy + F_TH) % NQ_SLOTS) * G.rw, qsrc + (size_t)(dy + F_TH) * G.rw, qrow_bytes, &bars[1]);
+      if (tid == 0) {
+        cc->next[(dy + 1) & 1] = 0;
+        if (dy + 1 < ndy) {
+          fence_proxy_async();
+          mbar_expect_tx(&bars[1], rrow_bytes + NRINGS * qrow_bytes);
+          tma_load_1d(rring + (size_t)((dy + G.ltile_rows) % G.ring_slots) * G.rw, rsrc + (size_t)(dy + G.ltile_rows) * G.rw, rrow_bytes, &bars[1]);
+          tma_load_1d(aring + (size_t)((dy + F_TH) % NQ_SLOTS) * G.rw, asrc + (size_t)(dy + F_TH) * G.rw, qrow_bytes, &bars[1]);
+          if (MODE == M_NCC)
+            tma_load_1d(qring + (size_t)((dy + F_TH) % NQ_SLOTS) * G.rw, qsrc + (size_t)(dy + F_TH) * G.rw, qrow_bytes, &bars[1]);
+        }
       }
-      for (int g = sub; g < ngroups; g += F_SUBSETS) {
+      // work units of this dy = (dx octet, row half); warps draw them from a shared counter: the octets around the
+      // cost peak carry most of the candidate handling, a static split would leave the other warps waiting at the barrier
+      for (;;) {
+        int u = 0;
+        if (lane == 0) u = atoms_add_s32(c_sa + (uint32_t)offsetof(CandCtx, next) + 4u * (dy & 1), 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= nunits) break;
+        const int g = u % ngroups, row0 = (u / ngroups) * F_RH;
+        const int ring_base = (dy + row0) % G.ring_slots;
+        const int qbase = (dy + row0) % NQ_SLOTS;
         if (G.sx - F_B * g >= F_B)
-          screen_pass<KX, true, MODE>(ltile, rring, qring, aring, thr, b_band, cnt, list, cap, nan_band, G.W, lane, g, G.ky, G.ring_slots,
-                                      G.rw, ring_base, qbase, row0, F_B, G.sx, dy);
+          screen_pass<KX, true, MODE>(ltile, rring, qring, aring, thr, b_band, c_sa, lane, g, G.ky, G.ring_slots, G.rw, ring_base, qbase, row0,
+                                      F_B, G.sx, dy);
         else
-          screen_pass<KX, false, MODE>(ltile, rring, qring, aring, thr, b_band, cnt, list, cap, nan_band, G.W, lane, g, G.ky, G.ring_slots,
-                                       G.rw, ring_base, qbase, row0, G.sx - F_B * g, G.sx, dy);
+          screen_pass<KX, false, MODE>(ltile, rring, qring, aring, thr, b_band, c_sa, lane, g, G.ky, G.ring_slots, G.rw, ring_base, qbase, row0,
+                                       G.sx - F_B * g, G.sx, dy);
       }
       if (dy + 1 < ndy) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
       __syncthreads();
-      const int n = min(*reinterpret_cast<volatile int*>(cnt), cap);
+      const int n = min(*reinterpret_cast<volatile int*>(&cc->cnt), cap);
       if (n > cap / 2 || (dy + 1 == ndy && n > 0)) {            // uniform across the CTA
         __syncthreads();
-        if (tid == 0) *cnt = 0;
+        if (tid == 0) cc->cnt = 0;
         screen_flush<MODE>(cx, thr, list, n, bk, bi, s0, y0, dy0, G.sx, tid);
 #ifdef VWB_SCREEN_STATS
         if (tid == 0) atomicAdd(&g_screen_stats[4], 1ull);
