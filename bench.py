@@ -260,6 +260,14 @@ def run_ours(a):
         alg_bytes = H * S * (4 + 4 + 12)                 # left + right + 12-byte disparity pixel
         achieved = alg_bytes / (kms * 1e-3) / 1e9
         evals = H * S * s * s
+        kname = "k1_generic_kernel" if path != "exact-int" else ("k1_fast_abs_kernel" if a.cost == "abs" else "k1_screen_kernel")
+        traffic = None
+        try:          # measured once under ncu for the default workload; null for any other
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json"))).get(f"{kname}|{S}|{s}|{a.kernel}|{a.cost}")
+            if tr and world == 1:
+                traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+        except Exception:
+            pass
         line = {
             "metric": "disparity Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -271,8 +279,10 @@ def run_ours(a):
                     "d2h_bytes_per_step": int(hout_np.nbytes), "ms_per_step": te / a.steps, "bytes_are": "per rank"},
             "gpu_launches": int(nl.item()),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_is": which, "kernel": "k1_fast_abs_kernel" if path == "exact-int" else "k1_generic_kernel",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/traffic_r01.json)",
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "peak_is": which, "kernel": kname,
                          "kernel_ms": kms, "kernel_share_of_step": kms * a.steps / ms if world == 1 else None,
                          "note": "ALU/issue-bound by construction (SURVEY 8d): ~10 issue slots per pixel*disparity vs 20 B per pixel",
                          "alu": {"achieved_Teval_s": evals / (kms * 1e-3) / 1e12, "evals_per_launch": evals}},
