@@ -1,12 +1,15 @@
 """Time PyramidCorrelationView.rasterize over all tiles of a synthetic pair (BASELINE config 3 shape).
-Usage: python tools/time_view.py SIZE TILE LEVELS COST KERNEL SEARCH [check]"""
+Usage: [THREADS=n] python tools/time_view.py SIZE TILE LEVELS COST KERNEL SEARCH [check]
+THREADS > 1 rasterises tiles from a pool of host threads, as VW's block writer does (Image/ImageIO.h:228-235)."""
 import sys, os, time
+from concurrent.futures import ThreadPoolExecutor
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import visionworkbench_b200 as v
 from visionworkbench_b200.synth import make_pair
 S, T, LV, cost, k, s = [int(a) for a in sys.argv[1:7]]
 check = len(sys.argv) > 7
+NT = int(os.environ.get("THREADS", "1"))
 search = (-s // 2, -s // 2, s // 2, s // 2)
 t0 = time.time()
 left, right, lm, rm, _ = make_pair(S, S, search, 103, dropout=0.0 if os.environ.get("NODROP") else 0.03)
@@ -17,11 +20,18 @@ out = torch.empty((S, S, 3), dtype=torch.float32, device="cuda")
 for it in range(2):
     n0 = v.kernel_launches()
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    for y in range(0, S, T):
-        for x in range(0, S, T):
-            out[y:y+T, x:x+T] = view.rasterize(None, (x, y, min(S, x+T), min(S, y+T)))
+    tiles = [(x, y) for y in range(0, S, T) for x in range(0, S, T)]
+    def one(t):
+        x, y = t
+        out[y:y+T, x:x+T] = view.rasterize(None, (x, y, min(S, x+T), min(S, y+T)))
+    if NT > 1:
+        with ThreadPoolExecutor(NT) as ex:
+            list(ex.map(one, tiles))
+    else:
+        for t in tiles:
+            one(t)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print(f"view {S}x{S} tiles {T} levels {LV} cost {cost} k{k} search {s}: {dt*1e3:.1f} ms  {S*S/dt/1e6:.2f} Mpix/s  launches {v.kernel_launches()-n0}  valid {float((out[...,2]>0).float().mean()):.3f}")
+    print(f"view {S}x{S} tiles {T} levels {LV} cost {cost} k{k} search {s} threads {NT}: {dt*1e3:.1f} ms  {S*S/dt/1e6:.2f} Mpix/s  launches {v.kernel_launches()-n0}  valid {float((out[...,2]>0).float().mean()):.3f}")
 if check:
     import oracle
     p = oracle.make_params(search, (k, k), cost=cost, consistency_threshold=2.0, filter_half_kernel=5, max_pyramid_levels=LV)
