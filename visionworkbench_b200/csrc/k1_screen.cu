@@ -339,6 +339,8 @@ __device__ __forceinline__ void screen_pass(const int16_t* __restrict__ ltile, c
         Tv[r] = MODE == M_NCC ? t : __fmaf_rd(0.5f, t, Bv[r]);            // SQ: T/2 + nB
       }
     }
+    // hot part: branch-free over the 8 dx of the octet; bit b of `hit` = some pixel of this lane is a candidate at dx b
+    uint32_t hit = 0;
 #pragma unroll
     for (int b = 0; b < F_B; ++b) {
       if (!FULL && b >= nb) break;
@@ -347,30 +349,41 @@ __device__ __forceinline__ void screen_pass(const int16_t* __restrict__ ltile, c
 #pragma unroll
       for (int a = 1; a < 8; ++a) p[a] = p[a - 1] + V[a][b];
       window_sums<KX>(p, o);
-      float f[8];
       bool any = false;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        f[r] = __int2float_rn(o[r]);
+        const float f = __int2float_rn(o[r]);
         const float rhs = MODE == M_NCC ? __fadd_rd(__fmaf_rd(Tv[r], Qv[r + b], Bv[r]), -Av[r + b])      // T*Qi - B - E - A
                                         : __fadd_rd(Tv[r], Av[r + b]);                                     // T/2 + nB + A
-        any |= !(f[r] < rhs);
+        any |= !(f < rhs);
       }
-      if (any) {
-#ifdef VWB_SCREEN_STATS
-        if (__ffs(__activemask()) - 1 == lane) atomicAdd(&g_screen_stats[1], 1ull);
-#endif
-        const uint32_t t_sa = smem_u32(trow);
-        const uint32_t key0 = (uint32_t)((row0 + y) * F_COLS + 8 * lane) | ((uint32_t)(dy_rel * sx + F_B * g + b) << 13);
+      if (any) hit |= 1u << b;
+    }
+    // rare part (warp-uniform branches): recompute the window sums of the flagged dx (V is unchanged) and hand the
+    // candidates over.  ~4 % of the (row, dx) pairs get here.
+    if (__any_sync(0xffffffffu, hit != 0)) {
+      const uint32_t t_sa = smem_u32(trow);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float t = lds_volatile_f32(t_sa + 128u * r);                    // re-read: keeps these tests out of the hot path
-          const float rhs = MODE == M_NCC ? __fadd_rd(__fmaf_rd(t, Qv[r + b], Bv[r]), -Av[r + b])
-                                          : __fadd_rd(__fmaf_rd(0.5f, t, Bv[r]), Av[r + b]);
-          if (!(f[r] < rhs)) {
-            screen_candidate<MODE>(t_sa + 128u * r, c_sa, key0 + r, o[r], f[r], Av[r + b], Bv[r], MODE == M_NCC ? Qv[r + b] : 1.0f);
-            const float t2 = lds_volatile_f32(t_sa + 128u * r);
-            Tv[r] = MODE == M_NCC ? t2 : __fmaf_rd(0.5f, t2, Bv[r]);
+      for (int b = 0; b < F_B; ++b) {
+        if (!FULL && b >= nb) break;
+        if (!__any_sync(0xffffffffu, (hit >> b) & 1u)) continue;
+#ifdef VWB_SCREEN_STATS
+        if (lane == 0) atomicAdd(&g_screen_stats[1], 1ull);
+#endif
+        int p[8], o[8];
+        p[0] = V[0][b];
+#pragma unroll
+        for (int a = 1; a < 8; ++a) p[a] = p[a - 1] + V[a][b];
+        window_sums<KX>(p, o);
+        if ((hit >> b) & 1u) {
+          const uint32_t key0 = (uint32_t)((row0 + y) * F_COLS + 8 * lane) | ((uint32_t)(dy_rel * sx + F_B * g + b) << 13);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float f = __int2float_rn(o[r]);
+            const float t = lds_volatile_f32(t_sa + 128u * r);
+            const float rhs = MODE == M_NCC ? __fadd_rd(__fmaf_rd(t, Qv[r + b], Bv[r]), -Av[r + b])
+                                            : __fadd_rd(__fmaf_rd(0.5f, t, Bv[r]), Av[r + b]);
+            if (!(f < rhs)) screen_candidate<MODE>(t_sa + 128u * r, c_sa, key0 + r, o[r], f, Av[r + b], Bv[r], MODE == M_NCC ? Qv[r + b] : 1.0f);
           }
         }
       }
