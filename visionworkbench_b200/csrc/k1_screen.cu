@@ -76,6 +76,9 @@ struct ScreenWs {
   unsigned long long* pk; int* pi;   // per-dy-chunk partials (J > 1)
   unsigned char* nanflag;            // W x H: replay this pixel (NaN cost seen, or its candidates overflowed the list)
   Zone* zone;
+  // seeding stage: half-resolution AbsoluteCost search -> predicted disparity -> exact cost there -> initial threshold
+  float *L2, *R2, *T0; vwb200_dispi* d2; unsigned char* ws2; size_t ws2_bytes;
+  int W2, H2, kx2, ky2, sx2, sy2;
   size_t total;
 };
 static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -105,6 +108,15 @@ static ScreenWs carve(const FastGeom& g, int mode, void* base) {
   w.pi = (int*)take(g.J > 1 ? (size_t)g.J * g.W * g.H * 4 : 16);
   w.nanflag = take((size_t)g.W * g.H);
   w.zone = (Zone*)take(sizeof(Zone));
+  w.W2 = (g.W + 1) / 2; w.H2 = (g.H + 1) / 2;
+  w.kx2 = std::max(3, (g.kx / 2) | 1); w.ky2 = std::max(1, (g.ky / 2) | 1);
+  w.sx2 = (((g.sx + 1) / 2 + 7) / 8) * 8; w.sy2 = (g.sy + 1) / 2;
+  w.L2 = (float*)take((size_t)(w.W2 + w.kx2 - 1) * (w.H2 + w.ky2 - 1) * 4);
+  w.R2 = (float*)take((size_t)(w.W2 + w.kx2 - 1 + w.sx2 - 1) * (w.H2 + w.ky2 - 1 + w.sy2 - 1) * 4);
+  w.d2 = (vwb200_dispi*)take((size_t)w.W2 * w.H2 * sizeof(vwb200_dispi));
+  w.T0 = (float*)take((size_t)g.W * g.H * 4);
+  w.ws2_bytes = k1_fast_workspace_bytes(w.W2, w.H2, w.sx2, w.sy2, w.kx2, w.ky2);
+  w.ws2 = take(w.ws2_bytes);
   w.total = off;
   return w;
 }
@@ -172,6 +184,46 @@ __global__ void screen_pack_b_kernel(const int* __restrict__ Sl, int c, double K
   }
 }
 
+// ---- seeding stage ---------------------------------------------------------------------------------------------
+// every second pixel of every second row (clamped at the edges): integer imagery stays integer
+__global__ void screen_subsample2_kernel(ImgF in, int ow, int oh, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= ow || y >= oh) return;
+  out[(size_t)y * ow + x] = in.p[(ptrdiff_t)min(2 * y, in.h - 1) * in.pitch + min(2 * x, in.w - 1)];
+}
+// T0(pixel) = float lower bound of the exact cost key at d0 = 2 * (half-resolution arg-best): any searched disparity gives
+// a valid lower bound of the best cost, a good prediction makes it a tight one (the hot loop then drops everything
+// outside the immediate neighbourhood of the peak without creating candidates).
+template <int MODE>
+__global__ void screen_seed_kernel(ImgF L, ImgF R, const vwb200_dispi* __restrict__ d2, int W2, FastGeom g, int c, long long K,
+                                   const int* __restrict__ Sl, const int* __restrict__ Sr, const double* __restrict__ rp,
+                                   float* __restrict__ T0) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= g.W || y >= g.H) return;
+  const vwb200_dispi q = d2[(size_t)(y >> 1) * W2 + (x >> 1)];
+  const int dx = min(2 * q.dx, g.sx - 1), dy = min(2 * q.dy, g.sy - 1);
+  int s = 0;
+  for (int j = 0; j < g.ky; ++j) {
+    const float* lr = L.p + (ptrdiff_t)(y + j) * L.pitch + x;
+    const float* rr = R.p + (ptrdiff_t)(y + j + dy) * R.pitch + x + dx;
+    for (int i = 0; i < g.kx; ++i) s += ((int)lr[i] - c) * ((int)rr[i] - c);
+  }
+  const int ow = g.W + g.sx - 1;
+  const size_t kl = (size_t)y * g.W + x, kr = (size_t)(y + dy) * ow + (x + dx);
+  float t = 0.0f;
+  if (MODE == M_NCC) {
+    const double r = rp[kr];
+    if (!isinf(r)) {
+      const long long slr = (long long)s + (long long)c * ((long long)Sl[kl] + (long long)Sr[kr]) - K;
+      t = __double2float_rd((double)slr * sqrt(r) * (1.0 - 1.0e-6));
+    }
+  } else {
+    const long long cost = (long long)Sl[kl] + (long long)Sr[kr] - 2ll * (long long)s;
+    t = __double2float_rd((double)(K - cost) * (1.0 - 1.0e-6) - 1.0);
+  }
+  T0[kl] = t > 0.0f ? t : 0.0f;
+}
+
 // ---- device helpers -----------------------------------------------------------------------------------------
 // prmt with sign replication (selector nibble 8|k = msb of byte k in all 8 bits); __byte_perm() only honours 3 selector bits
 __device__ __forceinline__ int prmt_s(uint32_t a, uint32_t sel) {
@@ -202,6 +254,7 @@ struct ScreenCtx {           // what the exact evaluation needs
   unsigned char* nanflag;
   int W, H, ow, c;
   long long K;                              // NCC: N c^2;  SQ: M0 = 4 N maxc^2 (>= any cost)
+  const float* T0;                          // initial thresholds (lower bound of the cost at a predicted disparity) or null
 };
 
 #ifdef VWB_SCREEN_STATS
@@ -500,7 +553,7 @@ k1_screen_kernel(const int16_t* __restrict__ L16, const int16_t* __restrict__ R1
       const int x = 8 * l + r;
       float t = INFINITY;
       if (x < G.out_cols && s0 + x < G.W && y0 + y < G.H) {
-        t = 0.0f;
+        t = cx.T0 ? cx.T0[(size_t)(y0 + y) * G.W + s0 + x] : 0.0f;
         if (MODE == M_NCC && b_band[y * F_COLS + x] == INFINITY) { t = INFINITY; nan_band[(size_t)y * G.W + x] = 1; }
       }
       thr[k] = t;
@@ -654,7 +707,23 @@ static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, 
     screen_pack_b_kernel<MODE><<<gb, 256, 0, st>>>(ws.Sl, c, (double)K, g, ws.Bp);
     VWB_LAUNCH_CHECK();
   }
-  ScreenCtx cx{ws.lp, ws.rp, ws.Sl, ws.Sr, ws.nanflag, W, H, ow, c, K};
+  // seeding stage (skipped when the half-resolution problem is outside what k1_fast handles)
+  const float* T0 = nullptr;
+  if (!getenv("VWB200_SCREEN_NOSEED") && W >= 64 && H >= 64 &&
+      k1_fast_supported(VWB200_ABSOLUTE_DIFFERENCE, ws.kx2, ws.ky2, ws.sx2, ws.sy2, vmin, vmax, true) == VWB200_OK) {
+    const int lw2 = ws.W2 + ws.kx2 - 1, lh2 = ws.H2 + ws.ky2 - 1, rw2 = lw2 + ws.sx2 - 1, rh2 = lh2 + ws.sy2 - 1;
+    dim3 b2(32, 8);
+    screen_subsample2_kernel<<<dim3((lw2 + 31) / 32, (lh2 + 7) / 8), b2, 0, st>>>(left, lw2, lh2, ws.L2);
+    VWB_LAUNCH_CHECK();
+    screen_subsample2_kernel<<<dim3((rw2 + 31) / 32, (rh2 + 7) / 8), b2, 0, st>>>(right, rw2, rh2, ws.R2);
+    VWB_LAUNCH_CHECK();
+    VWB_TRY(k1_fast_launch(VWB200_ABSOLUTE_DIFFERENCE, ImgF{ws.L2, lw2, lh2, lw2}, ImgF{ws.R2, rw2, rh2, rw2}, ws.W2, ws.H2, ws.sx2, ws.sy2,
+                           ws.kx2, ws.ky2, vmin, vmax, ws.d2, ws.W2, ws.ws2, ws.ws2_bytes, st));
+    screen_seed_kernel<MODE><<<dim3((W + 31) / 32, (H + 7) / 8), b2, 0, st>>>(left, right, ws.d2, ws.W2, g, c, K, ws.Sl, ws.Sr, ws.rp, ws.T0);
+    VWB_LAUNCH_CHECK();
+    T0 = ws.T0;
+  }
+  ScreenCtx cx{ws.lp, ws.rp, ws.Sl, ws.Sr, ws.nanflag, W, H, ow, c, K, T0};
   int dev = 0, nsm = 148;
   VWB_CUDA(cudaGetDevice(&dev));
   VWB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
