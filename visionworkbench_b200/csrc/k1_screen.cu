@@ -575,10 +575,15 @@ k1_screen_kernel(const int16_t* __restrict__ L16, const int16_t* __restrict__ R1
       }
       // work units of this dy = (dx octet, row half); warps draw them from a shared counter: the octets around the
       // cost peak carry most of the candidate handling, a static split would leave the other warps waiting at the barrier
-      for (;;) {
-        int u = 0;
-        if (lane == 0) u = atoms_add_s32(c_sa + (uint32_t)offsetof(CandCtx, next) + 4u * (dy & 1), 1);
-        u = __shfl_sync(0xffffffffu, u, 0);
+      for (int uu = 0;; ++uu) {
+        int u;
+        if (G.pad_dynamic) {
+          u = 0;
+          if (lane == 0) u = atoms_add_s32(c_sa + (uint32_t)offsetof(CandCtx, next) + 4u * (dy & 1), 1);
+          u = __shfl_sync(0xffffffffu, u, 0);
+        } else {
+          u = w + F_WARPS * uu;                            // static round-robin: unit u -> (octet u % ngroups, half u / ngroups)
+        }
         if (u >= nunits) break;
         const int g = u % ngroups, row0 = (u / ngroups) * F_RH;
         const int ring_base = (dy + row0) % G.ring_slots;
@@ -678,6 +683,7 @@ static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, 
                            vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev) {
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
   g.scale = 1;
+  g.pad_dynamic = getenv("VWB200_SCREEN_DYNAMIC") ? atoi(getenv("VWB200_SCREEN_DYNAMIC")) : 1;
   int c; double maxc;
   if (!screen_params(MODE, kx, ky, vmin, vmax, &c, &maxc)) { set_error("k1_screen: unsupported value range"); return VWB200_ENOIMPL; }
   const ScreenWs ws = carve(g, MODE, workspace);
