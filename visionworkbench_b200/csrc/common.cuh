@@ -69,8 +69,9 @@ struct NccMaps { const double* inv_l; int l_ox, l_oy, l_w, l_h; const double* in
 struct KEvents { cudaEvent_t e0 = nullptr, e1 = nullptr; };
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
                       int kx, int ky, NccMaps ncc, vwb200_dispi* out, double* scratch_cost, int* scratch_idx, bool clamp_reads,
-                      bool stage, cudaStream_t st, const KEvents* ev = nullptr);
+                      int stage_r_floats, cudaStream_t st, const KEvents* ev = nullptr);   // stage_r_floats: 0 = read through L1
 bool k1_generic_can_stage(int kx, int ky, int sx, int sy, int nchunks);
+long long k1_generic_stage_floats(int kx, int ky, int sx, int sy, int nchunks);
 static constexpr int K1G_DCHUNK = 256;
 // merge the per-chunk partial results of split zones (zone indices in d_split)
 int k1_generic_merge_launch(int cost, const Zone* d_zones, const int* d_split, int nsplit, const double* scratch_cost,

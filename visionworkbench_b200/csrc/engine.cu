@@ -119,10 +119,23 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
   std::vector<Tile> tiles, tiles_post;
   make_tiles(zones, k1_generic_tile_w(kx), k1_generic_tile_h(ky), tiles, true);
   if (skip) tiles.erase(std::remove_if(tiles.begin(), tiles.end(), [&](const Tile& t) { return (*skip)[t.zone] != 0; }), tiles.end());
-  // tiles whose right search patch fits in shared memory first (staged kernel), the rest after (L1 reads)
-  std::stable_partition(tiles.begin(), tiles.end(), [&](const Tile& t) { return k1_generic_can_stage(kx, ky, zones[t.zone].sx, zones[t.zone].sy, zones[t.zone].nchunks); });
-  int n_staged = 0;
-  for (const Tile& t : tiles) if (k1_generic_can_stage(kx, ky, zones[t.zone].sx, zones[t.zone].sy, zones[t.zone].nchunks)) ++n_staged;
+  // three launches: tiles with a small right search patch (staged; little shared memory -> 2-3 CTAs per SM), tiles with
+  // a large one (staged, 1 CTA per SM), and tiles whose patch does not fit (reads through L1)
+  static constexpr long long SMALL_R = 6144;
+  auto cls = [&](const Tile& t) {
+    const Zone& z = zones[t.zone];
+    const long long f = k1_generic_stage_floats(kx, ky, z.sx, z.sy, z.nchunks);
+    return !k1_generic_can_stage(kx, ky, z.sx, z.sy, z.nchunks) ? 2 : (f <= SMALL_R ? 0 : 1);
+  };
+  std::stable_sort(tiles.begin(), tiles.end(), [&](const Tile& a, const Tile& b) { return cls(a) < cls(b); });
+  int n_cls[3] = {0, 0, 0};
+  long long r_max[3] = {0, 0, 0};
+  for (const Tile& t : tiles) {
+    const int c = cls(t);
+    const Zone& z = zones[t.zone];
+    ++n_cls[c];
+    r_max[c] = std::max(r_max[c], k1_generic_stage_floats(kx, ky, z.sx, z.sy, z.nchunks));
+  }
   Zone* d_zones; Tile* d_tiles;
   double* d_sc = nullptr; int* d_si = nullptr; int* d_split = nullptr;
   if (!split.empty()) {
@@ -148,9 +161,17 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
     VWB_TRY(box_sq_inv_launch(right, kx, ky, rx0, ry0, rx1 - rx0, ry1 - ry0, ir, st));
     ncc = NccMaps{il, lx0, ly0, lx1 - lx0, ly1 - ly0, ir, rx0, ry0, rx1 - rx0, ry1 - ry0};
   }
-  VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles, n_staged, kx, ky, ncc, d_out, d_sc, d_si, clamp_reads, true, st, ev));
-  VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles + n_staged, (int)tiles.size() - n_staged, kx, ky, ncc, d_out, d_sc, d_si,
-                            clamp_reads, false, st, n_staged ? nullptr : ev));
+  {
+    int off = 0;
+    bool ev_used = false;
+    for (int c = 0; c < 3; ++c) {
+      if (!n_cls[c]) continue;
+      VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles + off, n_cls[c], kx, ky, ncc, d_out, d_sc, d_si, clamp_reads,
+                                c == 2 ? 0 : (int)r_max[c], st, ev_used ? nullptr : ev));
+      ev_used = true;
+      off += n_cls[c];
+    }
+  }
   VWB_TRY(k1_generic_merge_launch(cost, d_zones, d_split, (int)split.size(), d_sc, d_si, d_out, st));
   if (cost == VWB200_CROSS_CORRELATION)
     VWB_TRY(k1_nan_fixup_launch(cost, left, right, d_zones, (int)zones.size(), kx, ky, ncc, d_out, st));

@@ -602,7 +602,7 @@ int k1_fast_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy
 #undef KCASE
     default: set_error("k1_fast: unsupported kernel width %d", kx); return VWB200_ENOIMPL;
   }
-  VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per-function state shared by all host threads: device maximum
   if (ev && ev->e0) cudaEventRecord(ev->e0, st);
   kern<<<grid, F_THREADS, smem, st>>>(L16, R16, g, idx, out, opitch, part_cost, part_idx);
   VWB_LAUNCH_CHECK();

@@ -82,10 +82,11 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
   const int vp = (ZT_W + kx - 1) | 1;                         // odd pitch: conflict-free when lanes walk rows
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* Vall = reinterpret_cast<double*>(smem_raw);          // [ZWARPS][ZT_H][vp]
-  double* bestall = Vall + (size_t)ZWARPS * ZT_H * vp;         // [ZWARPS][ZT_H*ZT_W]   (merge only)
-  int* bidxall = reinterpret_cast<int*>(bestall + (size_t)ZWARPS * ZT_H * ZT_W);
-  float* sL = reinterpret_cast<float*>(bidxall + (size_t)ZWARPS * ZT_H * ZT_W);   // [ph][pw]      (STAGE)
+  float* sL = reinterpret_cast<float*>(Vall + (size_t)ZWARPS * ZT_H * vp);          // [ph][pw]      (STAGE)
   float* sR = sL + (size_t)(ZT_H + ky - 1) * (ZT_W + kx - 1);                      // [ph+sy-1][pw+sx-1]
+  // the merge buffers are only used after the disparity loop and alias everything above
+  double* bestall = reinterpret_cast<double*>(smem_raw);        // [ZWARPS][ZT_H*ZT_W]
+  int* bidxall = reinterpret_cast<int*>(bestall + (size_t)ZWARPS * ZT_H * ZT_W);
   double* V = Vall + (size_t)warp * ZT_H * vp;
   const int lx0 = z.lx + t.tx, ly0 = z.ly + t.ty;
   const int rx0 = z.rx + t.tx, ry0 = z.ry + t.ty;
@@ -173,6 +174,7 @@ k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __
   }
   // ---- publish the warp's private bests, merge across warps; epilogue: 12-byte pixel writes ----
   const int nw = (nd - d_begin) < ZWARPS ? (nd - d_begin) : ZWARPS;
+  __syncthreads();            // every warp is done with V / the staged patches: reuse the memory for the merge
   if (p2 && warp < nw) {
 #pragma unroll
     for (int xi = 0; xi < ZCW; ++xi)
@@ -244,24 +246,28 @@ int k1_generic_merge_launch(int cost, const Zone* d_zones, const int* d_split, i
   return VWB200_OK;
 }
 
-static size_t k1g_smem_bytes(int kx, int ky, bool stage) {
+static size_t k1g_smem_bytes(int kx, int ky, int stage_r_floats) {
   const size_t vp = (size_t)((ZT_W + kx - 1) | 1);
-  size_t b = (size_t)ZWARPS * ZT_H * vp * sizeof(double) + (size_t)ZWARPS * ZT_H * ZT_W * (sizeof(double) + sizeof(int));
-  if (stage) b += ((size_t)(ZT_H + ky - 1) * (ZT_W + kx - 1) + ZR_MAX) * sizeof(float);
-  return b;
+  size_t b = (size_t)ZWARPS * ZT_H * vp * sizeof(double);
+  if (stage_r_floats > 0) b += ((size_t)(ZT_H + ky - 1) * (ZT_W + kx - 1) + (size_t)stage_r_floats) * sizeof(float);
+  const size_t merge = (size_t)ZWARPS * ZT_H * ZT_W * (sizeof(double) + sizeof(int));
+  return b > merge ? b : merge;
 }
-bool k1_generic_can_stage(int kx, int ky, int sx, int sy, int nchunks) {
-  // a CTA of a split zone only touches the search rows of its K1G_DCHUNK disparities
+// floats of right search patch a CTA of this zone stages (a CTA of a split zone only touches the search rows of its
+// K1G_DCHUNK disparities); > ZR_MAX: not staged
+long long k1_generic_stage_floats(int kx, int ky, int sx, int sy, int nchunks) {
   const int span = nchunks > 1 ? std::min(sy, (K1G_DCHUNK + sx - 1) / sx + 1) : sy;
-  return (long long)(ZT_W + kx - 1 + sx - 1) * (ZT_H + ky - 1 + span - 1) <= ZR_MAX;
+  return (long long)(ZT_W + kx - 1 + sx - 1) * (ZT_H + ky - 1 + span - 1);
 }
+bool k1_generic_can_stage(int kx, int ky, int sx, int sy, int nchunks) { return k1_generic_stage_floats(kx, ky, sx, sy, nchunks) <= ZR_MAX; }
 
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
                       int kx, int ky, NccMaps ncc, vwb200_dispi* out, double* scratch_cost, int* scratch_idx, bool clamp_reads,
-                      bool stage, cudaStream_t st, const KEvents* ev) {
+                      int stage_r_floats, cudaStream_t st, const KEvents* ev) {
   if (ntiles <= 0) return VWB200_OK;
   if (kx > 129 || ky > 129) { set_error("kernel size %dx%d exceeds the supported 129", kx, ky); return VWB200_ENOIMPL; }
-  const size_t smem = k1g_smem_bytes(kx, ky, stage);
+  const bool stage = stage_r_floats > 0;
+  const size_t smem = k1g_smem_bytes(kx, ky, stage_r_floats);
   void (*kern)(ImgF, ImgF, const Zone*, const Tile*, int, int, NccMaps, vwb200_dispi*, double*, int*);
 #define KSEL(C) (stage ? k1_generic_kernel<C, true, true> : (clamp_reads ? k1_generic_kernel<C, true, false> : k1_generic_kernel<C, false, false>))
   switch (cost) {
@@ -270,7 +276,9 @@ int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, cons
     default:                        kern = KSEL(VWB200_ABSOLUTE_DIFFERENCE); break;
   }
 #undef KSEL
-  VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the attribute is per-function state shared by all host threads: always the device maximum, never the per-launch size
+  if (smem > 227 * 1024) { set_error("zone kernel needs %zu bytes of shared memory", smem); return VWB200_ENOIMPL; }
+  VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (ev && ev->e0) cudaEventRecord(ev->e0, st);
   kern<<<ntiles, K1G_THREADS, smem, st>>>(left, right, d_zones, d_tiles, kx, ky, ncc, out, scratch_cost, scratch_idx);
   VWB_LAUNCH_CHECK();
@@ -340,7 +348,7 @@ box_sq_inv_kernel(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, do
 int box_sq_inv_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* out, cudaStream_t st) {
   if (ow <= 0 || oh <= 0) return VWB200_OK;
   size_t smem = (size_t)K1G_TILE * ((K1G_TILE + kx - 1) | 1) * sizeof(double);
-  VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per-function state shared by all host threads: device maximum
   dim3 grid((ow + K1G_TILE - 1) / K1G_TILE, (oh + K1G_TILE - 1) / K1G_TILE);
   box_sq_inv_kernel<0><<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, out, nullptr, 0.0f);
   VWB_LAUNCH_CHECK();
@@ -351,10 +359,10 @@ int box_sum_i32_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int o
   size_t smem = (size_t)K1G_TILE * ((K1G_TILE + kx - 1) | 1) * sizeof(double);
   dim3 grid((ow + K1G_TILE - 1) / K1G_TILE, (oh + K1G_TILE - 1) / K1G_TILE);
   if (centred) {
-    VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per-function state shared by all host threads: device maximum
     box_sq_inv_kernel<2><<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, nullptr, out, c);
   } else {
-    VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VWB_CUDA(cudaFuncSetAttribute(box_sq_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per-function state shared by all host threads: device maximum
     box_sq_inv_kernel<1><<<grid, K1G_THREADS, smem, st>>>(img, kx, ky, ox0, oy0, ow, oh, nullptr, out, 0.0f);
   }
   VWB_LAUNCH_CHECK();

@@ -746,7 +746,7 @@ static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, 
 #undef KCASE
     default: set_error("k1_screen: unsupported kernel width %d", kx); return VWB200_ENOIMPL;
   }
-  VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per-function state shared by all host threads: device maximum
   if (ev && ev->e0) cudaEventRecord(ev->e0, st);
   kern<<<grid, F_THREADS, smem, st>>>(ws.L16, ws.R16, ws.Qp, ws.Ap, ws.Bp, g, qrows, cx, ws.bk, ws.bi, ws.list, ws.cap, out, opitch, ws.pk, ws.pi);
   VWB_LAUNCH_CHECK();

@@ -111,7 +111,7 @@ int rm_outliers_launch(const vwb200_dispi* in, int w, int h, int hx, int hy, dou
   if (hx <= 0 || hy <= 0) { set_error("RmOutliersFunc: half kernel sizes must be non-zero."); return VWB200_EARG; }  // DisparityMap.h:345-346
   const size_t smem = (size_t)(RO_TW + 2 * hx) * (RO_TH + 2 * hy) * 2 * sizeof(int);
   if (smem > 200 * 1024) { set_error("outlier filter half kernel %dx%d too large", hx, hy); return VWB200_ENOIMPL; }
-  VWB_CUDA(cudaFuncSetAttribute(rm_outliers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VWB_CUDA(cudaFuncSetAttribute(rm_outliers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per-function state shared by all host threads: device maximum
   dim3 b(RO_TW, RO_TH), g((ow + RO_TW - 1) / RO_TW, (oh + RO_TH - 1) / RO_TH);
   rm_outliers_kernel<<<g, b, smem, st>>>(in, w, h, hx, hy, pt, rt, x0, y0, ow, oh, out);
   VWB_LAUNCH_CHECK();
