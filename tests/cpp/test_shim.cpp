@@ -6,6 +6,8 @@
 #include <thread>
 #include <vector>
 #include "vwb200/PyramidCorrelationView.h"
+#include "vwb200/ParabolaSubpixelView.h"
+#include <cmath>
 #include "../../oracle/vw_oracle.h"
 
 using namespace vw;
@@ -66,7 +68,31 @@ int main() {
         }
     }
     std::printf("shim: %ld mismatches, %ld valid of %d\n", bad, valid, W * H);
-    return bad ? 1 : 0;
+    if (bad) return 1;
+
+    // sub-pixel refinement through the second shim (Stereo/ParabolaSubpixelView.h:28-117)
+    ImageView<PixelMask<Vector2f>> disp = crop(view, BBox2i(0, 0, W, H));
+    threw = false;
+    try { b200_parabola_subpixel(crop(view, BBox2i(0, 0, W - 1, H)), left, right, PREFILTER_NONE, 0.f, kernel); }
+    catch (ArgumentErr const&) { threw = true; }
+    if (!threw) { std::printf("FAIL: size mismatch accepted\n"); return 1; }
+    B200ParabolaSubpixelView sub = b200_parabola_subpixel(disp, left, right, PREFILTER_LOG, 1.4f, kernel);
+    const BBox2i sb(40, 30, 150, 120);
+    ImageView<PixelMask<Vector2f>> fine = crop(sub, sb);
+    std::vector<float> sref(size_t(sb.width()) * sb.height() * 3);
+    if (vwo_parabola_subpixel(reinterpret_cast<const float*>(disp.data()), W, H, reinterpret_cast<const float*>(left.data()), W,
+                              reinterpret_cast<const float*>(right.data()), W, H, W, 7, 7, 1, 1.4f, sb.min()[0], sb.min()[1],
+                              sb.max()[0], sb.max()[1], sref.data())) return 1;
+    long sbad = 0, moved = 0;
+    for (int y = 0; y < sb.height(); ++y)
+      for (int x = 0; x < sb.width(); ++x) {
+        const PixelMask<Vector2f>& g = fine(x, y);
+        const float* r = &sref[(size_t(y) * sb.width() + x) * 3];
+        if (std::fabs(g.child()[0] - r[0]) > 1e-5f || std::fabs(g.child()[1] - r[1]) > 1e-5f || (is_valid(g) ? 1.f : 0.f) != r[2]) ++sbad;
+        if (is_valid(g) && g.child()[0] != std::floor(g.child()[0])) ++moved;
+      }
+    std::printf("subpixel shim: %ld mismatches, %ld refined of %d\n", sbad, moved, sb.width() * sb.height());
+    return sbad ? 1 : 0;
   } catch (LogicErr const& e) {
     std::printf("NODEVICE-or-CUDA: %s\n", e.what());
     return 3;

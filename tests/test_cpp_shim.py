@@ -16,7 +16,7 @@ def _build():
     oracle.build()
     os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
     src = os.path.join(ROOT, "tests", "cpp", "test_shim.cpp")
-    deps = [src, os.path.join(ROOT, "include", "vwb200", "PyramidCorrelationView.h"), os.path.join(ROOT, "include", "vwb200", "vw_standin.h")]
+    deps = [src] + [os.path.join(ROOT, "include", "vwb200", f) for f in ("PyramidCorrelationView.h", "ParabolaSubpixelView.h", "vw_standin.h")]
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
                                "-L", os.path.join(ROOT, "visionworkbench_b200"), "-lvwb200",
@@ -40,4 +40,4 @@ def test_shim_matches_oracle_from_threads():
     exe = _build()
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 mismatches" in r.stdout
+    assert "shim: 0 mismatches" in r.stdout and "subpixel shim: 0 mismatches" in r.stdout, r.stdout

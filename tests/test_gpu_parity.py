@@ -431,3 +431,18 @@ def test_screened_kernel_flat_regions_overflow_to_replay(vwb, oracle, cost):
     ref = oracle.calc_disparity(cost, left, right, search, kernel)
     assert (ref[..., 2] == 0).any() and (ref[..., 2] == 1).any()
     _assert_disp_equal(got, ref, "flat")
+
+
+@pytest.mark.parametrize("cost,kernel", [(2, (9, 9)), (1, (21, 21)), (2, (21, 21))])
+def test_view_single_level_uses_screened_kernel(vwb, oracle, cost, kernel):
+    """pyramid_correlate(max_pyramid_levels=0) with NCC / wide SquaredCost: the level-0 zone goes to k1_screen with the
+    zone's origins (edge-extended reads), the R->L pass' negative offsets and the half-resolution seeding stage."""
+    from visionworkbench_b200.synth import make_pair
+    search = (-20, -7, 12, 9)
+    left, right, lm, rm, _ = make_pair(420, 300, search, 63, dropout=0.0)
+    view = vwb.pyramid_correlate(left, right, lm, rm, 0, 0.0, search, kernel, cost, 0, 0.0, 2.0, 0, 3, 0)
+    p = oracle.make_params(search, kernel, cost=cost, consistency_threshold=2.0, filter_half_kernel=3, max_pyramid_levels=0)
+    for bbox in [(0, 0, 420, 300), (100, 60, 400, 290)]:
+        got = view.rasterize(None, bbox)
+        ref = oracle.pyramid_correlate(p, left, right, lm, rm, bbox=bbox)
+        _assert_disp_equal(got, ref, f"single level screened cost {cost} {bbox}")

@@ -83,18 +83,21 @@ int box_sq_inv_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh
 // boxsum(v) (centred == 0) or boxsum((v - c)^2) (centred == 1) as int32 over the same window-origin domain (integer imagery)
 int box_sum_i32_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, int* out, cudaStream_t st, int centred = 0,
                        float c = 0.0f);
+// left/right are whole images; the logical rasters start at (lox,loy) / (rox,roy) (constant edge extension outside),
+// (addx,addy) is added to every output disparity (R->L pass of the level loop)
+struct FastOrigin { int lox, loy, rox, roy, addx, addy; };
 // NCC / wide-range SquaredCost on the exact-integer path with fp32 screening (k1_screen.cu)
 int k1_screen_supported(int cost, int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued);
 size_t k1_screen_workspace_bytes(int cost, int W, int H, int sx, int sy, int kx, int ky);
 int k1_screen_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
-                     vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev = nullptr);
+                     vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev = nullptr,
+                     const FastOrigin* org = nullptr);
 // exact sequential re-evaluation of pixels flagged NaN by k1 (NCC zero-energy windows)
 int k1_nan_fixup_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, int nzones, int kx, int ky,
                         NccMaps ncc, vwb200_dispi* out, cudaStream_t st, int gridx = 8);
 
 // left/right are whole images; the logical rasters start at (lox,loy) / (rox,roy) (constant edge extension outside),
 // (addx,addy) is added to every output disparity (R->L pass of the level loop)
-struct FastOrigin { int lox, loy, rox, roy, addx, addy; };
 // ---- K1 fast (exact-integer path, single big zone) -------------------------------------------
 // Returns VWB200_ENOIMPL if the configuration is outside what the fast path handles.
 int k1_fast_supported(int cost, int kx, int ky, int sx, int sy, float vmin, float vmax, bool integer_valued);

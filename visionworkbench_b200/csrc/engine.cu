@@ -538,13 +538,19 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
     if (level == 0 && tile_integer) {
       auto try_fast = [&](const Zone& z, ImgF a, ImgF b, vwb200_dispi* dst, char& flag) -> int {
         if ((long long)z.w * z.h < 128 * 128 || (long long)z.sx * z.sy < 256) return VWB200_OK;
-        if (k1_fast_supported(p.cost_type, kx, ky, z.sx, z.sy, tile_vmin, tile_vmax, true) != VWB200_OK) return VWB200_OK;
-        const size_t wb = k1_fast_workspace_bytes(z.w, z.h, z.sx, z.sy, kx, ky);
-        unsigned char* ws;
-        VWB_TRY(ar.alloc(&ws, wb));
         const FastOrigin org{z.lx, z.ly, z.rx, z.ry, z.addx, z.addy};
-        VWB_TRY(k1_fast_launch(p.cost_type, a, b, z.w, z.h, z.sx, z.sy, kx, ky, tile_vmin, tile_vmax, dst + z.obase, z.opitch, ws, wb, st, nullptr, &org));
-        flag = 1;
+        unsigned char* ws;
+        if (k1_fast_supported(p.cost_type, kx, ky, z.sx, z.sy, tile_vmin, tile_vmax, true) == VWB200_OK) {
+          const size_t wb = k1_fast_workspace_bytes(z.w, z.h, z.sx, z.sy, kx, ky);
+          VWB_TRY(ar.alloc(&ws, wb));
+          VWB_TRY(k1_fast_launch(p.cost_type, a, b, z.w, z.h, z.sx, z.sy, kx, ky, tile_vmin, tile_vmax, dst + z.obase, z.opitch, ws, wb, st, nullptr, &org));
+          flag = 1;
+        } else if (k1_screen_supported(p.cost_type, kx, ky, z.sx, z.sy, tile_vmin, tile_vmax, true) == VWB200_OK) {
+          VWB_TRY(ar.alloc(&ws, k1_screen_workspace_bytes(p.cost_type, z.w, z.h, z.sx, z.sy, kx, ky)));
+          VWB_TRY(k1_screen_launch(p.cost_type, a, b, z.w, z.h, z.sx, z.sy, kx, ky, tile_vmin, tile_vmax, dst + z.obase, z.opitch, ws, st, nullptr, &org));
+          flag = 1;
+          if (getenv("VWB200_DEBUG")) fprintf(stderr, "[vwb200] level 0 zone %dx%d search %dx%d -> k1_screen\n", z.w, z.h, z.sx, z.sy);
+        }
         return VWB200_OK;
       };
       for (size_t i = 0; i < zl.size(); ++i) VWB_TRY(try_fast(zl[i], Ll, Rl, disp, fast_l[i]));

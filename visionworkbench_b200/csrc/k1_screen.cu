@@ -126,6 +126,11 @@ size_t k1_screen_workspace_bytes(int cost, int W, int H, int sx, int sy, int kx,
 }
 
 __global__ void screen_set_zone_kernel(Zone* dst, Zone z) { *dst = z; }
+// constant edge extension (Image/EdgeExtension.tcc:47-59): zones of the level loop may reach outside the rasters
+__device__ __forceinline__ float ld_edge(const ImgF& im, int x, int y) {
+  x = max(0, min(x, im.w - 1)); y = max(0, min(y, im.h - 1));
+  return __ldg(im.p + (ptrdiff_t)y * im.pitch + x);
+}
 
 // ---- pack kernels ---------------------------------------------------------------------------------------------
 __global__ void screen_pack_img_kernel(ImgF img, int c, FastGeom g, int right, int16_t* __restrict__ out) {
@@ -137,7 +142,7 @@ __global__ void screen_pack_img_kernel(ImgF img, int c, FastGeom g, int right, i
   for (int col = threadIdx.x; col < rowlen; col += blockDim.x) {
     const int gx = s0 + col;
     int16_t v = 0;
-    if (row < lh && gx < lw) v = (int16_t)((int)img.p[(ptrdiff_t)row * img.pitch + gx] - c);
+    if (row < lh && gx < lw) v = (int16_t)((int)ld_edge(img, (right ? g.rox : g.lox) + gx, (right ? g.roy : g.loy) + row) - c);
     o[col] = v;
   }
 }
@@ -186,10 +191,10 @@ __global__ void screen_pack_b_kernel(const int* __restrict__ Sl, int c, double K
 
 // ---- seeding stage ---------------------------------------------------------------------------------------------
 // every second pixel of every second row (clamped at the edges): integer imagery stays integer
-__global__ void screen_subsample2_kernel(ImgF in, int ow, int oh, float* __restrict__ out) {
+__global__ void screen_subsample2_kernel(ImgF in, int ox, int oy, int ow, int oh, float* __restrict__ out) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= ow || y >= oh) return;
-  out[(size_t)y * ow + x] = in.p[(ptrdiff_t)min(2 * y, in.h - 1) * in.pitch + min(2 * x, in.w - 1)];
+  out[(size_t)y * ow + x] = ld_edge(in, ox + 2 * x, oy + 2 * y);
 }
 // T0(pixel) = float lower bound of the exact cost key at d0 = 2 * (half-resolution arg-best): any searched disparity gives
 // a valid lower bound of the best cost, a good prediction makes it a tight one (the hot loop then drops everything
@@ -203,11 +208,9 @@ __global__ void screen_seed_kernel(ImgF L, ImgF R, const vwb200_dispi* __restric
   const vwb200_dispi q = d2[(size_t)(y >> 1) * W2 + (x >> 1)];
   const int dx = min(2 * q.dx, g.sx - 1), dy = min(2 * q.dy, g.sy - 1);
   int s = 0;
-  for (int j = 0; j < g.ky; ++j) {
-    const float* lr = L.p + (ptrdiff_t)(y + j) * L.pitch + x;
-    const float* rr = R.p + (ptrdiff_t)(y + j + dy) * R.pitch + x + dx;
-    for (int i = 0; i < g.kx; ++i) s += ((int)lr[i] - c) * ((int)rr[i] - c);
-  }
+  for (int j = 0; j < g.ky; ++j)
+    for (int i = 0; i < g.kx; ++i)
+      s += ((int)ld_edge(L, g.lox + x + i, g.loy + y + j) - c) * ((int)ld_edge(R, g.rox + x + i + dx, g.roy + y + j + dy) - c);
   const int ow = g.W + g.sx - 1;
   const size_t kl = (size_t)y * g.W + x, kr = (size_t)(y + dy) * ow + (x + dx);
   float t = 0.0f;
@@ -662,7 +665,7 @@ __global__ void k1_screen_allequal_fixup(ImgF L, ImgF R, FastGeom g, const doubl
     long long s = 0;
     for (int j = 0; j < g.ky; ++j)
       for (int i = 0; i < g.kx; ++i) {
-        const long long a = (long long)L.p[(ptrdiff_t)(y + j) * L.pitch + x + i], b = (long long)R.p[(ptrdiff_t)(y + j + dy) * R.pitch + x + i + dx];
+        const long long a = (long long)ld_edge(L, g.lox + x + i, g.loy + y + j), b = (long long)ld_edge(R, g.rox + x + i + dx, g.roy + y + j + dy);
         s += MODE == M_NCC ? a * b : (a - b) * (a - b);
       }
     if (MODE == M_NCC)
@@ -680,9 +683,10 @@ __global__ void k1_screen_allequal_fixup(ImgF L, ImgF R, FastGeom g, const doubl
 
 template <int MODE>
 static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
-                           vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev) {
+                           vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev, const FastOrigin* org) {
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
   g.scale = 1;
+  if (org) { g.lox = org->lox; g.loy = org->loy; g.rox = org->rox; g.roy = org->roy; g.addx = org->addx; g.addy = org->addy; }
   g.pad_dynamic = getenv("VWB200_SCREEN_DYNAMIC") ? atoi(getenv("VWB200_SCREEN_DYNAMIC")) : 1;
   int c; double maxc;
   if (!screen_params(MODE, kx, ky, vmin, vmax, &c, &maxc)) { set_error("k1_screen: unsupported value range"); return VWB200_ENOIMPL; }
@@ -693,13 +697,13 @@ static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, 
   const long long K = MODE == M_NCC ? (long long)N * c * c : 4ll * N * (long long)maxc * (long long)maxc;
   // exact maps (reference definitions), then the packed hot-loop operands
   if (MODE == M_NCC) {
-    VWB_TRY(box_sq_inv_launch(left, kx, ky, 0, 0, W, H, ws.lp, st));
-    VWB_TRY(box_sq_inv_launch(right, kx, ky, 0, 0, ow, oh, ws.rp, st));
-    VWB_TRY(box_sum_i32_launch(left, kx, ky, 0, 0, W, H, ws.Sl, st));
-    VWB_TRY(box_sum_i32_launch(right, kx, ky, 0, 0, ow, oh, ws.Sr, st));
+    VWB_TRY(box_sq_inv_launch(left, kx, ky, g.lox, g.loy, W, H, ws.lp, st));
+    VWB_TRY(box_sq_inv_launch(right, kx, ky, g.rox, g.roy, ow, oh, ws.rp, st));
+    VWB_TRY(box_sum_i32_launch(left, kx, ky, g.lox, g.loy, W, H, ws.Sl, st));
+    VWB_TRY(box_sum_i32_launch(right, kx, ky, g.rox, g.roy, ow, oh, ws.Sr, st));
   } else {
-    VWB_TRY(box_sum_i32_launch(left, kx, ky, 0, 0, W, H, ws.Sl, st, 1, (float)c));
-    VWB_TRY(box_sum_i32_launch(right, kx, ky, 0, 0, ow, oh, ws.Sr, st, 1, (float)c));
+    VWB_TRY(box_sum_i32_launch(left, kx, ky, g.lox, g.loy, W, H, ws.Sl, st, 1, (float)c));
+    VWB_TRY(box_sum_i32_launch(right, kx, ky, g.rox, g.roy, ow, oh, ws.Sr, st, 1, (float)c));
   }
   VWB_CUDA(cudaMemsetAsync(ws.nanflag, 0, (size_t)W * H, st));
   {
@@ -719,9 +723,9 @@ static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, 
       k1_fast_supported(VWB200_ABSOLUTE_DIFFERENCE, ws.kx2, ws.ky2, ws.sx2, ws.sy2, vmin, vmax, true) == VWB200_OK) {
     const int lw2 = ws.W2 + ws.kx2 - 1, lh2 = ws.H2 + ws.ky2 - 1, rw2 = lw2 + ws.sx2 - 1, rh2 = lh2 + ws.sy2 - 1;
     dim3 b2(32, 8);
-    screen_subsample2_kernel<<<dim3((lw2 + 31) / 32, (lh2 + 7) / 8), b2, 0, st>>>(left, lw2, lh2, ws.L2);
+    screen_subsample2_kernel<<<dim3((lw2 + 31) / 32, (lh2 + 7) / 8), b2, 0, st>>>(left, g.lox, g.loy, lw2, lh2, ws.L2);
     VWB_LAUNCH_CHECK();
-    screen_subsample2_kernel<<<dim3((rw2 + 31) / 32, (rh2 + 7) / 8), b2, 0, st>>>(right, rw2, rh2, ws.R2);
+    screen_subsample2_kernel<<<dim3((rw2 + 31) / 32, (rh2 + 7) / 8), b2, 0, st>>>(right, g.rox, g.roy, rw2, rh2, ws.R2);
     VWB_LAUNCH_CHECK();
     VWB_TRY(k1_fast_launch(VWB200_ABSOLUTE_DIFFERENCE, ImgF{ws.L2, lw2, lh2, lw2}, ImgF{ws.R2, rw2, rh2, rw2}, ws.W2, ws.H2, ws.sx2, ws.sy2,
                            ws.kx2, ws.ky2, vmin, vmax, ws.d2, ws.W2, ws.ws2, ws.ws2_bytes, st));
@@ -772,11 +776,11 @@ static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, 
   // pixels marked for replay (valid == 2): the reference's sequential best/worst state machine
   {
     Zone z{};
-    z.obase = 0; z.opitch = (int)opitch; z.w = W; z.h = H; z.lx = 0; z.ly = 0; z.rx = 0; z.ry = 0; z.sx = sx; z.sy = sy;
-    z.addx = 0; z.addy = 0; z.nchunks = 1; z.sbase = 0;
+    z.obase = 0; z.opitch = (int)opitch; z.w = W; z.h = H; z.lx = g.lox; z.ly = g.loy; z.rx = g.rox; z.ry = g.roy; z.sx = sx; z.sy = sy;
+    z.addx = g.addx; z.addy = g.addy; z.nchunks = 1; z.sbase = 0;
     screen_set_zone_kernel<<<1, 1, 0, st>>>(ws.zone, z);
     VWB_LAUNCH_CHECK();
-    NccMaps maps{ws.lp, 0, 0, W, H, ws.rp, 0, 0, ow, oh};
+    NccMaps maps{ws.lp, g.lox, g.loy, W, H, ws.rp, g.rox, g.roy, ow, oh};
     const long long px = (long long)W * H;
     const int gridx = (int)std::min<long long>((px + 127) / 128, 148 * 16);
     VWB_TRY(k1_nan_fixup_launch(MODE == M_NCC ? VWB200_CROSS_CORRELATION : VWB200_SQUARED_DIFFERENCE, left, right, ws.zone, 1, kx, ky, maps, out,
@@ -786,9 +790,9 @@ static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, 
 }
 
 int k1_screen_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
-                     vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev) {
-  if (cost == VWB200_CROSS_CORRELATION) return screen_launch_t<M_NCC>(left, right, W, H, sx, sy, kx, ky, vmin, vmax, out, opitch, workspace, st, ev);
-  if (cost == VWB200_SQUARED_DIFFERENCE) return screen_launch_t<M_SQ>(left, right, W, H, sx, sy, kx, ky, vmin, vmax, out, opitch, workspace, st, ev);
+                     vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev, const FastOrigin* org) {
+  if (cost == VWB200_CROSS_CORRELATION) return screen_launch_t<M_NCC>(left, right, W, H, sx, sy, kx, ky, vmin, vmax, out, opitch, workspace, st, ev, org);
+  if (cost == VWB200_SQUARED_DIFFERENCE) return screen_launch_t<M_SQ>(left, right, W, H, sx, sy, kx, ky, vmin, vmax, out, opitch, workspace, st, ev, org);
   set_error("k1_screen: cost type %d not handled", cost);
   return VWB200_ENOIMPL;
 }
