@@ -8,11 +8,14 @@
 //     NCC : box(l*r)     = S' + c*(Sl + Sr[d]) - N*c^2                Sl, Sr   = box sums of l, r
 //     SQ  : box((l-r)^2) = SL2 + SR2[d] - 2*S'                        SL2, SR2 = box sums of (l-c)^2, (r-c)^2
 // The hot loop is the one of k1_fast.cu (TMA-staged tiles, 8 columns x 8 dx per lane, sliding IMAD column sums, shuffle
-// window sums, 4 dx subsets x 2 row halves per CTA) and carries S' EXACTLY.  What it does not do is evaluate the cost:
+// window sums; work unit = one dx octet x one row half of a band, drawn by the 8 warps from a shared counter) and carries S'
+// EXACTLY.  What it does not do is evaluate the cost:
 //   * per pixel a float threshold T is kept that is a proven LOWER bound of the best cost seen so far (NCC: in units of
 //     cost/sqrt(lp); SQ: of M0 - cost).  Per (pixel, d) 3-4 fp32 operations with directed rounding decide whether the cost
 //     CAN reach T ("candidate": float(S') >= T*Qi[d] - B - A[d], resp. float(S') >= T/2 + B + A[d]); everything else
 //     (99.9 % of the evaluations) is provably worse than an already-seen disparity and is dropped.
+//   * T starts from the exact cost at a PREDICTED disparity (half-resolution AbsoluteCost search on k1_fast, doubled): any
+//     searched disparity gives a valid lower bound, a good prediction makes candidates rare (2 per pixel).
 //   * a candidate raises T (a float lower bound of its own cost, a handful of flops) and appends (pixel, d, S', upper bound)
 //     to a per-CTA list in global memory.
 //   * at the end of a band (or when the list is half full) the CTA walks the list with all threads: entries whose upper
@@ -580,7 +583,7 @@ k1_screen_kernel(const int16_t* __restrict__ L16, const int16_t* __restrict__ R1
       // cost peak carry most of the candidate handling, a static split would leave the other warps waiting at the barrier
       for (int uu = 0;; ++uu) {
         int u;
-        if (G.pad_dynamic) {
+        if (G.dynamic_units) {
           u = 0;
           if (lane == 0) u = atoms_add_s32(c_sa + (uint32_t)offsetof(CandCtx, next) + 4u * (dy & 1), 1);
           u = __shfl_sync(0xffffffffu, u, 0);
@@ -687,7 +690,7 @@ static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, 
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
   g.scale = 1;
   if (org) { g.lox = org->lox; g.loy = org->loy; g.rox = org->rox; g.roy = org->roy; g.addx = org->addx; g.addy = org->addy; }
-  g.pad_dynamic = getenv("VWB200_SCREEN_DYNAMIC") ? atoi(getenv("VWB200_SCREEN_DYNAMIC")) : 1;
+  g.dynamic_units = getenv("VWB200_SCREEN_DYNAMIC") ? atoi(getenv("VWB200_SCREEN_DYNAMIC")) : 1;
   int c; double maxc;
   if (!screen_params(MODE, kx, ky, vmin, vmax, &c, &maxc)) { set_error("k1_screen: unsupported value range"); return VWB200_ENOIMPL; }
   const ScreenWs ws = carve(g, MODE, workspace);
