@@ -28,6 +28,7 @@ struct FastGeom {
   int J, dy_per;            // the dy range is split into J chunks of dy_per rows (more, smaller work items for small rasters)
   int lox, loy, rox, roy;   // origin of the (logical) left / right rasters inside the images passed to the pack kernels
   int addx, addy;           // constant added to the output disparities
+  int sd;                   // k1_screen: dy rows per synchronisation period (ring depth)
   int dynamic_units;          // k1_screen: 1 = warps draw (octet, half) work units from a shared counter, 0 = static round-robin
 };
 static inline FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
@@ -41,7 +42,7 @@ static inline FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
   g.lrows = g.NB * F_TH + ky - 1;
   g.rrows = g.NB * F_TH + ky - 1 + sy;
   g.rw = ((F_COLS + sx + 7) / 8) * 8 + 8;
-  g.lox = g.loy = g.rox = g.roy = 0; g.addx = g.addy = 0; g.scale = F_B; g.dynamic_units = 1;
+  g.lox = g.loy = g.rox = g.roy = 0; g.addx = g.addy = 0; g.scale = F_B; g.dynamic_units = 1; g.sd = 1;
   // enough work items to fill 148 persistent CTAs several times over: split the dy range when the raster is small
   g.J = 1;
   const int items = g.NS * g.NB;

@@ -34,7 +34,8 @@
 namespace vwb200 {
 
 enum { M_NCC = 0, M_SQ = 1 };
-static constexpr int NQ_SLOTS = F_TH + 1;
+static constexpr int SD_MAX = 3;                 // dy rows per synchronisation period (ring depth): fewer, cheaper barriers
+static inline __host__ __device__ int nq_slots(int sd) { return F_TH + 2 * sd - 1; }
 static constexpr float QI_ZERO = 1.0e-30f;      // Qi of a zero-energy right window (its cost is NaN)
 static constexpr float NCC_E = 64.0f;           // half ulp of float(S'), |S'| < 2^31
 static constexpr float NCC_SLACK = 4096.0f;     // > all roundings of f + A - nB (magnitudes < 2^33) + conversion + E
@@ -43,7 +44,17 @@ static constexpr float SQ_SLACK = 8192.0f;
 static size_t screen_smem_bytes(const FastGeom& g, int mode) {
   return (size_t)F_TH * F_COLS * 4                                                   // T
          + (size_t)g.ltile_rows * F_COLS * 2 + (size_t)g.ring_slots * g.rw * 2      // left tile, right ring (int16)
-         + (mode == M_NCC ? 2 : 1) * (size_t)NQ_SLOTS * g.rw * 4 + 128;              // A ring (+ Qi ring)
+         + (mode == M_NCC ? 2 : 1) * (size_t)nq_slots(g.sd) * g.rw * 4 + 128;       // A ring (+ Qi ring)
+}
+// ring of right rows: a period of sd dy rows needs ltile_rows + sd - 1 rows resident while the next period's sd rows
+// arrive; the deepest ring that fits in shared memory is used
+static bool screen_geom(FastGeom& g, int mode) {
+  const int rrows0 = g.rrows;
+  for (int sd = SD_MAX; sd >= 1; --sd) {
+    g.sd = sd; g.ring_slots = g.ltile_rows + 2 * sd - 1; g.rrows = rrows0 + SD_MAX;
+    if (screen_smem_bytes(g, mode) <= 227 * 1024) return true;
+  }
+  return false;
 }
 
 static bool screen_params(int mode, int kx, int ky, float vmin, float vmax, int* c_out, double* maxc_out) {
@@ -66,7 +77,7 @@ int k1_screen_supported(int cost, int kx, int ky, int sx, int sy, float vmin, fl
   if (kx < 3 || kx > 31 || ky < 1 || ky > 41) return VWB200_ENOIMPL;
   if (sx < F_B || sx > 512 || sy < 1 || (long long)sx * sy < 64 || (long long)sx * sy > 65536) return VWB200_ENOIMPL;
   FastGeom g = make_geom(256, 32, sx, sy, kx, ky);
-  if (screen_smem_bytes(g, mode) > 227 * 1024) return VWB200_ENOIMPL;
+  if (!screen_geom(g, mode)) return VWB200_ENOIMPL;
   return VWB200_OK;
 }
 
@@ -91,7 +102,7 @@ static ScreenWs carve(const FastGeom& g, int mode, void* base) {
   size_t off = 0;
   auto take = [&](size_t bytes) { unsigned char* q = p ? p + off : nullptr; off += al(bytes); return q; };
   const size_t ow = (size_t)g.W + g.sx - 1, oh = (size_t)g.H + g.sy - 1;
-  const size_t qrows = (size_t)g.NB * F_TH + g.sy;
+  const size_t qrows = (size_t)g.NB * F_TH + g.sy + SD_MAX;
   w.L16 = (int16_t*)take((size_t)g.NS * g.lrows * F_COLS * 2);
   w.R16 = (int16_t*)take((size_t)g.NS * g.rrows * g.rw * 2);
   w.Qp = (float*)take(mode == M_NCC ? (size_t)g.NS * qrows * g.rw * 4 : 16);
@@ -101,12 +112,13 @@ static ScreenWs carve(const FastGeom& g, int mode, void* base) {
   w.rp = (double*)take(mode == M_NCC ? ow * oh * 8 : 16);
   w.Sl = (int*)take((size_t)g.W * g.H * 4);
   w.Sr = (int*)take(ow * oh * 4);
-  w.bk = (unsigned long long*)take((size_t)148 * F_TH * F_COLS * 8);
-  w.bi = (int*)take((size_t)148 * F_TH * F_COLS * 4);
+  const size_t ncta = (size_t)std::min(148, g.NS * g.NB * g.J);          // persistent CTAs actually launched
+  w.bk = (unsigned long long*)take(ncta * F_TH * F_COLS * 8);
+  w.bi = (int*)take(ncta * F_TH * F_COLS * 4);
   // list capacity: a flush is forced when a list is half full at a dy boundary; 24 entries per pixel of a band is ~25x the
   // typical total per pixel.  Entries that do not fit mark their pixel for replay (correct, slow).
   w.cap = F_TH * (F_COLS - (g.kx - 1)) * 24;
-  w.list = (uint4*)take((size_t)148 * w.cap * 16);
+  w.list = (uint4*)take(ncta * w.cap * 16);
   w.pk = (unsigned long long*)take(g.J > 1 ? (size_t)g.J * g.W * g.H * 8 : 16);
   w.pi = (int*)take(g.J > 1 ? (size_t)g.J * g.W * g.H * 4 : 16);
   w.nanflag = take((size_t)g.W * g.H);
@@ -125,6 +137,7 @@ static ScreenWs carve(const FastGeom& g, int mode, void* base) {
 }
 size_t k1_screen_workspace_bytes(int cost, int W, int H, int sx, int sy, int kx, int ky) {
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
+  screen_geom(g, cost == VWB200_CROSS_CORRELATION ? M_NCC : M_SQ);
   return carve(g, cost == VWB200_CROSS_CORRELATION ? M_NCC : M_SQ, nullptr).total + 256;
 }
 
@@ -329,7 +342,7 @@ template <int KX, bool FULL, int MODE>
 __device__ __forceinline__ void screen_pass(const int16_t* __restrict__ ltile, const int16_t* __restrict__ rring,
                                             const float* __restrict__ qring, const float* __restrict__ aring,
                                             float* __restrict__ thr, const float* __restrict__ b_band, uint32_t c_sa,
-                                            int lane, int g, int ky, int ring_slots, int rw, int ring_base, int qbase,
+                                            int lane, int g, int ky, int ring_slots, int nq, int rw, int ring_base, int qbase,
                                             int row0, int nb, int sx, int dy_rel) {
   int V[8][F_B];
 #pragma unroll
@@ -447,7 +460,7 @@ __device__ __forceinline__ void screen_pass(const int16_t* __restrict__ ltile, c
         }
       }
     }
-    if (++qslot == NQ_SLOTS) qslot = 0;
+    if (++qslot == nq) qslot = 0;
   }
 }
 
@@ -518,6 +531,7 @@ k1_screen_kernel(const int16_t* __restrict__ L16, const int16_t* __restrict__ R1
   int16_t* ltile = reinterpret_cast<int16_t*>(smem + (size_t)F_TH * F_COLS * 4);
   int16_t* rring = ltile + (size_t)G.ltile_rows * F_COLS;
   float* aring = reinterpret_cast<float*>(rring + (size_t)G.ring_slots * G.rw);
+  const int SD = G.sd, NQ_SLOTS = nq_slots(G.sd);
   float* qring = aring + (size_t)NQ_SLOTS * G.rw;                                           // NCC only
   uint64_t* bars = reinterpret_cast<uint64_t*>(aring + (size_t)(MODE == M_NCC ? 2 : 1) * NQ_SLOTS * G.rw);
   CandCtx* cc = reinterpret_cast<CandCtx*>(bars + 2);
@@ -545,11 +559,12 @@ k1_screen_kernel(const int16_t* __restrict__ L16, const int16_t* __restrict__ R1
     unsigned char* nan_band = cx.nanflag + (size_t)y0 * G.W + s0;
     if (tid == 0) {
       fence_proxy_async();
-      mbar_expect_tx(&bars[0], lbytes + (uint32_t)G.ltile_rows * rrow_bytes + NRINGS * F_TH * qrow_bytes);
+      // first period: right rows 0 .. ltile_rows + SD - 2 and window-origin rows 0 .. F_TH + SD - 2 (slot = row)
+      mbar_expect_tx(&bars[0], lbytes + (uint32_t)(G.ltile_rows + SD - 1) * rrow_bytes + NRINGS * (F_TH + SD - 1) * qrow_bytes);
       tma_load_1d(ltile, lsrc, lbytes, &bars[0]);
-      tma_load_1d(rring, rsrc, (uint32_t)G.ltile_rows * rrow_bytes, &bars[0]);
-      tma_load_1d(aring, asrc, (uint32_t)F_TH * qrow_bytes, &bars[0]);       // window-origin rows y0+dy0 .. +31 -> slots 0..31
-      if (MODE == M_NCC) tma_load_1d(qring, qsrc, (uint32_t)F_TH * qrow_bytes, &bars[0]);
+      tma_load_1d(rring, rsrc, (uint32_t)(G.ltile_rows + SD - 1) * rrow_bytes, &bars[0]);
+      tma_load_1d(aring, asrc, (uint32_t)(F_TH + SD - 1) * qrow_bytes, &bars[0]);
+      if (MODE == M_NCC) tma_load_1d(qring, qsrc, (uint32_t)(F_TH + SD - 1) * qrow_bytes, &bars[0]);
       cc->list = list; cc->nan_band = nan_band; cc->cap = cap; cc->W = G.W; cc->cnt = 0; cc->next[0] = 0; cc->next[1] = 0;
     }
     // thresholds: 0 for live pixels (every cost key is >= 0), +inf for closed ones (outside the raster / strip; NCC:
@@ -567,44 +582,49 @@ k1_screen_kernel(const int16_t* __restrict__ L16, const int16_t* __restrict__ R1
     }
     __syncthreads();
     mbar_wait(&bars[0], ph0); ph0 ^= 1;
-    for (int dy = 0; dy < ndy; ++dy) {
+    for (int dyp = 0, per = 0; dyp < ndy; dyp += SD, ++per) {
+      const int dcur = min(SD, ndy - dyp);                 // dy rows of this period
+      const int nnext = min(SD, ndy - dyp - dcur);         // dy rows of the next one: their last rows are fetched now
       if (tid == 0) {
-        cc->next[(dy + 1) & 1] = 0;
-        if (dy + 1 < ndy) {
+        cc->next[(per + 1) & 1] = 0;
+        if (nnext > 0) {
           fence_proxy_async();
-          mbar_expect_tx(&bars[1], rrow_bytes + NRINGS * qrow_bytes);
-          tma_load_1d(rring + (size_t)((dy + G.ltile_rows) % G.ring_slots) * G.rw, rsrc + (size_t)(dy + G.ltile_rows) * G.rw, rrow_bytes, &bars[1]);
-          tma_load_1d(aring + (size_t)((dy + F_TH) % NQ_SLOTS) * G.rw, asrc + (size_t)(dy + F_TH) * G.rw, qrow_bytes, &bars[1]);
-          if (MODE == M_NCC)
-            tma_load_1d(qring + (size_t)((dy + F_TH) % NQ_SLOTS) * G.rw, qsrc + (size_t)(dy + F_TH) * G.rw, qrow_bytes, &bars[1]);
+          mbar_expect_tx(&bars[1], (uint32_t)nnext * (rrow_bytes + NRINGS * qrow_bytes));
+          for (int j = 0; j < nnext; ++j) {
+            const int rr = dyp + SD - 1 + G.ltile_rows + j, qr = dyp + SD - 1 + F_TH + j;
+            tma_load_1d(rring + (size_t)(rr % G.ring_slots) * G.rw, rsrc + (size_t)rr * G.rw, rrow_bytes, &bars[1]);
+            tma_load_1d(aring + (size_t)(qr % NQ_SLOTS) * G.rw, asrc + (size_t)qr * G.rw, qrow_bytes, &bars[1]);
+            if (MODE == M_NCC) tma_load_1d(qring + (size_t)(qr % NQ_SLOTS) * G.rw, qsrc + (size_t)qr * G.rw, qrow_bytes, &bars[1]);
+          }
         }
       }
-      // work units of this dy = (dx octet, row half); warps draw them from a shared counter: the octets around the
-      // cost peak carry most of the candidate handling, a static split would leave the other warps waiting at the barrier
+      // work units of this period = (dy, dx octet, row half); warps draw them from a shared counter: unit durations
+      // differ (candidate handling around the cost peak), a static split leaves warps waiting at the barrier
       for (int uu = 0;; ++uu) {
         int u;
         if (G.dynamic_units) {
           u = 0;
-          if (lane == 0) u = atoms_add_s32(c_sa + (uint32_t)offsetof(CandCtx, next) + 4u * (dy & 1), 1);
+          if (lane == 0) u = atoms_add_s32(c_sa + (uint32_t)offsetof(CandCtx, next) + 4u * (per & 1), 1);
           u = __shfl_sync(0xffffffffu, u, 0);
         } else {
           u = w + F_WARPS * uu;                            // static round-robin: unit u -> (octet u % ngroups, half u / ngroups)
         }
-        if (u >= nunits) break;
-        const int g = u % ngroups, row0 = (u / ngroups) * F_RH;
+        if (u >= nunits * dcur) break;
+        const int dy = dyp + u / nunits, uu2 = u % nunits;
+        const int g = uu2 % ngroups, row0 = (uu2 / ngroups) * F_RH;
         const int ring_base = (dy + row0) % G.ring_slots;
         const int qbase = (dy + row0) % NQ_SLOTS;
         if (G.sx - F_B * g >= F_B)
-          screen_pass<KX, true, MODE>(ltile, rring, qring, aring, thr, b_band, c_sa, lane, g, G.ky, G.ring_slots, G.rw, ring_base, qbase, row0,
+          screen_pass<KX, true, MODE>(ltile, rring, qring, aring, thr, b_band, c_sa, lane, g, G.ky, G.ring_slots, NQ_SLOTS, G.rw, ring_base, qbase, row0,
                                       F_B, G.sx, dy);
         else
-          screen_pass<KX, false, MODE>(ltile, rring, qring, aring, thr, b_band, c_sa, lane, g, G.ky, G.ring_slots, G.rw, ring_base, qbase, row0,
+          screen_pass<KX, false, MODE>(ltile, rring, qring, aring, thr, b_band, c_sa, lane, g, G.ky, G.ring_slots, NQ_SLOTS, G.rw, ring_base, qbase, row0,
                                        G.sx - F_B * g, G.sx, dy);
       }
-      if (dy + 1 < ndy) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
+      if (nnext > 0) { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
       __syncthreads();
       const int n = min(*reinterpret_cast<volatile int*>(&cc->cnt), cap);
-      if (n > cap / 2 || (dy + 1 == ndy && n > 0)) {            // uniform across the CTA
+      if (n > cap / 2 || (dyp + dcur == ndy && n > 0)) {        // uniform across the CTA
         __syncthreads();
         if (tid == 0) cc->cnt = 0;
         screen_flush<MODE>(cx, thr, list, n, bk, bi, s0, y0, dy0, G.sx, tid);
@@ -688,6 +708,7 @@ template <int MODE>
 static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
                            vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev, const FastOrigin* org) {
   FastGeom g = make_geom(W, H, sx, sy, kx, ky);
+  if (!screen_geom(g, MODE)) { set_error("k1_screen: search width %d does not fit in shared memory", sx); return VWB200_ENOIMPL; }
   g.scale = 1;
   if (org) { g.lox = org->lox; g.loy = org->loy; g.rox = org->rox; g.roy = org->roy; g.addx = org->addx; g.addy = org->addy; }
   g.dynamic_units = getenv("VWB200_SCREEN_DYNAMIC") ? atoi(getenv("VWB200_SCREEN_DYNAMIC")) : 1;
@@ -696,7 +717,7 @@ static int screen_launch_t(ImgF left, ImgF right, int W, int H, int sx, int sy, 
   const ScreenWs ws = carve(g, MODE, workspace);
   const int N = kx * ky;
   const int ow = W + sx - 1, oh = H + sy - 1;
-  const int qrows = g.NB * F_TH + sy;
+  const int qrows = g.NB * F_TH + sy + SD_MAX;
   const long long K = MODE == M_NCC ? (long long)N * c * c : 4ll * N * (long long)maxc * (long long)maxc;
   // exact maps (reference definitions), then the packed hot-loop operands
   if (MODE == M_NCC) {
