@@ -446,3 +446,36 @@ def test_view_single_level_uses_screened_kernel(vwb, oracle, cost, kernel):
         got = view.rasterize(None, bbox)
         ref = oracle.pyramid_correlate(p, left, right, lm, rm, bbox=bbox)
         _assert_disp_equal(got, ref, f"single level screened cost {cost} {bbox}")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_screened_kernel_randomised_imagery(vwb, oracle, seed):
+    """Adversarial inputs for the fp32 screening of k1_screen: narrow-band (low contrast) imagery with masses of near ties,
+    dark / zero areas, full 12-bit range, shifted origins, odd sizes -- NCC and SquaredCost must stay bit-identical."""
+    rng = np.random.default_rng(1000 + seed)
+    W, H = int(rng.integers(64, 330)), int(rng.integers(64, 120))
+    kx = int(rng.choice([3, 7, 15, 21])); ky = int(rng.choice([3, 7, 15, 21]))
+    sx = int(rng.choice([8, 11, 16, 37])); sy = int(rng.integers(8, 13))
+    style = seed % 4
+    rw, rh = W + kx - 1 + sx - 1, H + ky - 1 + sy - 1
+    if style == 0:      # narrow band near the top of the range
+        right = 3900.0 + np.floor(rng.random((rh, rw)) * 40)
+    elif style == 1:    # full range noise with a dark quarter and a zero block
+        right = np.floor(rng.random((rh, rw)) * 4096)
+        right[: rh // 2, : rw // 2] = np.floor(right[: rh // 2, : rw // 2] / 512)
+        right[rh // 3: rh // 3 + 12, rw // 3: rw // 3 + 40] = 0
+    elif style == 2:    # smooth ramp + 1 bit of noise: long plateaus of equal costs
+        yy, xx = np.mgrid[0:rh, 0:rw]
+        right = np.floor((xx * 7 + yy * 3) % 1024 + rng.integers(0, 2, (rh, rw)))
+    else:               # 10-bit texture
+        right = np.floor(rng.random((rh, rw)) * 1024)
+    right = right.astype(np.float32)
+    dx0, dy0 = int(rng.integers(0, sx)), int(rng.integers(0, sy))
+    left = np.ascontiguousarray(right[dy0:dy0 + H + ky - 1, dx0:dx0 + W + kx - 1]).copy()
+    left += np.floor(rng.random(left.shape) * 3).astype(np.float32) * (style != 2)
+    left = np.clip(left, 0, 4095)
+    for cost in (2, 1):
+        got = vwb.calc_disparity(cost, left, right, (sx, sy), (kx, ky))
+        assert vwb.last_k1_stats()["path"] == "exact-int"
+        ref = oracle.calc_disparity(cost, left, right, (sx, sy), (kx, ky))
+        _assert_disp_equal(got, ref, f"random screened seed {seed} cost {cost} {W}x{H} k{kx}x{ky} s{sx}x{sy} style {style}")
