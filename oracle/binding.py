@@ -15,7 +15,7 @@ PREFILTER_NONE, PREFILTER_LOG, PREFILTER_MEANSUB = 0, 1, 2
 def build(force=False):
     """Compile the oracle with gcc (Makefile next to this file)."""
     so = os.path.join(_HERE, "libvworacle.so")
-    src = [os.path.join(_HERE, f) for f in ("vw_oracle.c", "vw_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("vw_oracle.c", "vw_sgm_oracle.c", "vw_oracle.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-s", "-C", _HERE])
     return so
@@ -289,6 +289,22 @@ def parabola_subpixel(disp, left, right, kernel, prefilter_mode=0, prefilter_wid
     if rc:
         raise ValueError(rc)
     return out
+
+
+def sgm_calc_disparity(left, right, search, kernel_size, p1=0, p2=0):
+    """vw::stereo::calc_disparity_sgm (Stereo/SGM.cc:167-230), CENSUS_TRANSFORM, SGM, constant search box [0, search] (inclusive)
+    for every pixel.  left / right: the cropped left_region / right_region rasters.  Returns int32 (oh, ow, 3) {dx, dy, valid}."""
+    l, r = _f32(left), _f32(right)
+    out = np.empty((l.shape[0], l.shape[1], 3), np.int32)
+    ow, oh = C.c_int(0), C.c_int(0)
+    f = lib().vwo_sgm_calc_disparity
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                  C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rc = f(_p(l), l.shape[1], l.shape[0], l.shape[1], _p(r), r.shape[1], r.shape[0], r.shape[1], search[0], search[1], kernel_size, p1, p2,
+           _p(out), C.byref(ow), C.byref(oh))
+    if rc:
+        raise ValueError(f"vwo_sgm_calc_disparity rc={rc}")
+    return out.reshape(-1)[: ow.value * oh.value * 3].reshape(oh.value, ow.value, 3).copy()
 
 
 def max_threads():

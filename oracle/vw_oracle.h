@@ -127,6 +127,13 @@ int vwo_parabola_subpixel(const float* disp, int cols, int rows, const float* le
                           int kx, int ky, int prefilter_mode, float prefilter_width,
                           int bx0, int by0, int bx1, int by1, float* out);
 
+/* vw::stereo::calc_disparity_sgm (Stereo/SGM.cc:167-230) -> SemiGlobalMatcher::semi_global_matching_func (:2387-2448):
+ * CENSUS_TRANSFORM (kernel 3/5/7/9), SGM accumulation along 8 directions (SSE flavour of evaluate_path), integer winner of
+ * select_best_disparity; the same search box [0, search_x] x [0, search_y] (inclusive) for every pixel.  See
+ * vw_sgm_oracle.c for what is and is not restated.  out: out_w x out_h {dx, dy, valid} triples (caller allocates lw*lh*3). */
+int vwo_sgm_calc_disparity(const float* left, int lw, int lh, int lpitch, const float* right, int rw, int rh, int rpitch,
+                           int search_x, int search_y, int kernel_size, int p1, int p2, int* out, int* out_w, int* out_h);
+
 /* number of pyramid levels prerasterize would use for this bbox (CorrelationView.cc:301-310,
  * CorrelationView.h:99-105) */
 int vwo_num_levels(const vwo_corr_params* p, int bw, int bh);

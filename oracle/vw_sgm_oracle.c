@@ -1,0 +1,245 @@
+/* vw_sgm_oracle.c -- CPU restatement of Vision Workbench's SemiGlobalMatcher core.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/vw_oracle.h): nothing under visionworkbench_b200/ may use it.
+ *
+ * Scope of this first cut (round 1): vw::stereo::calc_disparity_sgm (Stereo/SGM.cc:167-230) ->
+ * SemiGlobalMatcher::semi_global_matching_func (:2387-2448) with
+ *   - CENSUS_TRANSFORM costs, kernel 3/5/7/9 (Image/CensusTransform.h:64-160, SGM.cc:39-73,1740-1873),
+ *   - the same search box for every pixel (populate_constant_disp_bound_image, :231-239): no masks, no previous disparity,
+ *   - plain SGM accumulation along 8 directions (accum_sgm_multithread, :2462-2611; PixelPassTask, SGMAssist.h:691-832)
+ *     with the SSE flavour of evaluate_path (:1014-1141, compute_path_internals_sse :950-990: unsigned 16-bit min,
+ *     SATURATING add / subtract) -- the reference is built with SSE4.1, and the scalar flavour (:806-913) differs on overflow,
+ *   - the integer winner of select_best_disparity (:1159-1288, including its tie-smoothing iterations that rewrite the
+ *     accumulated costs) as used by create_disparity_view (:1290-1346).
+ * Not restated yet: MGM, ternary census, per-pixel search boxes from a previous disparity (populate_disp_bound_image,
+ * :241-675), the sub-pixel view (:1497-1614).  The GPU implementation of this row is round-2 work; this file exists so
+ * that it starts from a pinned oracle (TestSGM.cxx:27-75: > 99 % of the pixels equal the true constant offset).
+ *
+ * The accumulation order of the reference is thread dependent but irrelevant: every pixel lies on exactly one line per
+ * direction and the per-line results are ADDED (uint16, wrapping) into the accumulation buffer (SGMAssist.h:790-815).
+ */
+#include "vw_oracle.h"
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef uint8_t cost_t;      /* SemiGlobalMatcher::CostType      (SGM.h:81) */
+typedef uint16_t accum_t;    /* SemiGlobalMatcher::AccumCostType (SGM.h:82) */
+
+/* vw::u8_convert (Image/ImageThresh.h:274-286): min/max stretch to 0..255, float arithmetic of ChannelNormalizeFunctor
+ * (Image/Algorithms.h:106-126: float difference, double ratio), truncating cast */
+static void u8_convert(const float* in, int w, int h, int pitch, uint8_t* out) {
+  double mn = in[0], mx = in[0];
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) { const double v = in[(size_t)y * pitch + x]; if (v < mn) mn = v; if (v > mx) mx = v; }
+  if (mx == mn) mx = mn + 1.0;
+  const float old_min = (float)mn, old_max = (float)mx, new_min = 0.0f, new_max = 255.0f;
+  const double ratio = (old_max == old_min) ? 0.0 : (double)(new_max - new_min) / (double)(old_max - old_min);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      float v = in[(size_t)y * pitch + x];
+      if (v < old_min) v = old_min;
+      if (v > old_max) v = old_max;
+      const float n = (float)((double)(v - old_min) * ratio + (double)new_min);
+      out[(size_t)y * w + x] = (uint8_t)n;
+    }
+}
+
+/* census signatures: only the SET of neighbours compared (strictly greater than the centre) matters for the Hamming
+ * distance.  3x3/5x5/7x7: all neighbours (CensusTransform.h:64-110); 9x9: the 32 positions of :112-160. */
+static const int C9_COLS[32] = {0, 4, 8, 1, 3, 5, 7, 2, 4, 6, 1, 4, 7, 0, 2, 3, 5, 6, 8, 1, 4, 7, 2, 4, 6, 1, 3, 5, 7, 0, 4, 8};
+static const int C9_ROWS[32] = {0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8};
+
+static uint64_t census_value(const uint8_t* img, int w, int col, int row, int k) {
+  const int hk = (k - 1) / 2;
+  const int center = img[(size_t)row * w + col];
+  uint64_t out = 0, addend = 1;
+  if (k == 9) {
+    for (int i = 0; i < 32; ++i) {
+      if ((int)img[(size_t)(row + C9_ROWS[i] - 4) * w + (col + C9_COLS[i] - 4)] > center) out += addend;
+      addend *= 2;
+    }
+    return out;
+  }
+  for (int r = row + hk; r >= row - hk; --r)
+    for (int c = col + hk; c >= col - hk; --c) {
+      if (r == row && c == col) continue;
+      if ((int)img[(size_t)r * w + c] > center) out += addend;
+      addend *= 2;
+    }
+  return out;
+}
+static inline int popcount64(uint64_t v) { return __builtin_popcountll(v); }
+
+static inline accum_t sat_add(accum_t a, accum_t b) { const unsigned s = (unsigned)a + b; return (accum_t)(s > 65535u ? 65535u : s); }
+static inline accum_t sat_sub(accum_t a, accum_t b) { return (accum_t)(a > b ? a - b : 0); }
+static inline accum_t min16(accum_t a, accum_t b) { return a < b ? a : b; }
+
+typedef struct {
+  int ndx, ndy, nd;          /* disparities: dx in [0, ndx), dy in [0, ndy) (min_disp = 0 in calc_disparity_sgm) */
+  int p1, p2;
+  int ow, oh, min_col, min_row;
+  const uint8_t* left; int lw;
+  const cost_t* cost;        /* [oh][ow][nd] */
+  accum_t* accum;            /* [oh][ow][nd] */
+  int* adj;                  /* [nd][8] (populate_adjacent_disp_lookup_table, :755-800) */
+} Sgm;
+
+/* one line of PixelPassTask::PixelPassDoWork (SGMAssist.h:705-774) starting at (c, r) going (sc, sr) */
+static void sgm_line(const Sgm* s, int c, int r, int sc, int sr, accum_t* buf /* 2 * nd */) {
+  const int nd = s->nd;
+  accum_t* prior = buf;
+  accum_t* cur = buf + nd;
+  int last_val = -1;
+  while (c >= 0 && c < s->ow && r >= 0 && r < s->oh) {
+    const cost_t* local = s->cost + ((size_t)r * s->ow + c) * nd;
+    const int cur_val = s->left[(size_t)(r + s->min_row) * s->lw + (c + s->min_col)];
+    const int diff = abs(cur_val - last_val);
+    if (last_val >= 0) {
+      /* evaluate_path, SSE flavour (:1014-1141) */
+      accum_t p2_mod = (accum_t)s->p2;
+      if (diff > 0) p2_mod = (accum_t)(p2_mod / diff);
+      if (p2_mod < s->p1) p2_mod = (accum_t)s->p1;
+      accum_t min_prior = (accum_t)(255 + s->p2);                 /* get_bad_accum_val (SGM.h:240) */
+      for (int d = 0; d < nd; ++d) if (prior[d] < min_prior) min_prior = prior[d];
+      const accum_t dJ = (accum_t)(min_prior + p2_mod);           /* uint16 arithmetic of the reference (:1056) */
+      for (int d = 0; d < nd; ++d) {
+        const int* a = s->adj + (size_t)d * 8;
+        accum_t m = min16(min16(min16(prior[a[0]], prior[a[1]]), min16(prior[a[2]], prior[a[3]])),
+                          min16(min16(prior[a[4]], prior[a[5]]), min16(prior[a[6]], prior[a[7]])));
+        accum_t res = sat_add(m, (accum_t)s->p1);
+        res = min16(res, min16(prior[d], dJ));
+        res = sat_add(res, (accum_t)local[d]);
+        cur[d] = sat_sub(res, min_prior);
+      }
+    } else {
+      for (int d = 0; d < nd; ++d) cur[d] = local[d];
+    }
+    accum_t* acc = s->accum + ((size_t)r * s->ow + c) * nd;      /* update_accum_buffer (SGMAssist.h:790-815) */
+    for (int d = 0; d < nd; ++d) acc[d] = (accum_t)(acc[d] + cur[d]);
+    accum_t* t = prior; prior = cur; cur = t;
+    last_val = cur_val;
+    c += sc; r += sr;
+  }
+}
+
+/* select_best_disparity (:1159-1288): returns the index of the winner; may rewrite accum_vec (tie smoothing) */
+static int select_best(accum_t* accum_vec, int width, int height, accum_t* buffer) {
+  const int num = width * height;
+  int min_count = 0, min_index = 0;
+  accum_t min_val = 65535;
+  for (int i = 0; i < num; ++i) {
+    const accum_t v = accum_vec[i];
+    buffer[i] = v;
+    if (v == min_val) ++min_count;
+    if (v < min_val) { min_index = i; min_val = v; min_count = 1; }
+  }
+  accum_t* input_array = accum_vec;
+  accum_t* output_array = buffer;
+  const double filter[3] = {1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0};
+  int iter_count = 0, index = 0;
+  while (min_count > 1) {
+    accum_t* sw = input_array; input_array = output_array; output_array = sw;
+    index = 0; min_count = 0; min_val = 65535; min_index = 0;
+    for (int row = 0; row < height; ++row)
+      for (int col = 0; col < width; ++col) {
+        int mn = -1, mx = 1;
+        double result = 0, weight_total = 0;
+        if (iter_count < 5) {
+          if (mn + col < 0) mn = 0;
+          if (mx + col >= width) mx = 0;
+          for (int k = mn; k <= mx; ++k) { const double wgt = filter[k + 1]; result += (double)input_array[index + k] * wgt; weight_total += wgt; }
+        } else {
+          if (mn + row < 0) mn = 0;
+          if (mx + row >= height) mx = 0;
+          for (int k = mn; k <= mx; ++k) { const double wgt = filter[k + 1]; result += (double)input_array[index + k * width] * wgt; weight_total += wgt; }
+        }
+        const accum_t v = (accum_t)round(result / weight_total);
+        if (v == min_val) ++min_count;
+        if (v < min_val) { min_index = index; min_val = v; min_count = 1; }
+        output_array[index] = v;
+        ++index;
+      }
+    if (++iter_count >= 6) break;
+  }
+  if (iter_count > 0 && iter_count % 2 == 0)
+    for (int i = 0; i < index; ++i) input_array[i] = output_array[i];
+  return min_index;
+}
+
+int vwo_sgm_calc_disparity(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
+                           int search_x, int search_y, int kernel_size, int p1, int p2, int* out, int* out_w, int* out_h) {
+  if (kernel_size != 3 && kernel_size != 5 && kernel_size != 7 && kernel_size != 9) return -2;     /* NoImplErr (:1885-1888) */
+  if (search_x < 0 || search_y < 0) return -1;
+  if (p1 <= 0) p1 = kernel_size == 3 ? 3 : kernel_size == 5 ? 15 : kernel_size == 7 ? 30 : 20;      /* set_parameters (:112-122) */
+  if (p2 <= 0) p2 = kernel_size == 3 ? 70 : kernel_size == 5 ? 750 : kernel_size == 7 ? 1500 : 1000; /* (:141-151) */
+  uint8_t* left = (uint8_t*)malloc((size_t)lw * lh);
+  uint8_t* right = (uint8_t*)malloc((size_t)rw * rh);
+  u8_convert(left_f, lw, lh, lpitch, left);
+  u8_convert(right_f, rw, rh, rpitch, right);
+  const int hk = (kernel_size - 1) / 2;
+  Sgm s;
+  s.ndx = search_x + 1; s.ndy = search_y + 1; s.nd = s.ndx * s.ndy; s.p1 = p1; s.p2 = p2;
+  /* semi_global_matching_func (:2397-2420); min_disp = 0, max_disp = search */
+  int min_row = hk, min_col = hk;
+  int max_row = (lh - 1 - hk) < (rh - 1 - (hk + search_y)) ? (lh - 1 - hk) : (rh - 1 - (hk + search_y));
+  int max_col = (lw - 1 - hk) < (rw - 1 - (hk + search_x)) ? (lw - 1 - hk) : (rw - 1 - (hk + search_x));
+  if (max_row > lh - 1) max_row = lh - 1;
+  if (max_col > lw - 1) max_col = lw - 1;
+  s.ow = max_col - min_col + 1; s.oh = max_row - min_row + 1; s.min_col = min_col; s.min_row = min_row;
+  *out_w = s.ow > 0 ? s.ow : 0; *out_h = s.oh > 0 ? s.oh : 0;
+  if (s.ow <= 0 || s.oh <= 0) { free(left); free(right); return 0; }
+  s.left = left; s.lw = lw;
+  /* census images (:1740-1873) and Hamming costs (get_hamming_distance_costs, :39-73) */
+  const int clw = lw - 2 * hk, clh = lh - 2 * hk, crw = rw - 2 * hk, crh = rh - 2 * hk;
+  uint64_t* lc = (uint64_t*)malloc((size_t)clw * clh * 8);
+  uint64_t* rc = (uint64_t*)malloc((size_t)crw * crh * 8);
+  for (int r = 0; r < clh; ++r) for (int c = 0; c < clw; ++c) lc[(size_t)r * clw + c] = census_value(left, lw, c + hk, r + hk, kernel_size);
+  for (int r = 0; r < crh; ++r) for (int c = 0; c < crw; ++c) rc[(size_t)r * crw + c] = census_value(right, rw, c + hk, r + hk, kernel_size);
+  const size_t total = (size_t)s.ow * s.oh * s.nd;
+  cost_t* cost = (cost_t*)malloc(total);
+  accum_t* accum = (accum_t*)calloc(total, sizeof(accum_t));
+  size_t ci = 0;
+  for (int r = min_row; r <= max_row; ++r)
+    for (int c = min_col; c <= max_col; ++c) {
+      const int br = r - hk, bc = c - hk;
+      for (int dy = 0; dy <= search_y; ++dy)
+        for (int dx = 0; dx <= search_x; ++dx)
+          cost[ci++] = (cost_t)popcount64(lc[(size_t)br * clw + bc] ^ rc[(size_t)(br + dy) * crw + (bc + dx)]);
+    }
+  s.cost = cost; s.accum = accum;
+  /* adjacent-disparity table (:755-800) */
+  s.adj = (int*)malloc((size_t)s.nd * 8 * sizeof(int));
+  for (int dy = 0, d = 0; dy < s.ndy; ++dy) {
+    const int yl = dy - 1 < 0 ? dy : dy - 1, ym = dy + 1 > search_y ? dy : dy + 1;
+    for (int dx = 0; dx < s.ndx; ++dx, ++d) {
+      const int xl = dx - 1 < 0 ? dx : dx - 1, xm = dx + 1 > search_x ? dx : dx + 1;
+      int* a = s.adj + (size_t)d * 8;
+      a[0] = yl * s.ndx + dx; a[1] = dy * s.ndx + xl; a[2] = dy * s.ndx + xm; a[3] = ym * s.ndx + dx;
+      a[4] = yl * s.ndx + xl; a[5] = yl * s.ndx + xm; a[6] = ym * s.ndx + xl; a[7] = ym * s.ndx + xm;
+    }
+  }
+  /* the eight directions of accum_sgm_multithread (:2462-2611): a line starts at every pixel whose predecessor is outside */
+  static const int DIRS[8][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
+  accum_t* buf = (accum_t*)malloc((size_t)2 * s.nd * sizeof(accum_t));
+  for (int k = 0; k < 8; ++k) {
+    const int sc = DIRS[k][0], sr = DIRS[k][1];
+    for (int r = 0; r < s.oh; ++r)
+      for (int c = 0; c < s.ow; ++c) {
+        const int pc = c - sc, pr = r - sr;
+        if (pc >= 0 && pc < s.ow && pr >= 0 && pr < s.oh) continue;
+        sgm_line(&s, c, r, sc, sr, buf);
+      }
+  }
+  /* create_disparity_view (:1290-1346) */
+  accum_t* tmp = (accum_t*)malloc((size_t)s.nd * sizeof(accum_t));
+  for (int j = 0; j < s.oh; ++j)
+    for (int i = 0; i < s.ow; ++i) {
+      const int idx = select_best(accum + ((size_t)j * s.ow + i) * s.nd, s.ndx, s.ndy, tmp);
+      int* o = out + ((size_t)j * s.ow + i) * 3;
+      o[1] = idx / s.ndx; o[0] = idx - o[1] * s.ndx; o[2] = 1;      /* disp_index_to_xy (:2737-2745), bounds = (0,0,sx,sy) */
+    }
+  free(tmp); free(buf); free(s.adj); free(cost); free(accum); free(lc); free(rc); free(left); free(right);
+  return 0;
+}

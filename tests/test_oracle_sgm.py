@@ -1,0 +1,64 @@
+"""SemiGlobalMatcher core of the oracle (oracle/vw_sgm_oracle.c): pinned by the reference's own
+known-answer test (Stereo/tests/TestSGM.cxx:27-75: constant offset (2,1), search [-4,4]^2, census 3x3, > 99 % correct)
+-- on the reference's fixture images when they are present, and on a synthetic equivalent that is always run."""
+import os
+
+import numpy as np
+import pytest
+
+REF_TESTS = "/root/reference/src/vw/Stereo/tests"
+
+
+def _constant_offset_pair(seed, W=180, H=150, off=(2, 1), smin=(-4, -4), ssize=(9, 9)):
+    """left ROI and the right ROI calc_disparity_sgm is given in TestSGM.cxx:47-52 (right = left ROI + search min,
+    grown by the search size), for a right image that is the left one shifted by `off`."""
+    rng = np.random.default_rng(seed)
+    base = np.floor(rng.random((H + 60, W + 60)) * 256)
+    # a little spatial correlation, like a real image
+    base = np.floor((base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) / 4).astype(np.float32)
+    x0 = y0 = 30
+    left = base[y0:y0 + H, x0:x0 + W]
+    ox, oy = x0 + smin[0] - off[0], y0 + smin[1] - off[1]
+    right = base[oy:oy + H + ssize[1], ox:ox + W + ssize[0]]
+    return np.ascontiguousarray(left), np.ascontiguousarray(right)
+
+
+@pytest.mark.parametrize("kernel", [3, 5, 7, 9])
+def test_sgm_constant_offset_synthetic(oracle, kernel):
+    left, right = _constant_offset_pair(7 + kernel)
+    d = oracle.sgm_calc_disparity(left, right, (8, 8), kernel)      # search volume (9, 9) -> inclusive maxima (8, 8)
+    hk = (kernel - 1) // 2
+    assert d.shape == (left.shape[0] - 2 * hk, left.shape[1] - 2 * hk, 3)   # SGM.cc:2404-2420
+    dd = d[..., :2] + np.array([-4, -4])
+    correct = ((dd[..., 0] == 2) & (dd[..., 1] == 1)).mean()
+    assert correct > 0.99, correct
+    assert (d[..., 2] == 1).all()
+
+
+def test_sgm_textureless_image_is_deterministic(oracle):
+    """All costs tie: select_best_disparity's smoothing iterations (SGM.cc:1196-1288) must terminate and be repeatable."""
+    left = np.full((40, 50), 100.0, np.float32)
+    right = np.full((48, 58), 100.0, np.float32)
+    a = oracle.sgm_calc_disparity(left, right, (8, 8), 3)
+    b = oracle.sgm_calc_disparity(left, right, (8, 8), 3)
+    assert np.array_equal(a, b) and a.shape[2] == 3
+
+
+def test_sgm_rejects_unsupported_kernel(oracle):
+    left, right = _constant_offset_pair(1, 60, 50)
+    with pytest.raises(ValueError):
+        oracle.sgm_calc_disparity(left, right, (8, 8), 11)      # NoImplErr in the reference (SGM.cc:1885-1888)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_TESTS, "left.tif")), reason="reference fixtures not present")
+def test_sgm_reference_fixture_kat(oracle):
+    cv2 = pytest.importorskip("cv2")
+    L = cv2.imread(os.path.join(REF_TESTS, "left.tif"), cv2.IMREAD_UNCHANGED).astype(np.float32)
+    R = cv2.imread(os.path.join(REF_TESTS, "left_const_offset.tif"), cv2.IMREAD_UNCHANGED).astype(np.float32)
+    # TestSGM.cxx uses leftRoi (0,0,400,400), whose right ROI starts at (-4,-4); an interior ROI avoids reading outside the file
+    x0, y0, w, h = 8, 8, 380, 380
+    left = L[y0:y0 + h, x0:x0 + w]
+    right = R[y0 - 4:y0 - 4 + h + 9, x0 - 4:x0 - 4 + w + 9]
+    d = oracle.sgm_calc_disparity(left, right, (8, 8), 3)
+    dd = d[..., :2] + np.array([-4, -4])
+    assert ((dd[..., 0] == 2) & (dd[..., 1] == 1)).mean() > 0.99
