@@ -119,6 +119,21 @@ int vwb200_parabola_subpixel(const float* disparity, int cols, int rows, const f
                              float* dest, ptrdiff_t dest_pitch, int on_device, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * vw::stereo::calc_disparity_sgm (src/vw/Stereo/SGM.cc:167-230, SGM.h:361-376) ->
+ * SemiGlobalMatcher::semi_global_matching_func (:2387-2448), first cut of row a10: CENSUS_TRANSFORM costs
+ * (kernel_size 3/5/7/9), SGM accumulation along 8 directions, integer winner; the same search box
+ * [0, search_x] x [0, search_y] (inclusive, = search_volume of the reference) for every pixel; no masks, no
+ * previous disparity, no MGM, no sub-pixel stage (-> VWB200_ENOIMPL / not offered).  left / right are the
+ * cropped left_region / right_region rasters (any float range: u8_convert is applied like the reference does).
+ * p1 / p2 <= 0 select the reference's defaults (:108-157).  out receives out_w x out_h pixels (row pitch
+ * opitch elements; the size is (:2397-2420) and can be queried first with out == NULL).
+ * ------------------------------------------------------------------------------------------- */
+int vwb200_sgm_calc_disparity(const float* left, int lw, int lh, ptrdiff_t lpitch,
+                              const float* right, int rw, int rh, ptrdiff_t rpitch,
+                              int search_x, int search_y, int kernel_size, int p1, int p2,
+                              vwb200_dispi* out, ptrdiff_t opitch, int* out_w, int* out_h, int on_device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * The lazy view: vw::stereo::PyramidCorrelationView (src/vw/Stereo/CorrelationView.h:35-193,
  * CorrelationView.cc:273-886) behind a handle.  vwb200_corr_params mirrors the constructor
  * arguments (CorrelationView.h:48-69) that the block-matching algorithm uses.

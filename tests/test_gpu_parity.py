@@ -479,3 +479,49 @@ def test_screened_kernel_randomised_imagery(vwb, oracle, seed):
         assert vwb.last_k1_stats()["path"] == "exact-int"
         ref = oracle.calc_disparity(cost, left, right, (sx, sy), (kx, ky))
         _assert_disp_equal(got, ref, f"random screened seed {seed} cost {cost} {W}x{H} k{kx}x{ky} s{sx}x{sy} style {style}")
+
+
+def _sgm_pair(seed, W, H, search, off, bits=8):
+    rng = np.random.default_rng(seed)
+    sx, sy = search
+    base = np.floor(rng.random((H + sy + 40, W + sx + 40)) * (1 << bits))
+    base = np.floor((base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) / 4).astype(np.float32)
+    left = base[20:20 + H, 20:20 + W]
+    right = base[20 - off[1]:20 - off[1] + H + sy, 20 - off[0]:20 - off[0] + W + sx]
+    return np.ascontiguousarray(left), np.ascontiguousarray(right)
+
+
+@pytest.mark.parametrize("kernel,search,shape", [(3, (8, 8), (150, 120)), (5, (8, 8), (133, 77)), (7, (12, 4), (160, 90)), (9, (6, 10), (97, 141)),
+                                                 (3, (0, 0), (40, 30)), (5, (31, 31), (70, 60))])
+def test_sgm_core_matches_oracle(vwb, oracle, kernel, search, shape):
+    """calc_disparity_sgm (census costs, 8-direction SGM, integer winner) is pure integer arithmetic: bit-identical to
+    oracle/vw_sgm_oracle.c, which the reference's own KAT pins (tests/test_oracle_sgm.py)."""
+    W, H = shape
+    left, right = _sgm_pair(31 + kernel + W, W, H, search, (min(3, search[0]), min(2, search[1])))
+    got = vwb.calc_disparity_sgm(left, right, search, kernel)
+    ref = oracle.sgm_calc_disparity(left, right, search, kernel)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref), f"{int((got != ref).any(-1).sum())} of {ref.shape[0] * ref.shape[1]} pixels differ"
+
+
+def test_sgm_core_ties_and_float_ranges(vwb, oracle):
+    """Textureless and few-level imagery (masses of tied accumulated costs -> select_best_disparity's smoothing iterations),
+    and a float input range that u8_convert stretches (Image/ImageThresh.h:274-286)."""
+    rng = np.random.default_rng(99)
+    for left, right in [
+        (np.full((40, 50), 100.0, np.float32), np.full((48, 58), 100.0, np.float32)),
+        (np.floor(rng.random((60, 70)) * 3).astype(np.float32), np.floor(rng.random((68, 78)) * 3).astype(np.float32)),
+        ((rng.random((64, 64)) * 1000.0 - 300.0).astype(np.float32), (rng.random((72, 72)) * 900.0 - 250.0).astype(np.float32)),
+    ]:
+        got = vwb.calc_disparity_sgm(left, right, (8, 8), 3)
+        ref = oracle.sgm_calc_disparity(left, right, (8, 8), 3)
+        assert np.array_equal(got, ref), f"{int((got != ref).any(-1).sum())} pixels differ"
+    with pytest.raises(vwb.NoImplErr):
+        vwb.calc_disparity_sgm(left, right, (8, 8), 11)
+
+
+def test_sgm_core_device_tensors(vwb, oracle):
+    import torch
+    left, right = _sgm_pair(5, 120, 90, (8, 8), (2, 1))
+    got = vwb.calc_disparity_sgm(torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda(), (8, 8), 5)
+    assert np.array_equal(got.cpu().numpy(), oracle.sgm_calc_disparity(left, right, (8, 8), 5))

@@ -89,6 +89,7 @@ def lib():
         L.vwb200_pyramid_down.argtypes = [P, I, I, Z, P, Z, I, P]
         L.vwb200_subsample_mask_by_two.argtypes = [P, I, I, Z, P, Z, I, P]
         L.vwb200_prefilter.argtypes = [P, I, I, Z, I, F, P, Z, I, P]
+        L.vwb200_sgm_calc_disparity.argtypes = [P, I, I, Z, P, I, I, Z, I, I, I, I, I, P, Z, C.POINTER(I), C.POINTER(I), I, P]
         L.vwb200_parabola_subpixel.argtypes = [P, I, I, P, Z, P, I, I, Z, I, I, I, F, I, I, I, I, P, Z, I, P]
         L.vwb200_cross_corr_consistency_check.argtypes = [P, I, I, Z, P, I, I, Z, F, I, P]
         L.vwb200_rm_outliers_using_thresh.argtypes = [P, I, I, I, I, D, D, P, I, P]
@@ -169,6 +170,32 @@ def calc_disparity(cost_type, left_in, right_in, search_volume, kernel_size):
     _check(lib().vwb200_calc_disparity(cost_type, l.ctypes.data, l.shape[1], l.shape[0], l.shape[1],
                                        r.ctypes.data, r.shape[1], r.shape[0], r.shape[1],
                                        sx, sy, kx, ky, out.ctypes.data, W, 0, None))
+    return out
+
+
+def calc_disparity_sgm(left_in, right_in, search_volume, kernel_size, p1=0, p2=0):
+    """vw::stereo::calc_disparity_sgm (Stereo/SGM.cc:167-230) for CENSUS_TRANSFORM / SGM on the cropped left_region and
+    right_region rasters: the search box is [0, search_volume] (inclusive) for every pixel.  kernel_size 3, 5, 7 or 9.
+    Returns int32 (out_h, out_w, 3) {dx, dy, valid} (the raster of SGM.cc:2397-2420: the borders the kernel and the search
+    cannot cover are cropped)."""
+    sx, sy = search_volume
+    ow, oh = C.c_int(0), C.c_int(0)
+    if _is_torch(left_in):
+        import torch
+        l = left_in.contiguous().float()
+        r = right_in.contiguous().float()
+        _check(lib().vwb200_sgm_calc_disparity(l.data_ptr(), l.shape[1], l.shape[0], l.stride(0), r.data_ptr(), r.shape[1], r.shape[0], r.stride(0),
+                                               sx, sy, kernel_size, p1, p2, None, 0, C.byref(ow), C.byref(oh), 1, None))
+        out = torch.empty((max(oh.value, 0), max(ow.value, 0), 3), dtype=torch.int32, device=l.device)
+        _check(lib().vwb200_sgm_calc_disparity(l.data_ptr(), l.shape[1], l.shape[0], l.stride(0), r.data_ptr(), r.shape[1], r.shape[0], r.stride(0),
+                                               sx, sy, kernel_size, p1, p2, out.data_ptr(), ow.value, C.byref(ow), C.byref(oh), 1, _stream_ptr()))
+        return out
+    l, r = _np(left_in, np.float32), _np(right_in, np.float32)
+    args = (l.ctypes.data, l.shape[1], l.shape[0], l.shape[1], r.ctypes.data, r.shape[1], r.shape[0], r.shape[1], sx, sy, kernel_size, p1, p2)
+    _check(lib().vwb200_sgm_calc_disparity(*args, None, 0, C.byref(ow), C.byref(oh), 0, None))
+    out = np.empty((max(oh.value, 0), max(ow.value, 0), 3), np.int32)
+    if out.size:
+        _check(lib().vwb200_sgm_calc_disparity(*args, out.ctypes.data, ow.value, C.byref(ow), C.byref(oh), 0, None))
     return out
 
 

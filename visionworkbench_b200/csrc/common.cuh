@@ -92,6 +92,11 @@ size_t k1_screen_workspace_bytes(int cost, int W, int H, int sx, int sy, int kx,
 int k1_screen_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
                      vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev = nullptr,
                      const FastOrigin* org = nullptr);
+// ---- SemiGlobalMatcher core (k5_sgm.cu) ------------------------------------------------------
+int sgm_output_size(int lw, int lh, int rw, int rh, int sx, int sy, int k, int* ow, int* oh);
+size_t sgm_workspace_bytes(int lw, int lh, int rw, int rh, int sx, int sy, int k);
+int sgm_launch(ImgF left, ImgF right, int sx, int sy, int k, int p1, int p2, vwb200_dispi* out, ptrdiff_t opitch, void* workspace,
+               cudaStream_t st);
 // exact sequential re-evaluation of pixels flagged NaN by k1 (NCC zero-energy windows)
 int k1_nan_fixup_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, int nzones, int kx, int ky,
                         NccMaps ncc, vwb200_dispi* out, cudaStream_t st, int gridx = 8);
