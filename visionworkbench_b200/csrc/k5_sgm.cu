@@ -116,10 +116,20 @@ __global__ void sgm_path_kernel(const uint8_t* __restrict__ left, const cost_t* 
   const accum_t BAD = (accum_t)(255 + g.p2);                  // get_bad_accum_val (SGM.h:240)
   int last_val = -1;
   accum_t cur = 0;
-  while (c >= 0 && c < g.ow && r >= 0 && r < g.oh) {
-    const size_t base = ((size_t)r * g.ow + c) * g.nd;
-    const accum_t local = act ? (accum_t)cost[base + d] : (accum_t)0;
-    const int cur_val = left[(size_t)(r + g.min_row) * g.lw + (c + g.min_col)];
+  // software pipeline: the next pixel's cost / accumulated cost / grey value are requested before the current pixel is
+  // evaluated (every step is a dependent chain otherwise: ncu showed 5.5 long-scoreboard stalls per issue)
+  bool in = c >= 0 && c < g.ow && r >= 0 && r < g.oh;
+  size_t base = in ? ((size_t)r * g.ow + c) * g.nd : 0;
+  accum_t local = (in && act) ? (accum_t)cost[base + d] : (accum_t)0;
+  accum_t acc_in = (in && act) ? accum[base + d] : (accum_t)0;
+  int cur_val = in ? (int)left[(size_t)(r + g.min_row) * g.lw + (c + g.min_col)] : 0;
+  while (in) {
+    const int cn = c + sc, rn = r + sr;
+    const bool in_n = cn >= 0 && cn < g.ow && rn >= 0 && rn < g.oh;
+    const size_t base_n = in_n ? ((size_t)rn * g.ow + cn) * g.nd : 0;
+    const accum_t local_n = (in_n && act) ? (accum_t)cost[base_n + d] : (accum_t)0;
+    const accum_t acc_n = (in_n && act) ? accum[base_n + d] : (accum_t)0;
+    const int val_n = in_n ? (int)left[(size_t)(rn + g.min_row) * g.lw + (cn + g.min_col)] : 0;
     if (last_val >= 0) {
       // block minimum of the previous pixel's path costs
       accum_t m = act ? prior[d] : (accum_t)65535;
@@ -150,11 +160,11 @@ __global__ void sgm_path_kernel(const uint8_t* __restrict__ left, const cost_t* 
     }
     if (act) {
       prior[d] = cur;
-      accum[base + d] = (accum_t)(accum[base + d] + cur);       // update_accum_buffer (SGMAssist.h:806-809), uint16 wrap
+      accum[base + d] = (accum_t)(acc_in + cur);                 // update_accum_buffer (SGMAssist.h:806-809), uint16 wrap
     }
     __syncthreads();
     last_val = cur_val;
-    c += sc; r += sr;
+    c = cn; r = rn; in = in_n; base = base_n; local = local_n; acc_in = acc_n; cur_val = val_n;
   }
 }
 
