@@ -95,3 +95,28 @@ def test_view_is_lazy_and_operator_call_throws(vwb):
     # construction places inputs in HBM -> fails loudly without a device
     with pytest.raises(vwb.NoDeviceErr):
         vwb.PyramidCorrelationView(l, l, m, m, 0, 0, (0, 0, 4, 4), (5, 5), 0, 0, 0.0, -1, 0, 0, 0)
+
+
+def test_sgm_boundary_without_a_device(vwb):
+    """vwb200_sgm_calc_disparity: the output-size query (SGM.cc:2397-2420) and the reference's argument asserts
+    (:184-188) are host logic; the compute call fails loudly without a device."""
+    import ctypes as C
+    L = vwb.lib()
+    left = np.zeros((50, 60), np.float32)
+    right = np.zeros((58, 68), np.float32)
+    ow, oh = C.c_int(-1), C.c_int(-1)
+    args = (left.ctypes.data, 60, 50, 60, right.ctypes.data, 68, 58, 68)
+    assert L.vwb200_sgm_calc_disparity(*args, 8, 8, 5, 0, 0, None, 0, C.byref(ow), C.byref(oh), 0, None) == 0
+    assert (ow.value, oh.value) == (60 - 4, 50 - 4)                  # cropped by the 5x5 census kernel only: the right raster covers the search
+    small = np.zeros((50, 60), np.float32)                              # right raster without room for the search: the output shrinks
+    assert L.vwb200_sgm_calc_disparity(left.ctypes.data, 60, 50, 60, small.ctypes.data, 60, 50, 60, 8, 8, 5, 0, 0, None, 0,
+                                       C.byref(ow), C.byref(oh), 0, None) == 0
+    assert (ow.value, oh.value) == (60 - 4 - 8, 50 - 4 - 8)
+    with pytest.raises(vwb.ArgumentErr):       # even kernel (SGM.cc:184-185)
+        vwb.calc_disparity_sgm(left, right, (8, 8), 4)
+    with pytest.raises(vwb.ArgumentErr):       # kernel larger than the region (:187-188)
+        vwb.calc_disparity_sgm(left[:3], right, (8, 8), 5)
+    if vwb.device_count() == 0:
+        with pytest.raises(vwb.VwError) as e:
+            vwb.calc_disparity_sgm(left, right, (8, 8), 5)
+        assert "CUDA" in str(e.value) or "device" in str(e.value)
