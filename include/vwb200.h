@@ -132,6 +132,15 @@ int vwb200_sgm_calc_disparity(const float* left, int lw, int lh, ptrdiff_t lpitc
                               const float* right, int rw, int rh, ptrdiff_t rpitch,
                               int search_x, int search_y, int kernel_size, int p1, int p2,
                               vwb200_dispi* out, ptrdiff_t opitch, int* out_w, int* out_h, int on_device, void* stream);
+/* ... followed by SemiGlobalMatcher::create_disparity_view_subpixel (SGM.cc:1497-1614) on the integer result:
+ * subpixel_mode = SgmSubpixelMode (SGM.h:93-99): 0 none, 2 linear, 3 poly4, 4 cosine, 5 lc_blend; 1 (2-D parabola)
+ * -> VWB200_ENOIMPL.  out (may be NULL) gets the integer disparity, out_sub the float {dx, dy, valid} pixels
+ * (sub_pitch in pixels).  Floats agree with the reference's double arithmetic within 1e-5. */
+int vwb200_sgm_calc_disparity_subpixel(const float* left, int lw, int lh, ptrdiff_t lpitch,
+                                       const float* right, int rw, int rh, ptrdiff_t rpitch,
+                                       int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode,
+                                       vwb200_dispi* out, ptrdiff_t opitch, float* out_sub, ptrdiff_t sub_pitch,
+                                       int* out_w, int* out_h, int on_device, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The lazy view: vw::stereo::PyramidCorrelationView (src/vw/Stereo/CorrelationView.h:35-193,

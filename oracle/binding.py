@@ -291,6 +291,23 @@ def parabola_subpixel(disp, left, right, kernel, prefilter_mode=0, prefilter_wid
     return out
 
 
+def sgm_calc_disparity_subpixel(left, right, search, kernel_size, subpixel_mode=5, p1=0, p2=0):
+    """calc_disparity_sgm + create_disparity_view_subpixel (SGM.cc:1497-1614).  Returns (int32 disparity, float32 disparity)."""
+    l, r = _f32(left), _f32(right)
+    out = np.empty((l.shape[0], l.shape[1], 3), np.int32)
+    sub = np.empty((l.shape[0], l.shape[1], 3), np.float32)
+    ow, oh = C.c_int(0), C.c_int(0)
+    f = lib().vwo_sgm_calc_disparity_subpixel
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                  C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rc = f(_p(l), l.shape[1], l.shape[0], l.shape[1], _p(r), r.shape[1], r.shape[0], r.shape[1], search[0], search[1], kernel_size, p1, p2,
+           subpixel_mode, _p(out), _p(sub), C.byref(ow), C.byref(oh))
+    if rc:
+        raise ValueError(f"vwo_sgm_calc_disparity_subpixel rc={rc}")
+    n = ow.value * oh.value * 3
+    return (out.reshape(-1)[:n].reshape(oh.value, ow.value, 3).copy(), sub.reshape(-1)[:n].reshape(oh.value, ow.value, 3).copy())
+
+
 def sgm_calc_disparity(left, right, search, kernel_size, p1=0, p2=0):
     """vw::stereo::calc_disparity_sgm (Stereo/SGM.cc:167-230), CENSUS_TRANSFORM, SGM, constant search box [0, search] (inclusive)
     for every pixel.  left / right: the cropped left_region / right_region rasters.  Returns int32 (oh, ow, 3) {dx, dy, valid}."""

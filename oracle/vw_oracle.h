@@ -134,6 +134,12 @@ int vwo_parabola_subpixel(const float* disp, int cols, int rows, const float* le
 int vwo_sgm_calc_disparity(const float* left, int lw, int lh, int lpitch, const float* right, int rw, int rh, int rpitch,
                            int search_x, int search_y, int kernel_size, int p1, int p2, int* out, int* out_w, int* out_h);
 
+/* calc_disparity_sgm followed by SemiGlobalMatcher::create_disparity_view_subpixel (SGM.cc:1497-1614) on its integer result;
+ * subpixel_mode = SgmSubpixelMode (SGM.h:93-99) except 1 (2-D parabola, not restated).  out_sub: {dx, dy, valid} floats. */
+int vwo_sgm_calc_disparity_subpixel(const float* left, int lw, int lh, int lpitch, const float* right, int rw, int rh, int rpitch,
+                                    int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode,
+                                    int* out, float* out_sub, int* out_w, int* out_h);
+
 /* number of pyramid levels prerasterize would use for this bbox (CorrelationView.cc:301-310,
  * CorrelationView.h:99-105) */
 int vwo_num_levels(const vwo_corr_params* p, int bw, int bh);

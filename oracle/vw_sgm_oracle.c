@@ -10,10 +10,12 @@
  *     with the SSE flavour of evaluate_path (:1014-1141, compute_path_internals_sse :950-990: unsigned 16-bit min,
  *     SATURATING add / subtract) -- the reference is built with SSE4.1, and the scalar flavour (:806-913) differs on overflow,
  *   - the integer winner of select_best_disparity (:1159-1288, including its tie-smoothing iterations that rewrite the
- *     accumulated costs) as used by create_disparity_view (:1290-1346).
+ *     accumulated costs) as used by create_disparity_view (:1290-1346),
+ *   - the 1-D sub-pixel models of create_disparity_view_subpixel (:1402-1480,1497-1614; every SgmSubpixelMode but the 2-D
+ *     parabola).
  * Not restated yet: MGM, ternary census, per-pixel search boxes from a previous disparity (populate_disp_bound_image,
- * :241-675), the sub-pixel view (:1497-1614).  The GPU implementation of this row is round-2 work; this file exists so
- * that it starts from a pinned oracle (TestSGM.cxx:27-75: > 99 % of the pixels equal the true constant offset).
+ * :241-675).  Pinned by TestSGM.cxx:27-75 (> 99 % of the pixels equal the true constant offset) on the reference's own
+ * fixture images; the sub-pixel stage has no known-answer test in the reference (floats: tolerance 1e-5 on the GPU side).
  *
  * The accumulation order of the reference is thread dependent but irrelevant: every pixel lies on exactly one line per
  * direction and the per-line results are ADDED (uint16, wrapping) into the accumulation buffer (SGMAssist.h:790-815).
@@ -168,8 +170,53 @@ static int select_best(accum_t* accum_vec, int width, int height, accum_t* buffe
   return min_index;
 }
 
+/* the 1-D sub-pixel models of SGM.cc:1402-1431 */
+static double linear_fit(double x) { return x / 2.0; }
+static double poly4_fit(double x) { return (x * x * x * x + x) / 4.0; }
+static double cos_fit(double x) { const double PI = 3.14159265359; return (1 - cos(x * PI / 3.0)); }
+static double lc_blend_fit(double x) {
+  const double PI = 3.14159265359;
+  const double factor = 1.195 - cos(x * (PI / 2.3));
+  return cos_fit(x) * factor + linear_fit(x) * (1.0 - factor);
+}
+/* compute_subpixel_offset (:1445-1480) */
+static double subpixel_offset(accum_t prev, accum_t center, accum_t next, int left_bound, int right_bound, int mode) {
+  const double ld = (int)prev - (int)center, rd = (int)next - (int)center;
+  if (rd == 0 && ld == 0) return 0;
+  if (left_bound) return 0.5 * ((double)center / (double)next);            /* two_value_subpixel (:1440-1442) */
+  if (right_bound) return -1.0 * (0.5 * ((double)center / (double)prev));
+  double x = rd / ld, mult = -1.0;
+  if (ld < rd) { x = ld / rd; mult = 1.0; }
+  double value;
+  switch (mode) {
+    case 3: value = poly4_fit(x); break;
+    case 4: value = cos_fit(x); break;
+    case 5: value = lc_blend_fit(x); break;
+    default: value = linear_fit(x); break;
+  }
+  return (value - 0.5) * mult;
+}
+
+static int sgm_core(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
+                    int search_x, int search_y, int kernel_size, int p1, int p2, int* out, int* out_w, int* out_h,
+                    int subpixel_mode, float* out_sub);
+
 int vwo_sgm_calc_disparity(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
                            int search_x, int search_y, int kernel_size, int p1, int p2, int* out, int* out_w, int* out_h) {
+  return sgm_core(left_f, lw, lh, lpitch, right_f, rw, rh, rpitch, search_x, search_y, kernel_size, p1, p2, out, out_w, out_h, 0, NULL);
+}
+/* calc_disparity_sgm followed by create_disparity_view_subpixel on its (unfiltered) integer result (:1497-1614).
+ * subpixel_mode: SgmSubpixelMode (SGM.h:93-99) 0 none, 2 linear, 3 poly4, 4 cosine, 5 lc_blend; 1 (2-D parabola) is not restated. */
+int vwo_sgm_calc_disparity_subpixel(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
+                                    int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode,
+                                    int* out, float* out_sub, int* out_w, int* out_h) {
+  if (subpixel_mode == 1 || subpixel_mode < 0 || subpixel_mode > 5) return -2;
+  return sgm_core(left_f, lw, lh, lpitch, right_f, rw, rh, rpitch, search_x, search_y, kernel_size, p1, p2, out, out_w, out_h, subpixel_mode, out_sub);
+}
+
+static int sgm_core(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
+                    int search_x, int search_y, int kernel_size, int p1, int p2, int* out, int* out_w, int* out_h,
+                    int subpixel_mode, float* out_sub) {
   if (kernel_size != 3 && kernel_size != 5 && kernel_size != 7 && kernel_size != 9) return -2;     /* NoImplErr (:1885-1888) */
   if (search_x < 0 || search_y < 0) return -1;
   if (p1 <= 0) p1 = kernel_size == 3 ? 3 : kernel_size == 5 ? 15 : kernel_size == 7 ? 30 : 20;      /* set_parameters (:112-122) */
@@ -240,6 +287,27 @@ int vwo_sgm_calc_disparity(const float* left_f, int lw, int lh, int lpitch, cons
       int* o = out + ((size_t)j * s.ow + i) * 3;
       o[1] = idx / s.ndx; o[0] = idx - o[1] * s.ndx; o[2] = 1;      /* disp_index_to_xy (:2737-2745), bounds = (0,0,sx,sy) */
     }
+  if (out_sub) {                                                      /* create_disparity_view_subpixel (:1497-1614) */
+    for (int j = 0; j < s.oh; ++j)
+      for (int i = 0; i < s.ow; ++i) {
+        const int* o = out + ((size_t)j * s.ow + i) * 3;
+        float* f = out_sub + ((size_t)j * s.ow + i) * 3;
+        const int dx = o[0], dy = o[1], width = s.ndx;
+        f[2] = 1.0f;
+        if (subpixel_mode == 0) { f[0] = (float)dx; f[1] = (float)dy; continue; }
+        const int min_index = dy * width + dx;
+        int x_left = -1, x_right = 1, y_up = -width, y_down = width;
+        int lb = 0, rb = 0, tb = 0, bb = 0;
+        if (dx == 0) { x_left = 0; lb = 1; }
+        if (dx == search_x) { x_right = 0; rb = 1; }
+        if (dy == 0) { y_up = 0; tb = 1; }
+        if (dy == search_y) { y_down = 0; bb = 1; }
+        const accum_t* av = accum + ((size_t)j * s.ow + i) * s.nd;
+        const double ddx = subpixel_offset(av[min_index + x_left], av[min_index], av[min_index + x_right], lb, rb, subpixel_mode);
+        const double ddy = subpixel_offset(av[min_index + y_up], av[min_index], av[min_index + y_down], tb, bb, subpixel_mode);
+        f[0] = (float)(dx + ddx); f[1] = (float)(dy + ddy);          /* p_type(dx+delta_x, dy+delta_y): Vector2f from double */
+      }
+  }
   free(tmp); free(buf); free(s.adj); free(cost); free(accum); free(lc); free(rc); free(left); free(right);
   return 0;
 }

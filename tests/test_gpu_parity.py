@@ -525,3 +525,22 @@ def test_sgm_core_device_tensors(vwb, oracle):
     left, right = _sgm_pair(5, 120, 90, (8, 8), (2, 1))
     got = vwb.calc_disparity_sgm(torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda(), (8, 8), 5)
     assert np.array_equal(got.cpu().numpy(), oracle.sgm_calc_disparity(left, right, (8, 8), 5))
+
+
+@pytest.mark.parametrize("mode", [0, 2, 3, 4, 5])
+def test_sgm_subpixel_modes(vwb, oracle, mode):
+    """create_disparity_view_subpixel (SGM.cc:1497-1614): the integer part is bit-identical, the float offsets (double
+    arithmetic with cos()) agree within 1e-5 -- the tolerance north_star states for floating point."""
+    import scipy.ndimage as ndi
+    rng = np.random.default_rng(17)
+    base = ndi.gaussian_filter(np.floor(rng.random((130, 150)) * 256).astype(np.float32), 1.2)
+    left = np.ascontiguousarray(base[10:100, 10:120])
+    right = np.ascontiguousarray(ndi.shift(base, (1.4, 2.3), order=3)[10:108, 10:128]).astype(np.float32)
+    gi, gf = vwb.calc_disparity_sgm_subpixel(left, right, (8, 8), 5, mode)
+    ri, rf = oracle.sgm_calc_disparity_subpixel(left, right, (8, 8), 5, mode)
+    assert np.array_equal(gi, ri)
+    assert np.abs(gf - rf).max() <= 1e-5, float(np.abs(gf - rf).max())
+    if mode:
+        assert (gf[..., 0] != np.floor(gf[..., 0])).mean() > 0.5          # offsets were applied
+    with pytest.raises(vwb.NoImplErr):
+        vwb.calc_disparity_sgm_subpixel(left, right, (8, 8), 5, 1)

@@ -90,6 +90,7 @@ def lib():
         L.vwb200_subsample_mask_by_two.argtypes = [P, I, I, Z, P, Z, I, P]
         L.vwb200_prefilter.argtypes = [P, I, I, Z, I, F, P, Z, I, P]
         L.vwb200_sgm_calc_disparity.argtypes = [P, I, I, Z, P, I, I, Z, I, I, I, I, I, P, Z, C.POINTER(I), C.POINTER(I), I, P]
+        L.vwb200_sgm_calc_disparity_subpixel.argtypes = [P, I, I, Z, P, I, I, Z, I, I, I, I, I, I, P, Z, P, Z, C.POINTER(I), C.POINTER(I), I, P]
         L.vwb200_parabola_subpixel.argtypes = [P, I, I, P, Z, P, I, I, Z, I, I, I, F, I, I, I, I, P, Z, I, P]
         L.vwb200_cross_corr_consistency_check.argtypes = [P, I, I, Z, P, I, I, Z, F, I, P]
         L.vwb200_rm_outliers_using_thresh.argtypes = [P, I, I, I, I, D, D, P, I, P]
@@ -197,6 +198,22 @@ def calc_disparity_sgm(left_in, right_in, search_volume, kernel_size, p1=0, p2=0
     if out.size:
         _check(lib().vwb200_sgm_calc_disparity(*args, out.ctypes.data, ow.value, C.byref(ow), C.byref(oh), 0, None))
     return out
+
+
+def calc_disparity_sgm_subpixel(left_in, right_in, search_volume, kernel_size, subpixel_mode=5, p1=0, p2=0):
+    """calc_disparity_sgm followed by SemiGlobalMatcher::create_disparity_view_subpixel (Stereo/SGM.cc:1497-1614).
+    subpixel_mode: SgmSubpixelMode (SGM.h:93-99), default SUBPIXEL_LC_BLEND.  Returns (int32 (h, w, 3), float32 (h, w, 3))."""
+    sx, sy = search_volume
+    ow, oh = C.c_int(0), C.c_int(0)
+    l, r = _np(left_in, np.float32), _np(right_in, np.float32)
+    args = (l.ctypes.data, l.shape[1], l.shape[0], l.shape[1], r.ctypes.data, r.shape[1], r.shape[0], r.shape[1], sx, sy, kernel_size, p1, p2,
+            subpixel_mode)
+    _check(lib().vwb200_sgm_calc_disparity_subpixel(*args, None, 0, None, 0, C.byref(ow), C.byref(oh), 0, None))
+    out = np.empty((max(oh.value, 0), max(ow.value, 0), 3), np.int32)
+    sub = np.empty((max(oh.value, 0), max(ow.value, 0), 3), np.float32)
+    if out.size:
+        _check(lib().vwb200_sgm_calc_disparity_subpixel(*args, out.ctypes.data, ow.value, sub.ctypes.data, ow.value, C.byref(ow), C.byref(oh), 0, None))
+    return out, sub
 
 
 def pyramid_down(img):

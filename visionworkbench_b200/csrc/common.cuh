@@ -96,7 +96,7 @@ int k1_screen_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int 
 int sgm_output_size(int lw, int lh, int rw, int rh, int sx, int sy, int k, int* ow, int* oh);
 size_t sgm_workspace_bytes(int lw, int lh, int rw, int rh, int sx, int sy, int k);
 int sgm_launch(ImgF left, ImgF right, int sx, int sy, int k, int p1, int p2, vwb200_dispi* out, ptrdiff_t opitch, void* workspace,
-               cudaStream_t st);
+               cudaStream_t st, int subpixel_mode = 0, float* out_sub = nullptr, ptrdiff_t sub_pitch = 0);
 // exact sequential re-evaluation of pixels flagged NaN by k1 (NCC zero-energy windows)
 int k1_nan_fixup_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, int nzones, int kx, int ky,
                         NccMaps ncc, vwb200_dispi* out, cudaStream_t st, int gridx = 8);

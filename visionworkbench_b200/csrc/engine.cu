@@ -739,16 +739,19 @@ int vwb200_prefilter(const float* in, int w, int h, ptrdiff_t pitch, int mode, f
   return VWB200_OK;
 }
 
-int vwb200_sgm_calc_disparity(const float* left, int lw, int lh, ptrdiff_t lpitch, const float* right, int rw, int rh, ptrdiff_t rpitch,
-                              int search_x, int search_y, int kernel_size, int p1, int p2, vwb200_dispi* out, ptrdiff_t opitch,
-                              int* out_w, int* out_h, int on_device, void* stream) {
+static int sgm_run(const float* left, int lw, int lh, ptrdiff_t lpitch, const float* right, int rw, int rh, ptrdiff_t rpitch,
+                   int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, vwb200_dispi* out, ptrdiff_t opitch,
+                   float* out_sub, ptrdiff_t sub_pitch, bool want_sub, int* out_w, int* out_h, int on_device, void* stream) {
   if (!left || !right || lw <= 0 || lh <= 0 || rw <= 0 || rh <= 0 || !out_w || !out_h) { set_error("sgm_calc_disparity: bad arguments"); return VWB200_EARG; }
   if (kernel_size % 2 != 1) { set_error("calc_disparity_sgm: Kernel input not sized with odd values."); return VWB200_EARG; }       // SGM.cc:184-185
   if (kernel_size > lw || kernel_size > lh) { set_error("calc_disparity_sgm: Kernel size too large of active region."); return VWB200_EARG; }
   if (search_x < 0 || search_y < 0) { set_error("calc_disparity_sgm: negative search volume"); return VWB200_EARG; }
+  if (want_sub && (subpixel_mode < 0 || subpixel_mode > 5)) { set_error("sgm: unknown sub-pixel mode %d", subpixel_mode); return VWB200_EARG; }
+  if (want_sub && subpixel_mode == 1) { set_error("sgm: SUBPIXEL_PARABOLA (2-D fit) is not implemented"); return VWB200_ENOIMPL; }
   VWB_TRY(sgm_output_size(lw, lh, rw, rh, search_x, search_y, kernel_size, out_w, out_h));
-  if (!out) return VWB200_OK;                       // size query
-  if (opitch < *out_w) { set_error("sgm_calc_disparity: output pitch smaller than the output width"); return VWB200_EARG; }
+  if (!out && !out_sub) return VWB200_OK;           // size query
+  const int W = *out_w, H = *out_h;
+  if ((out && opitch < W) || (out_sub && sub_pitch < W)) { set_error("sgm_calc_disparity: output pitch smaller than the output width"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
   StreamGuard sg; VWB_TRY(sg.init(stream));
   cudaStream_t st = sg.st;
@@ -757,20 +760,38 @@ int vwb200_sgm_calc_disparity(const float* left, int lw, int lh, ptrdiff_t lpitc
     const float *dl, *dr; ptrdiff_t dlp, drp;
     VWB_TRY(stage_in(left, lw, lh, lpitch, on_device, ar, st, &dl, &dlp));
     VWB_TRY(stage_in(right, rw, rh, rpitch, on_device, ar, st, &dr, &drp));
-    const int W = *out_w, H = *out_h;
     if (W > 0 && H > 0) {
       vwb200_dispi* dout = out; ptrdiff_t dop = opitch;
-      if (!on_device) { VWB_TRY(ar.alloc(&dout, (size_t)W * H)); dop = W; }
+      if (!on_device || !out) { VWB_TRY(ar.alloc(&dout, (size_t)W * H)); dop = W; }
+      float* dsub = out_sub; ptrdiff_t dsp = sub_pitch * 3;
+      if (out_sub && !on_device) { VWB_TRY(ar.alloc(&dsub, (size_t)W * H * 3)); dsp = (ptrdiff_t)W * 3; }
       unsigned char* ws;
       VWB_TRY(ar.alloc(&ws, sgm_workspace_bytes(lw, lh, rw, rh, search_x, search_y, kernel_size)));
-      VWB_TRY(sgm_launch(ImgF{dl, lw, lh, dlp}, ImgF{dr, rw, rh, drp}, search_x, search_y, kernel_size, p1, p2, dout, dop, ws, st));
-      if (!on_device)
+      VWB_TRY(sgm_launch(ImgF{dl, lw, lh, dlp}, ImgF{dr, rw, rh, drp}, search_x, search_y, kernel_size, p1, p2, dout, dop, ws, st,
+                         subpixel_mode, out_sub ? dsub : nullptr, dsp));
+      if (!on_device && out)
         VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch * sizeof(vwb200_dispi), dout, (size_t)W * sizeof(vwb200_dispi),
                                    (size_t)W * sizeof(vwb200_dispi), H, cudaMemcpyDeviceToHost, st));
+      if (!on_device && out_sub)
+        VWB_CUDA(cudaMemcpy2DAsync(out_sub, (size_t)sub_pitch * 12, dsub, (size_t)W * 12, (size_t)W * 12, H, cudaMemcpyDeviceToHost, st));
     }
     VWB_CUDA(cudaStreamSynchronize(st));
   }
   return VWB200_OK;
+}
+
+int vwb200_sgm_calc_disparity(const float* left, int lw, int lh, ptrdiff_t lpitch, const float* right, int rw, int rh, ptrdiff_t rpitch,
+                              int search_x, int search_y, int kernel_size, int p1, int p2, vwb200_dispi* out, ptrdiff_t opitch,
+                              int* out_w, int* out_h, int on_device, void* stream) {
+  return sgm_run(left, lw, lh, lpitch, right, rw, rh, rpitch, search_x, search_y, kernel_size, p1, p2, 0, out, opitch, nullptr, 0, false,
+                 out_w, out_h, on_device, stream);
+}
+int vwb200_sgm_calc_disparity_subpixel(const float* left, int lw, int lh, ptrdiff_t lpitch, const float* right, int rw, int rh, ptrdiff_t rpitch,
+                                       int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode,
+                                       vwb200_dispi* out, ptrdiff_t opitch, float* out_sub, ptrdiff_t sub_pitch,
+                                       int* out_w, int* out_h, int on_device, void* stream) {
+  return sgm_run(left, lw, lh, lpitch, right, rw, rh, rpitch, search_x, search_y, kernel_size, p1, p2, subpixel_mode, out, opitch, out_sub,
+                 sub_pitch, true, out_w, out_h, on_device, stream);
 }
 
 int vwb200_parabola_subpixel(const float* disparity, int cols, int rows, const float* left, ptrdiff_t lpitch,

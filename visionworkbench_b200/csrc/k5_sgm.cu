@@ -219,6 +219,51 @@ __global__ void sgm_wta_kernel(accum_t* __restrict__ accum, accum_t* __restrict_
   out[(ptrdiff_t)(pix / g.ow) * opitch + (pix % g.ow)] = o;
 }
 
+// ---- create_disparity_view_subpixel (SGM.cc:1402-1480, 1497-1614): the 1-D models -----------------------------------
+__device__ __forceinline__ double sgm_fit(double x, int mode) {
+  const double PI = 3.14159265359;
+  const double lin = __ddiv_rn(x, 2.0);
+  if (mode == 3) return __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(x, x), x), x), x), 4.0);      // poly4Fit
+  const double cf = __dsub_rn(1.0, cos(__ddiv_rn(__dmul_rn(x, PI), 3.0)));                               // cosFit
+  if (mode == 4) return cf;
+  if (mode == 5) {                                                                                        // lcBlendFit
+    const double factor = __dsub_rn(1.195, cos(__dmul_rn(x, PI / 2.3)));
+    return __dadd_rn(__dmul_rn(cf, factor), __dmul_rn(lin, __dsub_rn(1.0, factor)));
+  }
+  return lin;
+}
+__device__ __forceinline__ double sgm_subpixel_offset(int prev, int center, int next, bool left_bound, bool right_bound, int mode) {
+  const double ld = (double)(prev - center), rd = (double)(next - center);
+  if (rd == 0 && ld == 0) return 0.0;
+  if (left_bound) return __dmul_rn(0.5, __ddiv_rn((double)center, (double)next));                  // two_value_subpixel
+  if (right_bound) return __dmul_rn(-1.0, __dmul_rn(0.5, __ddiv_rn((double)center, (double)prev)));
+  double x = __ddiv_rn(rd, ld), mult = -1.0;
+  if (ld < rd) { x = __ddiv_rn(ld, rd); mult = 1.0; }
+  return __dmul_rn(__dsub_rn(sgm_fit(x, mode), 0.5), mult);
+}
+__global__ void sgm_subpixel_kernel(const accum_t* __restrict__ accum, const vwb200_dispi* __restrict__ disp, ptrdiff_t dpitch, SgmGeom g,
+                                    int mode, float* __restrict__ out, ptrdiff_t opitch /* floats */) {
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (size_t)g.ow * g.oh) return;
+  const int i = (int)(pix % g.ow), j = (int)(pix / g.ow);
+  const vwb200_dispi d = disp[(ptrdiff_t)j * dpitch + i];
+  float* o = out + (ptrdiff_t)j * opitch + 3 * i;
+  o[2] = 1.0f;
+  if (mode == 0) { o[0] = (float)d.dx; o[1] = (float)d.dy; return; }
+  const int width = g.ndx, min_index = d.dy * width + d.dx;
+  int x_left = -1, x_right = 1, y_up = -width, y_down = width;
+  bool lb = false, rb = false, tb = false, bb = false;
+  if (d.dx == 0) { x_left = 0; lb = true; }
+  if (d.dx == g.ndx - 1) { x_right = 0; rb = true; }
+  if (d.dy == 0) { y_up = 0; tb = true; }
+  if (d.dy == g.ndy - 1) { y_down = 0; bb = true; }
+  const accum_t* av = accum + pix * g.nd;
+  const double ddx = sgm_subpixel_offset(av[min_index + x_left], av[min_index], av[min_index + x_right], lb, rb, mode);
+  const double ddy = sgm_subpixel_offset(av[min_index + y_up], av[min_index], av[min_index + y_down], tb, bb, mode);
+  o[0] = (float)__dadd_rn((double)d.dx, ddx);
+  o[1] = (float)__dadd_rn((double)d.dy, ddy);
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -241,7 +286,7 @@ size_t sgm_workspace_bytes(int lw, int lh, int rw, int rh, int sx, int sy, int k
 }
 
 int sgm_launch(ImgF left, ImgF right, int sx, int sy, int k, int p1, int p2, vwb200_dispi* out, ptrdiff_t opitch, void* workspace,
-               cudaStream_t st) {
+               cudaStream_t st, int subpixel_mode, float* out_sub, ptrdiff_t sub_pitch) {
   if (k != 3 && k != 5 && k != 7 && k != 9) {
     set_error("Census transforms are only available in size 3, 5, 7, and 9.");       // SGM.cc:1885-1888
     return VWB200_ENOIMPL;
@@ -296,6 +341,10 @@ int sgm_launch(ImgF left, ImgF right, int sx, int sy, int k, int p1, int p2, vwb
   const size_t npix = (size_t)g.ow * g.oh;
   sgm_wta_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, scratch, g, out, opitch);
   VWB_LAUNCH_CHECK();
+  if (out_sub) {
+    sgm_subpixel_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, out, opitch, g, subpixel_mode, out_sub, sub_pitch);
+    VWB_LAUNCH_CHECK();
+  }
   return VWB200_OK;
 }
 
