@@ -171,3 +171,30 @@ def test_pyramid_view_statistical(oracle):
         assert valid[inner].mean() >= 0.99
         ok = (d[..., 0] == tx) & (d[..., 1] == ty) & valid
         assert ok[inner].mean() >= 0.90
+
+
+def test_parabola_subpixel_reference_kat(oracle):
+    """Stereo/tests/TestSubPixel.cxx:95-139 (a11): identical images with disparity (1,1) stay at (1,1) +- 0.1 ("null
+    test"); on a 95 % horizontally stretched pair the refined disparity has a mean error below 0.6 px and below the
+    rounding error of the integer input."""
+    const = np.full((50, 50), 7.0, np.float32)
+    d = np.zeros((50, 50, 3), np.float32)
+    d[..., 0] = 1; d[..., 1] = 1; d[..., 2] = 1
+    o = oracle.parabola_subpixel(d, const, const, (7, 7), 0, 0.0)
+    assert np.abs(o[..., :2] - 1).max() <= 0.1 and (o[..., 2] == 1).all()
+    rng = np.random.default_rng(52)
+    W, H, stretch = 120, 90, 0.95
+    base = np.floor(rng.random((H, W + 20)) * 1024).astype(np.float32)
+    base = np.floor((base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, -1, 0) + np.roll(base, -1, 1)) / 5)
+    left = np.ascontiguousarray(base[:, :W])
+    xs = np.arange(W) * stretch
+    x0 = np.floor(xs).astype(int)
+    f = (xs - x0).astype(np.float32)
+    right = np.floor(base[:, np.clip(x0, 0, W + 18)] * (1 - f) + base[:, np.clip(x0 + 1, 0, W + 18)] * f).astype(np.float32)
+    true = np.arange(W) / stretch - np.arange(W)
+    disp = np.zeros((H, W, 3), np.float32)
+    disp[..., 0] = np.rint(true)[None, :]
+    disp[..., 2] = 1
+    o = oracle.parabola_subpixel(disp, left, right, (7, 7), 0, 0.0)
+    err = np.abs(o[10:80, 10:100, 0] - true[None, 10:100]).mean()
+    assert err < 0.6 and err < np.abs(np.rint(true) - true)[10:100].mean()
