@@ -291,6 +291,34 @@ def parabola_subpixel(disp, left, right, kernel, prefilter_mode=0, prefilter_wid
     return out
 
 
+def sgm_output_shape(left, right, search, kernel_size):
+    """(rows, cols) of the SGM output raster (SGM.cc:2397-2420)."""
+    hk = (kernel_size - 1) // 2
+    lh, lw = np.asarray(left).shape
+    rh, rw = np.asarray(right).shape
+    return (max(0, min(lh - 1 - hk, rh - 1 - (hk + search[1])) - hk + 1), max(0, min(lw - 1 - hk, rw - 1 - (hk + search[0])) - hk + 1))
+
+
+def sgm_calc_disparity_bounds(left, right, search, kernel_size, bounds, subpixel_mode=0, p1=0, p2=0):
+    """SGM core with a search box per pixel: bounds (oh, ow, 4) int32 {min_x, min_y, max_x, max_y} inclusive (max < min = none).
+    Returns (int32 disparity, float32 sub-pixel disparity)."""
+    l, r = _f32(left), _f32(right)
+    b = np.ascontiguousarray(bounds, np.int32)
+    oh, ow = sgm_output_shape(l, r, search, kernel_size)
+    assert b.shape == (oh, ow, 4), (b.shape, (oh, ow, 4))
+    out = np.empty((oh, ow, 3), np.int32)
+    sub = np.empty((oh, ow, 3), np.float32)
+    cw, ch = C.c_int(0), C.c_int(0)
+    f = lib().vwo_sgm_calc_disparity_bounds
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rc = f(_p(l), l.shape[1], l.shape[0], l.shape[1], _p(r), r.shape[1], r.shape[0], r.shape[1], search[0], search[1], kernel_size, p1, p2,
+           subpixel_mode, _p(b), _p(out), _p(sub), C.byref(cw), C.byref(ch))
+    if rc:
+        raise ValueError(f"vwo_sgm_calc_disparity_bounds rc={rc}")
+    return out, sub
+
+
 def sgm_calc_disparity_subpixel(left, right, search, kernel_size, subpixel_mode=5, p1=0, p2=0):
     """calc_disparity_sgm + create_disparity_view_subpixel (SGM.cc:1497-1614).  Returns (int32 disparity, float32 disparity)."""
     l, r = _f32(left), _f32(right)

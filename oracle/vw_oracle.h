@@ -140,6 +140,12 @@ int vwo_sgm_calc_disparity_subpixel(const float* left, int lw, int lh, int lpitc
                                     int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode,
                                     int* out, float* out_sub, int* out_w, int* out_h);
 
+/* ... with a search box per pixel (m_disp_bound_image): bounds = out_w * out_h quadruples {min_x, min_y, max_x, max_y},
+ * inclusive, inside [0, search]; max < min marks a pixel without search area (comes out invalid).  out_sub may be NULL. */
+int vwo_sgm_calc_disparity_bounds(const float* left, int lw, int lh, int lpitch, const float* right, int rw, int rh, int rpitch,
+                                  int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, const int* bounds,
+                                  int* out, float* out_sub, int* out_w, int* out_h);
+
 /* number of pyramid levels prerasterize would use for this bbox (CorrelationView.cc:301-310,
  * CorrelationView.h:99-105) */
 int vwo_num_levels(const vwo_corr_params* p, int bw, int bh);

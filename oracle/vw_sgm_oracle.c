@@ -311,3 +311,196 @@ static int sgm_core(const float* left_f, int lw, int lh, int lpitch, const float
   free(tmp); free(buf); free(s.adj); free(cost); free(accum); free(lc); free(rc); free(left); free(right);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------------
+ * The same pipeline with a search box PER PIXEL (m_disp_bound_image, SGM.h:303; consumed by get_hamming_distance_costs
+ * :39-73, calc_main_buf_size :677-731, evaluate_path :1014-1141, create_disparity_view :1290-1346,
+ * create_disparity_view_subpixel :1497-1614).  bounds: out_w * out_h quadruples {min_x, min_y, max_x, max_y} (inclusive,
+ * inside [0, search]; max < min = "no search area", the pixel comes out invalid).  How the reference derives the boxes from
+ * the previous pyramid level (populate_disp_bound_image / constrain_disp_bound_image, :241-675) is not restated yet: this
+ * entry takes them as input, which is what the device kernels of round 2 will consume.
+ * ---------------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int ndx, ndy, nd, p1, p2, ow, oh, min_col, min_row, lw;
+  const uint8_t* left;
+  const int* bounds;       /* [oh][ow][4] */
+  const size_t* starts;    /* m_buffer_starts (:684-692) */
+  const cost_t* cost;
+  accum_t* accum;
+  const int* adj;
+} SgmB;
+
+static inline int nb_disp(const int* b) { return (b[2] < b[0] || b[3] < b[1]) ? 0 : (b[2] - b[0] + 1) * (b[3] - b[1] + 1); }   /* SGM.h:244-251 */
+
+static void sgm_line_bounds(const SgmB* s, int c, int r, int sc, int sr, accum_t* buf /* 2 * nd */, accum_t* full_prior /* nd, all BAD */) {
+  const accum_t BAD = (accum_t)(255 + s->p2);
+  accum_t* prior = buf;
+  accum_t* cur = buf + s->nd;
+  int last_val = -1;
+  const int* bp = NULL;                     /* previous pixel's box */
+  while (c >= 0 && c < s->ow && r >= 0 && r < s->oh) {
+    const int* b = s->bounds + ((size_t)r * s->ow + c) * 4;
+    const int n = nb_disp(b);
+    const size_t st = s->starts[(size_t)r * s->ow + c];
+    const cost_t* local = s->cost + st;
+    const int cur_val = s->left[(size_t)(r + s->min_row) * s->lw + (c + s->min_col)];
+    const int diff = abs(cur_val - last_val);
+    if (last_val >= 0) {
+      accum_t p2_mod = (accum_t)s->p2;
+      if (diff > 0) p2_mod = (accum_t)(p2_mod / diff);
+      if (p2_mod < s->p1) p2_mod = (accum_t)s->p1;
+      accum_t min_prior = BAD;
+      int d = 0;
+      for (int dy = bp[1]; dy <= bp[3]; ++dy)                       /* scatter the previous pixel's costs (:1037-1054) */
+        for (int dx = bp[0]; dx <= bp[2]; ++dx, ++d) {
+          if (prior[d] < min_prior) min_prior = prior[d];
+          full_prior[dy * s->ndx + dx] = prior[d];
+        }
+      const accum_t dJ = (accum_t)(min_prior + p2_mod);
+      int pd = 0;
+      for (int dy = b[1]; dy <= b[3]; ++dy)
+        for (int dx = b[0]; dx <= b[2]; ++dx, ++pd) {
+          const int fd = dy * s->ndx + dx;
+          const int* a = s->adj + (size_t)fd * 8;
+          accum_t m = min16(min16(min16(full_prior[a[0]], full_prior[a[1]]), min16(full_prior[a[2]], full_prior[a[3]])),
+                            min16(min16(full_prior[a[4]], full_prior[a[5]]), min16(full_prior[a[6]], full_prior[a[7]])));
+          accum_t res = sat_add(m, (accum_t)s->p1);
+          res = min16(res, min16(full_prior[fd], dJ));
+          res = sat_add(res, (accum_t)local[pd]);
+          cur[pd] = sat_sub(res, min_prior);
+        }
+      for (int dy = bp[1]; dy <= bp[3]; ++dy)                       /* restore the flag value (:1131-1139) */
+        for (int dx = bp[0]; dx <= bp[2]; ++dx) full_prior[dy * s->ndx + dx] = BAD;
+    } else {
+      for (int d = 0; d < n; ++d) cur[d] = local[d];
+    }
+    accum_t* acc = s->accum + st;
+    for (int d = 0; d < n; ++d) acc[d] = (accum_t)(acc[d] + cur[d]);
+    accum_t* t = prior; prior = cur; cur = t;
+    bp = b;
+    last_val = cur_val;
+    c += sc; r += sr;
+  }
+}
+
+int vwo_sgm_calc_disparity_bounds(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
+                                  int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, const int* bounds,
+                                  int* out, float* out_sub, int* out_w, int* out_h) {
+  if (kernel_size != 3 && kernel_size != 5 && kernel_size != 7 && kernel_size != 9) return -2;
+  if (search_x < 0 || search_y < 0 || !bounds) return -1;
+  if (out_sub && (subpixel_mode == 1 || subpixel_mode < 0 || subpixel_mode > 5)) return -2;
+  if (p1 <= 0) p1 = kernel_size == 3 ? 3 : kernel_size == 5 ? 15 : kernel_size == 7 ? 30 : 20;
+  if (p2 <= 0) p2 = kernel_size == 3 ? 70 : kernel_size == 5 ? 750 : kernel_size == 7 ? 1500 : 1000;
+  const int hk = (kernel_size - 1) / 2;
+  SgmB s;
+  s.ndx = search_x + 1; s.ndy = search_y + 1; s.nd = s.ndx * s.ndy; s.p1 = p1; s.p2 = p2; s.lw = lw;
+  const int min_row = hk, min_col = hk;
+  int max_row = (lh - 1 - hk) < (rh - 1 - (hk + search_y)) ? (lh - 1 - hk) : (rh - 1 - (hk + search_y));
+  int max_col = (lw - 1 - hk) < (rw - 1 - (hk + search_x)) ? (lw - 1 - hk) : (rw - 1 - (hk + search_x));
+  if (max_row > lh - 1) max_row = lh - 1;
+  if (max_col > lw - 1) max_col = lw - 1;
+  s.ow = max_col - min_col + 1; s.oh = max_row - min_row + 1; s.min_col = min_col; s.min_row = min_row;
+  *out_w = s.ow > 0 ? s.ow : 0; *out_h = s.oh > 0 ? s.oh : 0;
+  if (s.ow <= 0 || s.oh <= 0) return 0;
+  const size_t npix = (size_t)s.ow * s.oh;
+  for (size_t i = 0; i < npix; ++i) {
+    const int* b = bounds + i * 4;
+    if (nb_disp(b) && (b[0] < 0 || b[1] < 0 || b[2] > search_x || b[3] > search_y)) return -1;
+  }
+  uint8_t* left = (uint8_t*)malloc((size_t)lw * lh);
+  uint8_t* right = (uint8_t*)malloc((size_t)rw * rh);
+  u8_convert(left_f, lw, lh, lpitch, left);
+  u8_convert(right_f, rw, rh, rpitch, right);
+  s.left = left; s.bounds = bounds;
+  size_t* starts = (size_t*)malloc(npix * sizeof(size_t));
+  size_t total = 0;
+  for (size_t i = 0; i < npix; ++i) { starts[i] = total; total += (size_t)nb_disp(bounds + i * 4); }
+  if (total < 6) total = 6;                                            /* (:695-696) */
+  s.starts = starts;
+  const int clw = lw - 2 * hk, clh = lh - 2 * hk, crw = rw - 2 * hk, crh = rh - 2 * hk;
+  uint64_t* lc = (uint64_t*)malloc((size_t)clw * clh * 8);
+  uint64_t* rc = (uint64_t*)malloc((size_t)crw * crh * 8);
+  for (int r = 0; r < clh; ++r) for (int c = 0; c < clw; ++c) lc[(size_t)r * clw + c] = census_value(left, lw, c + hk, r + hk, kernel_size);
+  for (int r = 0; r < crh; ++r) for (int c = 0; c < crw; ++c) rc[(size_t)r * crw + c] = census_value(right, rw, c + hk, r + hk, kernel_size);
+  cost_t* cost = (cost_t*)malloc(total);
+  accum_t* accum = (accum_t*)calloc(total, sizeof(accum_t));
+  size_t ci = 0;
+  for (int r = min_row; r <= max_row; ++r)
+    for (int c = min_col; c <= max_col; ++c) {
+      const int br = r - hk, bc = c - hk;
+      const int* b = bounds + ((size_t)(r - min_row) * s.ow + (c - min_col)) * 4;
+      for (int dy = b[1]; dy <= b[3]; ++dy)
+        for (int dx = b[0]; dx <= b[2]; ++dx)
+          cost[ci++] = (cost_t)popcount64(lc[(size_t)br * clw + bc] ^ rc[(size_t)(br + dy) * crw + (bc + dx)]);
+    }
+  s.cost = cost; s.accum = accum;
+  int* adj = (int*)malloc((size_t)s.nd * 8 * sizeof(int));
+  for (int dy = 0, d = 0; dy < s.ndy; ++dy) {
+    const int yl = dy - 1 < 0 ? dy : dy - 1, ym = dy + 1 > search_y ? dy : dy + 1;
+    for (int dx = 0; dx < s.ndx; ++dx, ++d) {
+      const int xl = dx - 1 < 0 ? dx : dx - 1, xm = dx + 1 > search_x ? dx : dx + 1;
+      int* a = adj + (size_t)d * 8;
+      a[0] = yl * s.ndx + dx; a[1] = dy * s.ndx + xl; a[2] = dy * s.ndx + xm; a[3] = ym * s.ndx + dx;
+      a[4] = yl * s.ndx + xl; a[5] = yl * s.ndx + xm; a[6] = ym * s.ndx + xl; a[7] = ym * s.ndx + xm;
+    }
+  }
+  s.adj = adj;
+  static const int DIRS[8][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
+  accum_t* buf = (accum_t*)malloc((size_t)2 * s.nd * sizeof(accum_t));
+  accum_t* full_prior = (accum_t*)malloc((size_t)s.nd * sizeof(accum_t));
+  for (int d = 0; d < s.nd; ++d) full_prior[d] = (accum_t)(255 + p2);
+  for (int k = 0; k < 8; ++k) {
+    const int sc = DIRS[k][0], sr = DIRS[k][1];
+    for (int r = 0; r < s.oh; ++r)
+      for (int c = 0; c < s.ow; ++c) {
+        const int pc = c - sc, pr = r - sr;
+        if (pc >= 0 && pc < s.ow && pr >= 0 && pr < s.oh) continue;
+        sgm_line_bounds(&s, c, r, sc, sr, buf, full_prior);
+      }
+  }
+  accum_t* tmp = (accum_t*)malloc((size_t)s.nd * sizeof(accum_t));
+  for (int j = 0; j < s.oh; ++j)
+    for (int i = 0; i < s.ow; ++i) {
+      const size_t pix = (size_t)j * s.ow + i;
+      const int* b = bounds + pix * 4;
+      int* o = out + pix * 3;
+      float* f = out_sub ? out_sub + pix * 3 : NULL;
+      if (nb_disp(b) == 0) {                                          /* never valid (:1317-1321) */
+        o[0] = o[1] = o[2] = 0;
+        if (f) { f[0] = f[1] = f[2] = 0.0f; }
+        continue;
+      }
+      const int width = b[2] - b[0] + 1, height = b[3] - b[1] + 1;
+      accum_t* av = accum + starts[pix];
+      const int idx = select_best(av, width, height, tmp);
+      const int dyi = idx / width;
+      const int dx = idx - dyi * width + b[0], dy = dyi + b[1];     /* disp_index_to_xy (:2737-2745) */
+      o[0] = dx; o[1] = dy; o[2] = 1;
+    }
+  if (out_sub) {
+    for (int j = 0; j < s.oh; ++j)
+      for (int i = 0; i < s.ow; ++i) {
+        const size_t pix = (size_t)j * s.ow + i;
+        const int* b = bounds + pix * 4;
+        const int* o = out + pix * 3;
+        float* f = out_sub + pix * 3;
+        if (!o[2]) continue;
+        const int dx = o[0], dy = o[1], width = b[2] - b[0] + 1;
+        f[2] = 1.0f;
+        if (subpixel_mode == 0) { f[0] = (float)dx; f[1] = (float)dy; continue; }
+        const int min_index = (dy - b[1]) * width + (dx - b[0]);
+        int x_left = -1, x_right = 1, y_up = -width, y_down = width;
+        int lb = 0, rb = 0, tb = 0, bb = 0;
+        if (dx == b[0]) { x_left = 0; lb = 1; }
+        if (dx == b[2]) { x_right = 0; rb = 1; }
+        if (dy == b[1]) { y_up = 0; tb = 1; }
+        if (dy == b[3]) { y_down = 0; bb = 1; }
+        const accum_t* av = accum + starts[pix];
+        const double ddx = subpixel_offset(av[min_index + x_left], av[min_index], av[min_index + x_right], lb, rb, subpixel_mode);
+        const double ddy = subpixel_offset(av[min_index + y_up], av[min_index], av[min_index + y_down], tb, bb, subpixel_mode);
+        f[0] = (float)(dx + ddx); f[1] = (float)(dy + ddy);
+      }
+  }
+  free(tmp); free(full_prior); free(buf); free(adj); free(cost); free(accum); free(lc); free(rc); free(starts); free(left); free(right);
+  return 0;
+}

@@ -62,3 +62,37 @@ def test_sgm_reference_fixture_kat(oracle):
     d = oracle.sgm_calc_disparity(left, right, (8, 8), 3)
     dd = d[..., :2] + np.array([-4, -4])
     assert ((dd[..., 0] == 2) & (dd[..., 1] == 1)).mean() > 0.99
+
+
+def test_sgm_per_pixel_boxes_reduce_to_the_constant_case(oracle):
+    """The per-pixel-box entry (what round 2's device kernels consume) with the full box everywhere must equal the
+    constant-box pipeline bit for bit, integer and sub-pixel."""
+    left, right = _constant_offset_pair(21, 90, 70)
+    oh, ow = oracle.sgm_output_shape(left, right, (8, 8), 5)
+    full = np.tile(np.array([0, 0, 8, 8], np.int32), (oh, ow, 1))
+    bi, bf = oracle.sgm_calc_disparity_bounds(left, right, (8, 8), 5, full, subpixel_mode=5)
+    ci, cf = oracle.sgm_calc_disparity_subpixel(left, right, (8, 8), 5, 5)
+    assert np.array_equal(bi, ci) and np.array_equal(bf, cf)
+
+
+def test_sgm_per_pixel_boxes_ragged(oracle):
+    """Random sub-boxes around the truth, empty boxes (-> invalid pixels) and single-disparity boxes."""
+    rng = np.random.default_rng(5)
+    left, right = _constant_offset_pair(22, 100, 80)
+    oh, ow = oracle.sgm_output_shape(left, right, (8, 8), 3)
+    b = np.empty((oh, ow, 4), np.int32)
+    b[..., 0] = rng.integers(0, 7, (oh, ow)); b[..., 1] = rng.integers(0, 6, (oh, ow))          # truth is (6, 5) in box coordinates
+    b[..., 2] = np.minimum(8, np.maximum(b[..., 0], 6) + rng.integers(0, 3, (oh, ow)))
+    b[..., 3] = np.minimum(8, np.maximum(b[..., 1], 5) + rng.integers(0, 4, (oh, ow)))
+    empty = rng.random((oh, ow)) < 0.05
+    b[empty] = (0, 0, -1, -1)
+    single = (rng.random((oh, ow)) < 0.05) & ~empty
+    b[single] = (6, 5, 6, 5)
+    di, df = oracle.sgm_calc_disparity_bounds(left, right, (8, 8), 3, b, subpixel_mode=5)
+    assert (di[empty] == 0).all() and (df[empty] == 0).all()
+    ok = ~empty
+    assert (di[ok][:, 2] == 1).all()
+    inside = (di[..., 0] >= b[..., 0]) & (di[..., 0] <= b[..., 2]) & (di[..., 1] >= b[..., 1]) & (di[..., 1] <= b[..., 3])
+    assert inside[ok].all()
+    assert ((di[..., 0] == 6) & (di[..., 1] == 5))[ok].mean() > 0.97
+    assert np.abs(df[ok][:, :2] - di[ok][:, :2]).max() <= 1.0      # sub-pixel offsets stay inside one pixel
