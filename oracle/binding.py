@@ -319,6 +319,27 @@ def sgm_calc_disparity_bounds(left, right, search, kernel_size, bounds, subpixel
     return out, sub
 
 
+def sgm_disp_bounds(shape, search, search_buffer, prev=None, lmask=None, rmask=None, conserve_level=0):
+    """populate_disp_bound_image + constrain_disp_bound_image (SGM.cc:241-668).  shape = (oh, ow) of the SGM output raster;
+    prev: (ph, pw, 3) int {dx, dy, valid} at half resolution.  Returns (ok, bounds (oh, ow, 4) int32)."""
+    oh, ow = shape
+    b = np.empty((oh, ow, 4), np.int32)
+    pv = None if prev is None else np.ascontiguousarray(prev, np.int32)
+    lm = None if lmask is None else np.ascontiguousarray(lmask, np.uint8)
+    rm = None if rmask is None else np.ascontiguousarray(rmask, np.uint8)
+    if lm is not None:
+        assert lm.shape == (oh, ow)
+    f = lib().vwo_sgm_disp_bounds
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                  C.c_void_p]
+    rc = f(None if pv is None else _p(pv), 0 if pv is None else pv.shape[1], 0 if pv is None else pv.shape[0],
+           None if lm is None else _p(lm), None if rm is None else _p(rm), 0 if rm is None else rm.shape[1], 0 if rm is None else rm.shape[0],
+           ow, oh, search[0], search[1], search_buffer[0], search_buffer[1], conserve_level, _p(b))
+    if rc < 0:
+        raise ValueError(f"vwo_sgm_disp_bounds rc={rc}")
+    return bool(rc), b
+
+
 def sgm_calc_disparity_subpixel(left, right, search, kernel_size, subpixel_mode=5, p1=0, p2=0):
     """calc_disparity_sgm + create_disparity_view_subpixel (SGM.cc:1497-1614).  Returns (int32 disparity, float32 disparity)."""
     l, r = _f32(left), _f32(right)

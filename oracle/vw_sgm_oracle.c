@@ -13,8 +13,10 @@
  *     accumulated costs) as used by create_disparity_view (:1290-1346),
  *   - the 1-D sub-pixel models of create_disparity_view_subpixel (:1402-1480,1497-1614; every SgmSubpixelMode but the 2-D
  *     parabola).
- * Not restated yet: MGM, ternary census, per-pixel search boxes from a previous disparity (populate_disp_bound_image,
- * :241-675).  Pinned by TestSGM.cxx:27-75 (> 99 % of the pixels equal the true constant offset) on the reference's own
+ * Further down: the same pipeline with a search box per pixel (vwo_sgm_calc_disparity_bounds) and the derivation of those
+ * boxes from masks and the previous pyramid level (vwo_sgm_disp_bounds: populate_disp_bound_image / constrain_disp_bound_image,
+ * :241-668) -- oracle only so far, the device side is round-2 work.
+ * Not restated yet: MGM, ternary census, the memory-limit retry loop (:476-497), the 2-D parabola sub-pixel mode.  Pinned by TestSGM.cxx:27-75 (> 99 % of the pixels equal the true constant offset) on the reference's own
  * fixture images; the sub-pixel stage has no known-answer test in the reference (floats: tolerance 1e-5 on the GPU side).
  *
  * The accumulation order of the reference is thread dependent but irrelevant: every pixel lies on exactly one line per
@@ -503,4 +505,121 @@ int vwo_sgm_calc_disparity_bounds(const float* left_f, int lw, int lh, int lpitc
   }
   free(tmp); free(full_prior); free(buf); free(adj); free(cost); free(accum); free(lc); free(rc); free(starts); free(left); free(right);
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------------
+ * SemiGlobalMatcher::populate_disp_bound_image (SGM.cc:241-500) + one pass of constrain_disp_bound_image (:502-668): the
+ * per-pixel search boxes from the masks and the previous (half-resolution) disparity.  min_disp = (0,0), max_disp =
+ * (search_x, search_y) as set up by calc_disparity_sgm.  The reference retries conservation levels 0..3 until
+ * calc_main_buf_size() fits --corr-memory-mb (:476-497, thread-count dependent); here the level is an input.
+ *   prev      : pw x ph {dx, dy, valid} ints or NULL        lmask : ow x oh uint8 or NULL (must match the output size, :250-256)
+ *   rmask     : rmw x rmh uint8 or NULL (>= output + search, :262-268)
+ *   bounds    : ow x oh {min_x, min_y, max_x, max_y}; (0,0,-1,-1) = no search area
+ * Returns 1 (go on), 0 (the reference returns an all-invalid disparity, :2430-2436), < 0 on bad arguments.
+ * vw::BBox2i quirks that matter here (Math/BBox.tcc): grow(point) makes max = point (not + 1); empty() is
+ * min >= max in ANY axis, so a box grown from identical points counts as empty; expand() ignores empty boxes.
+ * ---------------------------------------------------------------------------------------------------------------------- */
+typedef struct { int x0, y0, x1, y1; } IBox;
+static const IBox IBOX_EMPTY = {2147483647, 2147483647, -2147483647 - 1, -2147483647 - 1};
+static int ibox_empty(const IBox* b) { return b->x0 >= b->x1 || b->y0 >= b->y1; }
+static void ibox_grow(IBox* b, int x, int y) { if (x > b->x1) b->x1 = x; if (x < b->x0) b->x0 = x; if (y > b->y1) b->y1 = y; if (y < b->y0) b->y0 = y; }
+static void ibox_crop(IBox* b, const IBox* o) { if (b->x0 < o->x0) b->x0 = o->x0; if (b->x1 > o->x1) b->x1 = o->x1; if (b->y0 < o->y0) b->y0 = o->y0; if (b->y1 > o->y1) b->y1 = o->y1; }
+
+int vwo_sgm_disp_bounds(const int* prev, int pw, int ph, const uint8_t* lmask, const uint8_t* rmask, int rmw, int rmh,
+                        int ow, int oh, int search_x, int search_y, int buffer_x, int buffer_y, int conserve_level, int* bounds) {
+  if (ow <= 0 || oh <= 0 || search_x < 0 || search_y < 0 || !bounds) return -1;
+  const int ndx = search_x + 1, ndy = search_y + 1;
+  if (rmask && !(rmw >= ow + ndx - 1 && rmh >= oh + ndy - 1)) return -3;               /* LogicErr (:262-268) */
+  const int check_x_edge = ndx >= 10, check_y_edge = ndy >= 10;                          /* (:286-289) */
+  uint8_t* full = (uint8_t*)calloc((size_t)ow * oh, 1);
+  double area = 0, percent_trusted = 0, percent_masked = 0;
+  int min_vr = 0, max_vr = 0;                                                            /* (:303-331) */
+  if (rmask) {
+    min_vr = rmh - 1;
+    for (int c = 0; c < ow; ++c) {
+      for (int i = rmh - 1; i > 0; --i) if (rmask[(size_t)i * rmw + c] > 0) { if (i > max_vr) max_vr = i; break; }
+      for (int i = 0; i < rmh; ++i) if (rmask[(size_t)i * rmw + c] > 0) { if (i < min_vr) min_vr = i; break; }
+    }
+  }
+  for (int r = 0; r < oh; ++r) {
+    const int r_in = r / 2;
+    int min_vc = -1, max_vc = -2;
+    if (rmask) {                                                                         /* (:343-359) */
+      for (int i = rmw - 1; i > 0; --i) if (rmask[(size_t)r * rmw + i] > 0) { max_vc = i; break; }
+      if (max_vc > 0) for (int i = 0; i < rmw; ++i) if (rmask[(size_t)r * rmw + i] > 0) { min_vc = i; break; }
+    }
+    for (int c = 0; c < ow; ++c) {
+      int* b = bounds + ((size_t)r * ow + c) * 4;
+      if (lmask && lmask[(size_t)r * ow + c] == 0) { b[0] = 0; b[1] = 0; b[2] = -1; b[3] = -1; percent_masked += 1; continue; }
+      int good = 0, dxs = 0, dys = 0;
+      const int c_in = c / 2;
+      if (prev && c_in < pw && r_in < ph) {                                              /* (:385-403) */
+        const int* d = prev + ((size_t)r_in * pw + c_in) * 3;
+        dxs = d[0] * 2; dys = d[1] * 2;
+        const int on_edge = (check_x_edge && (dxs <= 0 || dxs >= search_x)) || (check_y_edge && (dys <= 0 || dys >= search_y));
+        good = d[2] != 0 && !on_edge;
+      }
+      if (good) {                                                                        /* (:407-422) */
+        b[0] = dxs - buffer_x; b[2] = dxs + buffer_x; b[1] = dys - buffer_y; b[3] = dys + buffer_y;
+        if (b[0] < 0) b[0] = 0;
+        if (b[1] < 0) b[1] = 0;
+        if (b[2] > search_x) b[2] = search_x;
+        if (b[3] > search_y) b[3] = search_y;
+        percent_trusted += 1.0;
+      } else {
+        b[0] = 0; b[1] = 0; b[2] = search_x; b[3] = search_y;
+        full[(size_t)r * ow + c] = 255;
+      }
+      if (rmask) {                                                                       /* (:431-452) */
+        IBox v = {min_vc - c, min_vr - r, max_vc - c, max_vr - r};
+        const IBox fo = {b[0], b[1], b[2], b[3]};
+        ibox_crop(&v, &fo);
+        if (v.x0 > v.x1 || v.y0 > v.y1) { b[0] = 0; b[1] = 0; b[2] = -1; b[3] = -1; percent_masked += 1; full[(size_t)r * ow + c] = 0; continue; }
+        b[0] = v.x0; b[1] = v.y0; b[2] = v.x1; b[3] = v.y1;
+      }
+      area += (double)((b[3] - b[1] + 1) * (b[2] - b[0] + 1));
+    }
+  }
+  const double num_pixels = (double)oh * ow;
+  percent_masked /= num_pixels;
+  percent_trusted /= num_pixels;
+  /* constrain_disp_bound_image (:502-668) */
+  const IBox max_range = {0, 0, search_x, search_y};
+  int range = 10;
+  if (conserve_level == 1) range = 25;
+  if (conserve_level == 2) range = 3;
+  if (conserve_level == 3) range = 0;
+  if (prev) {
+    for (int r = 0; r < oh; ++r) {
+      int r0 = r - range, r1 = r + range;
+      if (r0 < 0) r0 = 0;
+      if (r1 >= oh) r1 = oh - 1;
+      for (int c = 0; c < ow; ++c) {
+        if (!full[(size_t)r * ow + c]) continue;
+        int c0 = c - range, c1 = c + range;
+        if (c0 < 0) c0 = 0;
+        if (c1 >= ow) c1 = ow - 1;
+        IBox nr = IBOX_EMPTY;
+        for (int rs = r0; rs <= r1; ++rs)
+          for (int cs = c0; cs <= c1; ++cs) {
+            if (full[(size_t)rs * ow + cs]) continue;
+            const int* v = bounds + ((size_t)rs * ow + cs) * 4;
+            if (v[0] == 0 && v[1] == 0 && v[2] == -1 && v[3] == -1) continue;
+            ibox_grow(&nr, v[0], v[1]);
+            ibox_grow(&nr, v[2], v[3]);
+          }
+        int* b = bounds + ((size_t)r * ow + c) * 4;
+        if (ibox_empty(&nr)) {
+          if (conserve_level > 0) { b[0] = 0; b[1] = 0; b[2] = -1; b[3] = -1; }
+          continue;
+        }
+        nr.x0 -= 2; nr.y0 -= 2; nr.x1 += 2; nr.y1 += 2;                                 /* expand(NEARBY_DISP_EXPANSION) */
+        ibox_crop(&nr, &max_range);
+        b[0] = nr.x0; b[1] = nr.y0; b[2] = nr.x1; b[3] = nr.y1;
+      }
+    }
+  }
+  free(full);
+  area /= num_pixels;
+  return !(area <= 0 || percent_masked >= 100);                                          /* (:664-666) */
 }

@@ -96,3 +96,39 @@ def test_sgm_per_pixel_boxes_ragged(oracle):
     assert inside[ok].all()
     assert ((di[..., 0] == 6) & (di[..., 1] == 5))[ok].mean() > 0.97
     assert np.abs(df[ok][:, :2] - di[ok][:, :2]).max() <= 1.0      # sub-pixel offsets stay inside one pixel
+
+
+def test_sgm_disp_bounds_from_previous_level(oracle):
+    """populate_disp_bound_image / constrain_disp_bound_image (SGM.cc:241-668): trusted prior -> 2 * d +- buffer clipped to
+    the search box; priors on the edge of a >= 10 wide search are not trusted; untrusted pixels take the hull of the
+    trusted boxes within 10 pixels, grown by 2 (or the full box when there is none); masks zero the box."""
+    oh, ow, search, buf = 40, 50, (19, 11), (2, 3)
+    ok, b = oracle.sgm_disp_bounds((oh, ow), search, buf)                       # no prior: the constant box (:231-239)
+    assert ok and (b == np.array([0, 0, 19, 11])).all()
+    prev = np.zeros((20, 25, 3), np.int32)
+    prev[..., 0] = 4; prev[..., 1] = 3; prev[..., 2] = 1                         # -> (8, 6) at this level
+    prev[:, :5, 2] = 0                                                           # invalid prior on the left
+    prev[10:, 20:, 0] = 0                                                        # dx = 0 is on the edge of a 20-wide search: not trusted
+    ok, b = oracle.sgm_disp_bounds((oh, ow), search, buf, prev=prev)
+    assert ok
+    assert (b[5, 20] == np.array([6, 3, 10, 9])).all()
+    # untrusted pixel within 10 px of trusted ones: hull (6,3)-(10,9) expanded by 2, cropped to the search box
+    assert (b[5, 5] == np.array([4, 1, 12, 11])).all()
+    # untrusted pixel farther than 10 px from any trusted one keeps the full box at conservation level 0 ...
+    prev2 = prev.copy(); prev2[:, :, 2] = 0; prev2[0, 24, 2] = 1
+    ok, b2 = oracle.sgm_disp_bounds((oh, ow), search, buf, prev=prev2)
+    assert (b2[30, 5] == np.array([0, 0, 19, 11])).all()
+    # ... and loses its search area at level 1 (:633-640)
+    ok, b3 = oracle.sgm_disp_bounds((oh, ow), search, buf, prev=prev2, conserve_level=1)
+    assert (b3[39, 0] == np.array([0, 0, -1, -1])).all()
+    # left mask
+    lm = np.full((oh, ow), 255, np.uint8); lm[:4] = 0
+    ok, b4 = oracle.sgm_disp_bounds((oh, ow), search, buf, prev=prev, lmask=lm)
+    assert (b4[:4] == np.array([0, 0, -1, -1])).all() and (b4[5, 20] == b[5, 20]).all()
+    # the boxes feed the ragged core
+    left, right = _constant_offset_pair(23, 60, 50, off=(2, 1), smin=(0, 0), ssize=(20, 12))
+    shape = oracle.sgm_output_shape(left, right, search, 3)
+    prev = np.zeros(((shape[0] + 1) // 2, (shape[1] + 1) // 2, 3), np.int32); prev[..., 0] = 1; prev[..., 1] = 1; prev[..., 2] = 1
+    ok, bb = oracle.sgm_disp_bounds(shape, search, buf, prev=prev)
+    di, _ = oracle.sgm_calc_disparity_bounds(left, right, search, 3, bb)
+    assert ((di[..., 0] == 2) & (di[..., 1] == 1)).mean() > 0.99
