@@ -299,7 +299,7 @@ def sgm_output_shape(left, right, search, kernel_size):
     return (max(0, min(lh - 1 - hk, rh - 1 - (hk + search[1])) - hk + 1), max(0, min(lw - 1 - hk, rw - 1 - (hk + search[0])) - hk + 1))
 
 
-def sgm_calc_disparity_bounds(left, right, search, kernel_size, bounds, subpixel_mode=0, p1=0, p2=0):
+def sgm_calc_disparity_bounds(left, right, search, kernel_size, bounds, subpixel_mode=0, p1=0, p2=0, use_mgm=False):
     """SGM core with a search box per pixel: bounds (oh, ow, 4) int32 {min_x, min_y, max_x, max_y} inclusive (max < min = none).
     Returns (int32 disparity, float32 sub-pixel disparity)."""
     l, r = _f32(left), _f32(right)
@@ -309,7 +309,7 @@ def sgm_calc_disparity_bounds(left, right, search, kernel_size, bounds, subpixel
     out = np.empty((oh, ow, 3), np.int32)
     sub = np.empty((oh, ow, 3), np.float32)
     cw, ch = C.c_int(0), C.c_int(0)
-    f = lib().vwo_sgm_calc_disparity_bounds
+    f = lib().vwo_mgm_calc_disparity_bounds if use_mgm else lib().vwo_sgm_calc_disparity_bounds
     f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     rc = f(_p(l), l.shape[1], l.shape[0], l.shape[1], _p(r), r.shape[1], r.shape[0], r.shape[1], search[0], search[1], kernel_size, p1, p2,

@@ -146,6 +146,11 @@ int vwo_sgm_calc_disparity_bounds(const float* left, int lw, int lh, int lpitch,
                                   int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, const int* bounds,
                                   int* out, float* out_sub, int* out_w, int* out_h);
 
+/* ... with MGM accumulation instead of SGM (accum_mgm_multithread, SGM.cc:2619-2700; SGMAssist.h:835-1239) */
+int vwo_mgm_calc_disparity_bounds(const float* left, int lw, int lh, int lpitch, const float* right, int rw, int rh, int rpitch,
+                                  int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, const int* bounds,
+                                  int* out, float* out_sub, int* out_w, int* out_h);
+
 /* SemiGlobalMatcher::populate_disp_bound_image (SGM.cc:241-500) + one constrain_disp_bound_image pass (:502-668) at the
  * given conservation level: per-pixel search boxes from masks and the previous half-resolution disparity. */
 int vwo_sgm_disp_bounds(const int* prev, int pw, int ph, const uint8_t* lmask, const uint8_t* rmask, int rmw, int rmh,

@@ -16,7 +16,8 @@
  * Further down: the same pipeline with a search box per pixel (vwo_sgm_calc_disparity_bounds) and the derivation of those
  * boxes from masks and the previous pyramid level (vwo_sgm_disp_bounds: populate_disp_bound_image / constrain_disp_bound_image,
  * :241-668) -- oracle only so far, the device side is round-2 work.
- * Not restated yet: MGM, ternary census, the memory-limit retry loop (:476-497), the 2-D parabola sub-pixel mode.  Pinned by TestSGM.cxx:27-75 (> 99 % of the pixels equal the true constant offset) on the reference's own
+ * and MGM accumulation (vwo_mgm_calc_disparity_bounds).  Not restated yet: ternary census, the memory-limit retry loop
+ * (:476-497), the 2-D parabola sub-pixel mode, the R->L / filtering glue of CorrelationView.cc:360-590.  Pinned by TestSGM.cxx:27-75 (> 99 % of the pixels equal the true constant offset) on the reference's own
  * fixture images; the sub-pixel stage has no known-answer test in the reference (floats: tolerance 1e-5 on the GPU side).
  *
  * The accumulation order of the reference is thread dependent but irrelevant: every pixel lies on exactly one line per
@@ -334,8 +335,38 @@ typedef struct {
 
 static inline int nb_disp(const int* b) { return (b[2] < b[0] || b[3] < b[1]) ? 0 : (b[2] - b[0] + 1) * (b[3] - b[1] + 1); }   /* SGM.h:244-251 */
 
-static void sgm_line_bounds(const SgmB* s, int c, int r, int sc, int sr, accum_t* buf /* 2 * nd */, accum_t* full_prior /* nd, all BAD */) {
+/* evaluate_path, SSE flavour (:1014-1141), for a pixel with box b whose predecessor has box bp and packed costs prior */
+static void eval_path_bounds(const SgmB* s, const int* b, const int* bp, const accum_t* prior, const cost_t* local, accum_t* out, int diff,
+                             accum_t* full_prior /* nd, all BAD on entry and on exit */) {
   const accum_t BAD = (accum_t)(255 + s->p2);
+  accum_t p2_mod = (accum_t)s->p2;
+  if (diff > 0) p2_mod = (accum_t)(p2_mod / diff);
+  if (p2_mod < s->p1) p2_mod = (accum_t)s->p1;
+  accum_t min_prior = BAD;
+  int d = 0;
+  for (int dy = bp[1]; dy <= bp[3]; ++dy)                           /* scatter the previous pixel's costs (:1037-1054) */
+    for (int dx = bp[0]; dx <= bp[2]; ++dx, ++d) {
+      if (prior[d] < min_prior) min_prior = prior[d];
+      full_prior[dy * s->ndx + dx] = prior[d];
+    }
+  const accum_t dJ = (accum_t)(min_prior + p2_mod);
+  int pd = 0;
+  for (int dy = b[1]; dy <= b[3]; ++dy)
+    for (int dx = b[0]; dx <= b[2]; ++dx, ++pd) {
+      const int fd = dy * s->ndx + dx;
+      const int* a = s->adj + (size_t)fd * 8;
+      accum_t m = min16(min16(min16(full_prior[a[0]], full_prior[a[1]]), min16(full_prior[a[2]], full_prior[a[3]])),
+                        min16(min16(full_prior[a[4]], full_prior[a[5]]), min16(full_prior[a[6]], full_prior[a[7]])));
+      accum_t res = sat_add(m, (accum_t)s->p1);
+      res = min16(res, min16(full_prior[fd], dJ));
+      res = sat_add(res, (accum_t)local[pd]);
+      out[pd] = sat_sub(res, min_prior);
+    }
+  for (int dy = bp[1]; dy <= bp[3]; ++dy)                           /* restore the flag value (:1131-1139) */
+    for (int dx = bp[0]; dx <= bp[2]; ++dx) full_prior[dy * s->ndx + dx] = BAD;
+}
+
+static void sgm_line_bounds(const SgmB* s, int c, int r, int sc, int sr, accum_t* buf /* 2 * nd */, accum_t* full_prior /* nd, all BAD */) {
   accum_t* prior = buf;
   accum_t* cur = buf + s->nd;
   int last_val = -1;
@@ -347,35 +378,8 @@ static void sgm_line_bounds(const SgmB* s, int c, int r, int sc, int sr, accum_t
     const cost_t* local = s->cost + st;
     const int cur_val = s->left[(size_t)(r + s->min_row) * s->lw + (c + s->min_col)];
     const int diff = abs(cur_val - last_val);
-    if (last_val >= 0) {
-      accum_t p2_mod = (accum_t)s->p2;
-      if (diff > 0) p2_mod = (accum_t)(p2_mod / diff);
-      if (p2_mod < s->p1) p2_mod = (accum_t)s->p1;
-      accum_t min_prior = BAD;
-      int d = 0;
-      for (int dy = bp[1]; dy <= bp[3]; ++dy)                       /* scatter the previous pixel's costs (:1037-1054) */
-        for (int dx = bp[0]; dx <= bp[2]; ++dx, ++d) {
-          if (prior[d] < min_prior) min_prior = prior[d];
-          full_prior[dy * s->ndx + dx] = prior[d];
-        }
-      const accum_t dJ = (accum_t)(min_prior + p2_mod);
-      int pd = 0;
-      for (int dy = b[1]; dy <= b[3]; ++dy)
-        for (int dx = b[0]; dx <= b[2]; ++dx, ++pd) {
-          const int fd = dy * s->ndx + dx;
-          const int* a = s->adj + (size_t)fd * 8;
-          accum_t m = min16(min16(min16(full_prior[a[0]], full_prior[a[1]]), min16(full_prior[a[2]], full_prior[a[3]])),
-                            min16(min16(full_prior[a[4]], full_prior[a[5]]), min16(full_prior[a[6]], full_prior[a[7]])));
-          accum_t res = sat_add(m, (accum_t)s->p1);
-          res = min16(res, min16(full_prior[fd], dJ));
-          res = sat_add(res, (accum_t)local[pd]);
-          cur[pd] = sat_sub(res, min_prior);
-        }
-      for (int dy = bp[1]; dy <= bp[3]; ++dy)                       /* restore the flag value (:1131-1139) */
-        for (int dx = bp[0]; dx <= bp[2]; ++dx) full_prior[dy * s->ndx + dx] = BAD;
-    } else {
-      for (int d = 0; d < n; ++d) cur[d] = local[d];
-    }
+    if (last_val >= 0) eval_path_bounds(s, b, bp, prior, local, cur, diff, full_prior);
+    else for (int d = 0; d < n; ++d) cur[d] = local[d];
     accum_t* acc = s->accum + st;
     for (int d = 0; d < n; ++d) acc[d] = (accum_t)(acc[d] + cur[d]);
     accum_t* t = prior; prior = cur; cur = t;
@@ -385,9 +389,67 @@ static void sgm_line_bounds(const SgmB* s, int c, int r, int sc, int sr, accum_t
   }
 }
 
+/* MGM (accum_mgm_multithread, SGM.cc:2619-2700; SmoothPathAccumTask, SGMAssist.h:835-1239): eight full-image sweeps; in
+ * each, a pixel's path cost is the (truncating) mean of evaluate_path from TWO predecessors, or its local cost on the
+ * borders listed below; the sweep's result is added to the accumulation buffer (MultiAccumRowBuffer::add_lead_buffer_to_accum,
+ * :357-387).  Both evaluations use the SAME grey-value difference, and get_path_pixel_diff (SGM.cc:2715-2721) looks at the
+ * pixel OPPOSITE to the direction it is given -- kept as is. */
+typedef struct { int p1c, p1r, p2c, p2r, dirx, diry; int need_r_gt0, need_r_lt, need_c_gt0, need_c_lt; int col_major, c_desc, r_desc; } MgmTask;
+static const MgmTask MGM_TASKS[8] = {
+  /* L  */ {-1, 0, 0, -1, -1, 0, 1, 0, 1, 0, 0, 0, 0},
+  /* R  */ {1, 0, 0, 1, 1, 0, 0, 1, 0, 1, 0, 1, 1},
+  /* TL */ {-1, -1, 1, -1, -1, -1, 1, 0, 1, 1, 0, 0, 0},
+  /* BR */ {1, 1, -1, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1},
+  /* T  */ {0, -1, 1, 0, 0, -1, 1, 0, 0, 1, 1, 1, 0},
+  /* B  */ {0, 1, -1, 0, 0, 1, 0, 1, 1, 0, 1, 0, 1},
+  /* TR */ {1, -1, 1, 1, 1, -1, 1, 1, 0, 1, 1, 1, 0},
+  /* BL */ {-1, 1, -1, -1, -1, 1, 1, 1, 1, 0, 1, 0, 1},
+};
+static void mgm_sweep(const SgmB* s, const MgmTask* t, accum_t* path /* ragged, like accum */, accum_t* tmp /* nd */, accum_t* full_prior) {
+  const int last_c = s->ow - 1, last_r = s->oh - 1;
+  const int n_outer = t->col_major ? s->ow : s->oh, n_inner = t->col_major ? s->oh : s->ow;
+  for (int oo = 0; oo < n_outer; ++oo)
+    for (int ii = 0; ii < n_inner; ++ii) {
+      int c, r;
+      if (t->col_major) { c = t->c_desc ? last_c - oo : oo; r = t->r_desc ? last_r - ii : ii; }
+      else { r = t->r_desc ? last_r - oo : oo; c = t->c_desc ? last_c - ii : ii; }
+      const size_t pix = (size_t)r * s->ow + c;
+      const int* b = s->bounds + pix * 4;
+      const int n = nb_disp(b);
+      if (n == 0) continue;
+      const cost_t* local = s->cost + s->starts[pix];
+      accum_t* out = path + s->starts[pix];
+      const int ok = (!t->need_r_gt0 || r > 0) && (!t->need_r_lt || r < last_r) && (!t->need_c_gt0 || c > 0) && (!t->need_c_lt || c < last_c);
+      if (!ok) { for (int d = 0; d < n; ++d) out[d] = local[d]; continue; }
+      const int a = s->left[(size_t)(r + s->min_row) * s->lw + (c + s->min_col)];
+      const int bb = s->left[(size_t)(r - t->diry + s->min_row) * s->lw + (c - t->dirx + s->min_col)];
+      const int diff = abs(a - bb);
+      const size_t q1 = (size_t)(r + t->p1r) * s->ow + (c + t->p1c), q2 = (size_t)(r + t->p2r) * s->ow + (c + t->p2c);
+      eval_path_bounds(s, b, s->bounds + q1 * 4, path + s->starts[q1], local, out, diff, full_prior);
+      eval_path_bounds(s, b, s->bounds + q2 * 4, path + s->starts[q2], local, tmp, diff, full_prior);
+      for (int d = 0; d < n; ++d) out[d] = (accum_t)(((int)out[d] + (int)tmp[d]) / 2);
+    }
+}
+
+static int sgm_bounds_core(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
+                           int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, const int* bounds,
+                           int* out, float* out_sub, int* out_w, int* out_h, int use_mgm);
 int vwo_sgm_calc_disparity_bounds(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
                                   int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, const int* bounds,
                                   int* out, float* out_sub, int* out_w, int* out_h) {
+  return sgm_bounds_core(left_f, lw, lh, lpitch, right_f, rw, rh, rpitch, search_x, search_y, kernel_size, p1, p2, subpixel_mode, bounds, out, out_sub,
+                         out_w, out_h, 0);
+}
+/* the same with MGM accumulation (use_mgm of calc_disparity_sgm) */
+int vwo_mgm_calc_disparity_bounds(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
+                                  int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, const int* bounds,
+                                  int* out, float* out_sub, int* out_w, int* out_h) {
+  return sgm_bounds_core(left_f, lw, lh, lpitch, right_f, rw, rh, rpitch, search_x, search_y, kernel_size, p1, p2, subpixel_mode, bounds, out, out_sub,
+                         out_w, out_h, 1);
+}
+static int sgm_bounds_core(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
+                           int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, const int* bounds,
+                           int* out, float* out_sub, int* out_w, int* out_h, int use_mgm) {
   if (kernel_size != 3 && kernel_size != 5 && kernel_size != 7 && kernel_size != 9) return -2;
   if (search_x < 0 || search_y < 0 || !bounds) return -1;
   if (out_sub && (subpixel_mode == 1 || subpixel_mode < 0 || subpixel_mode > 5)) return -2;
@@ -451,14 +513,24 @@ int vwo_sgm_calc_disparity_bounds(const float* left_f, int lw, int lh, int lpitc
   accum_t* buf = (accum_t*)malloc((size_t)2 * s.nd * sizeof(accum_t));
   accum_t* full_prior = (accum_t*)malloc((size_t)s.nd * sizeof(accum_t));
   for (int d = 0; d < s.nd; ++d) full_prior[d] = (accum_t)(255 + p2);
-  for (int k = 0; k < 8; ++k) {
-    const int sc = DIRS[k][0], sr = DIRS[k][1];
-    for (int r = 0; r < s.oh; ++r)
-      for (int c = 0; c < s.ow; ++c) {
-        const int pc = c - sc, pr = r - sr;
-        if (pc >= 0 && pc < s.ow && pr >= 0 && pr < s.oh) continue;
-        sgm_line_bounds(&s, c, r, sc, sr, buf, full_prior);
-      }
+  if (!use_mgm) {
+    for (int k = 0; k < 8; ++k) {
+      const int sc = DIRS[k][0], sr = DIRS[k][1];
+      for (int r = 0; r < s.oh; ++r)
+        for (int c = 0; c < s.ow; ++c) {
+          const int pc = c - sc, pr = r - sr;
+          if (pc >= 0 && pc < s.ow && pr >= 0 && pr < s.oh) continue;
+          sgm_line_bounds(&s, c, r, sc, sr, buf, full_prior);
+        }
+    }
+  } else {
+    accum_t* path = (accum_t*)malloc(total * sizeof(accum_t));
+    for (int k = 0; k < 8; ++k) {
+      memset(path, 0, total * sizeof(accum_t));
+      mgm_sweep(&s, &MGM_TASKS[k], path, buf, full_prior);
+      for (size_t i = 0; i < total; ++i) accum[i] = (accum_t)(accum[i] + path[i]);
+    }
+    free(path);
   }
   accum_t* tmp = (accum_t*)malloc((size_t)s.nd * sizeof(accum_t));
   for (int j = 0; j < s.oh; ++j)

@@ -132,3 +132,22 @@ def test_sgm_disp_bounds_from_previous_level(oracle):
     ok, bb = oracle.sgm_disp_bounds(shape, search, buf, prev=prev)
     di, _ = oracle.sgm_calc_disparity_bounds(left, right, search, 3, bb)
     assert ((di[..., 0] == 2) & (di[..., 1] == 1)).mean() > 0.99
+
+
+def test_mgm_accumulation(oracle):
+    """MGM (accum_mgm_multithread, SGM.cc:2619-2700): same KAT shape as TestSGM.cxx with use_mgm = true -- the constant
+    offset is recovered; the accumulated costs differ from plain SGM (two predecessors averaged), so the sub-pixel part does too."""
+    left, right = _constant_offset_pair(31, 120, 90)
+    oh, ow = oracle.sgm_output_shape(left, right, (8, 8), 3)
+    full = np.tile(np.array([0, 0, 8, 8], np.int32), (oh, ow, 1))
+    mi, mf = oracle.sgm_calc_disparity_bounds(left, right, (8, 8), 3, full, subpixel_mode=5, use_mgm=True)
+    si, sf = oracle.sgm_calc_disparity_bounds(left, right, (8, 8), 3, full, subpixel_mode=5)
+    dd = mi[..., :2] + np.array([-4, -4])
+    assert ((dd[..., 0] == 2) & (dd[..., 1] == 1)).mean() > 0.99
+    assert not np.array_equal(mf, sf)
+    mi2, mf2 = oracle.sgm_calc_disparity_bounds(left, right, (8, 8), 3, full, subpixel_mode=5, use_mgm=True)
+    assert np.array_equal(mi, mi2) and np.array_equal(mf, mf2)
+    # ragged boxes and empty pixels go through the MGM sweeps as well
+    b = full.copy(); b[10:20, 10:30] = (0, 0, -1, -1); b[40:50, :, 0] = 4; b[40:50, :, 1] = 3
+    ri, _ = oracle.sgm_calc_disparity_bounds(left, right, (8, 8), 3, b, use_mgm=True)
+    assert (ri[10:20, 10:30] == 0).all() and (ri[45, :, 0] >= 4).all()
