@@ -780,8 +780,10 @@ int vwo_parabola_subpixel(const float* disp, int cols, int rows, const float* le
       id[(size_t)y * bw + x] = v;
       if (v.valid) {      /* get_disparity_range (DisparityMap.h:52-66) */
         if (!any) { mnx = mxx = v.dx; mny = mxy = v.dy; any = 1; }
-        if (v.dx < mnx) mnx = v.dx; if (v.dx > mxx) mxx = v.dx;
-        if (v.dy < mny) mny = v.dy; if (v.dy > mxy) mxy = v.dy;
+        if (v.dx < mnx) mnx = v.dx;
+        if (v.dx > mxx) mxx = v.dx;
+        if (v.dy < mny) mny = v.dy;
+        if (v.dy > mxy) mxy = v.dy;
       }
     }
   /* entire_search_range: max += 1; expand(1)  (:296-299) */
