@@ -45,7 +45,13 @@ extern "C" {
 #define VWB200_ENOMEM     -7
 
 /* vw::stereo::CostFunctionType, src/vw/Stereo/CostFunctions.h:143-149 */
-enum { VWB200_ABSOLUTE_DIFFERENCE = 0, VWB200_SQUARED_DIFFERENCE = 1, VWB200_CROSS_CORRELATION = 2 };
+enum { VWB200_ABSOLUTE_DIFFERENCE = 0, VWB200_SQUARED_DIFFERENCE = 1, VWB200_CROSS_CORRELATION = 2,
+       VWB200_CENSUS_TRANSFORM = 3, VWB200_TERNARY_CENSUS_TRANSFORM = 4 };
+/* vw::stereo::CorrelationAlgorithm, src/vw/Stereo/CorrelationAlgorithms.h:29-35 */
+enum { VWB200_CORRELATION_BM = 0, VWB200_CORRELATION_SGM = 1, VWB200_CORRELATION_MGM = 2, VWB200_CORRELATION_FINAL_MGM = 3 };
+/* vw::stereo::SemiGlobalMatcher::SgmSubpixelMode, src/vw/Stereo/SGM.h:93-99 */
+enum { VWB200_SUBPIXEL_NONE = 0, VWB200_SUBPIXEL_PARABOLA = 1, VWB200_SUBPIXEL_LINEAR = 2, VWB200_SUBPIXEL_POLY4 = 3,
+       VWB200_SUBPIXEL_COSINE = 4, VWB200_SUBPIXEL_LC_BLEND = 5 };
 /* vw::stereo::PrefilterModeType, src/vw/Stereo/PrefilterEnum.h:24-28 */
 enum { VWB200_PREFILTER_NONE = 0, VWB200_PREFILTER_LOG = 1, VWB200_PREFILTER_MEANSUB = 2 };
 
@@ -120,27 +126,63 @@ int vwb200_parabola_subpixel(const float* disparity, int cols, int rows, const f
 
 /* ---------------------------------------------------------------------------------------------
  * vw::stereo::calc_disparity_sgm (src/vw/Stereo/SGM.cc:167-230, SGM.h:361-376) ->
- * SemiGlobalMatcher::semi_global_matching_func (:2387-2448), first cut of row a10: CENSUS_TRANSFORM costs
- * (kernel_size 3/5/7/9), SGM accumulation along 8 directions, integer winner; the same search box
- * [0, search_x] x [0, search_y] (inclusive, = search_volume of the reference) for every pixel; no masks, no
- * previous disparity, no MGM, no sub-pixel stage (-> VWB200_ENOIMPL / not offered).  left / right are the
- * cropped left_region / right_region rasters (any float range: u8_convert is applied like the reference does).
- * p1 / p2 <= 0 select the reference's defaults (:108-157).  out receives out_w x out_h pixels (row pitch
- * opitch elements; the size is (:2397-2420) and can be queried first with out == NULL).
+ * SemiGlobalMatcher::semi_global_matching_func (:2387-2448): u8_convert, (ternary) census costs for kernel 3/5/7/9,
+ * per-pixel search boxes, SGM or MGM accumulation along 8 directions, integer winner with the reference's tie
+ * smoothing, optional sub-pixel stage.  left / right are the cropped left_region / right_region rasters (any float
+ * range).  Disparities lie in [0, search_x] x [0, search_y] (inclusive = search_volume of the reference).
+ * out receives out_w x out_h pixels (row pitch opitch elements; the size is (:2397-2420) and can be queried first
+ * with all outputs NULL).
  * ------------------------------------------------------------------------------------------- */
+/* the simple form: the same search box for every pixel (populate_constant_disp_bound_image, :231-239), plain
+ * census costs, no masks, no previous disparity; p1 / p2 <= 0 select the reference's defaults (:108-157) */
 int vwb200_sgm_calc_disparity(const float* left, int lw, int lh, ptrdiff_t lpitch,
                               const float* right, int rw, int rh, ptrdiff_t rpitch,
                               int search_x, int search_y, int kernel_size, int p1, int p2,
                               vwb200_dispi* out, ptrdiff_t opitch, int* out_w, int* out_h, int on_device, void* stream);
 /* ... followed by SemiGlobalMatcher::create_disparity_view_subpixel (SGM.cc:1497-1614) on the integer result:
- * subpixel_mode = SgmSubpixelMode (SGM.h:93-99): 0 none, 2 linear, 3 poly4, 4 cosine, 5 lc_blend; 1 (2-D parabola)
- * -> VWB200_ENOIMPL.  out (may be NULL) gets the integer disparity, out_sub the float {dx, dy, valid} pixels
- * (sub_pitch in pixels).  Floats agree with the reference's double arithmetic within 1e-5. */
+ * subpixel_mode = SgmSubpixelMode.  out (may be NULL) gets the integer disparity, out_sub the float
+ * {dx, dy, valid} pixels (sub_pitch in pixels).  Floats agree with the reference's double arithmetic within 1e-5. */
 int vwb200_sgm_calc_disparity_subpixel(const float* left, int lw, int lh, ptrdiff_t lpitch,
                                        const float* right, int rw, int rh, ptrdiff_t rpitch,
                                        int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode,
                                        vwb200_dispi* out, ptrdiff_t opitch, float* out_sub, ptrdiff_t sub_pitch,
                                        int* out_w, int* out_h, int on_device, void* stream);
+
+/* the full form.  vwb200_sgm_params mirrors the SemiGlobalMatcher constructor (SGM.h:104-121). */
+typedef struct {
+  int32_t search_x, search_y;            /* max disparity, inclusive (min is 0) */
+  int32_t kernel_size;                   /* 3, 5, 7 or 9 */
+  int32_t cost_type;                     /* VWB200_CENSUS_TRANSFORM or VWB200_TERNARY_CENSUS_TRANSFORM; anything else:
+                                            VWB200_ENOIMPL like SGM.cc:1888-1892 */
+  int32_t ternary_threshold;             /* ternary_census_threshold (default 5) */
+  int32_t p1, p2;                        /* <= 0: the reference's defaults for the cost type and kernel */
+  int32_t use_mgm;
+  int32_t subpixel_mode;
+  int32_t search_buffer_x, search_buffer_y;   /* sgm_search_buffer, applied around the doubled previous disparity */
+  int32_t conserve_level;                /* -1: the reference's retry loop (SGM.cc:476-497): levels 0..3 until the buffers
+                                            fit memory_limit_mb; 0..3: exactly that level of constrain_disp_bound_image */
+  double  memory_limit_mb;               /* <= 0: 6000 (CorrelationView.h:65) */
+  int32_t assumed_threads;               /* vw_settings().default_num_threads() of the size estimate (:715-716); <= 0: 4 */
+  int32_t reserved;
+} vwb200_sgm_params;
+/* lmask (out_w x out_h, the size of the output, :250-256) / rmask (at least output + search, :262-268) / prev (the
+ * half-resolution integer disparity of the previous pyramid level) may each be NULL.  bounds != NULL: use these
+ * out_w * out_h boxes {min_x, min_y, max_x, max_y} (inclusive; max < min = no search area) instead of deriving them.
+ * bounds_out (may be NULL) receives the boxes that were used. */
+int vwb200_sgm_calc_disparity_ex(const vwb200_sgm_params* params,
+                                 const float* left, int lw, int lh, ptrdiff_t lpitch,
+                                 const float* right, int rw, int rh, ptrdiff_t rpitch,
+                                 const uint8_t* lmask, ptrdiff_t lmpitch,
+                                 const uint8_t* rmask, int rmw, int rmh, ptrdiff_t rmpitch,
+                                 const vwb200_dispi* prev, int pw, int ph, ptrdiff_t ppitch,
+                                 const int32_t* bounds,
+                                 vwb200_dispi* out, ptrdiff_t opitch, float* out_sub, ptrdiff_t sub_pitch,
+                                 int32_t* bounds_out, int* out_w, int* out_h, int on_device, void* stream);
+/* only SemiGlobalMatcher::populate_disp_bound_image + constrain_disp_bound_image (SGM.cc:241-668) for an
+ * ow x oh output: bounds receives ow * oh boxes */
+int vwb200_sgm_disp_bounds(const vwb200_sgm_params* params, const vwb200_dispi* prev, int pw, int ph, ptrdiff_t ppitch,
+                           const uint8_t* lmask, ptrdiff_t lmpitch, const uint8_t* rmask, int rmw, int rmh, ptrdiff_t rmpitch,
+                           int ow, int oh, int32_t* bounds, int on_device, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The lazy view: vw::stereo::PyramidCorrelationView (src/vw/Stereo/CorrelationView.h:35-193,

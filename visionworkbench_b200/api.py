@@ -22,10 +22,13 @@ _SO = os.path.join(_HERE, "libvwb200.so")
 _LIB = None
 
 # vw::stereo::CostFunctionType (Stereo/CostFunctions.h:143-149)
-ABSOLUTE_DIFFERENCE, SQUARED_DIFFERENCE, CROSS_CORRELATION = 0, 1, 2
+ABSOLUTE_DIFFERENCE, SQUARED_DIFFERENCE, CROSS_CORRELATION, CENSUS_TRANSFORM, TERNARY_CENSUS_TRANSFORM = 0, 1, 2, 3, 4
 # vw::stereo::PrefilterModeType (Stereo/PrefilterEnum.h:24-28)
 PREFILTER_NONE, PREFILTER_LOG, PREFILTER_MEANSUB = 0, 1, 2
-VW_CORRELATION_BM = 0
+# vw::stereo::CorrelationAlgorithm (Stereo/CorrelationAlgorithms.h:29-35)
+VW_CORRELATION_BM, VW_CORRELATION_SGM, VW_CORRELATION_MGM, VW_CORRELATION_FINAL_MGM = 0, 1, 2, 3
+# SemiGlobalMatcher::SgmSubpixelMode (Stereo/SGM.h:93-99)
+SUBPIXEL_NONE, SUBPIXEL_PARABOLA, SUBPIXEL_LINEAR, SUBPIXEL_POLY4, SUBPIXEL_COSINE, SUBPIXEL_LC_BLEND = 0, 1, 2, 3, 4, 5
 
 
 class VwError(RuntimeError):
@@ -69,6 +72,14 @@ class CorrParams(C.Structure):
                 ("algorithm", C.c_int32), ("blob_filter_area", C.c_int32)]
 
 
+class SgmParams(C.Structure):
+    _fields_ = [("search_x", C.c_int32), ("search_y", C.c_int32), ("kernel_size", C.c_int32), ("cost_type", C.c_int32),
+                ("ternary_threshold", C.c_int32), ("p1", C.c_int32), ("p2", C.c_int32), ("use_mgm", C.c_int32),
+                ("subpixel_mode", C.c_int32), ("search_buffer_x", C.c_int32), ("search_buffer_y", C.c_int32),
+                ("conserve_level", C.c_int32), ("memory_limit_mb", C.c_double), ("assumed_threads", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class K1Stats(C.Structure):
     _fields_ = [("path", C.c_int32), ("launches", C.c_int32), ("kernel_ms", C.c_float), ("reserved", C.c_int32)]
 
@@ -91,6 +102,9 @@ def lib():
         L.vwb200_prefilter.argtypes = [P, I, I, Z, I, F, P, Z, I, P]
         L.vwb200_sgm_calc_disparity.argtypes = [P, I, I, Z, P, I, I, Z, I, I, I, I, I, P, Z, C.POINTER(I), C.POINTER(I), I, P]
         L.vwb200_sgm_calc_disparity_subpixel.argtypes = [P, I, I, Z, P, I, I, Z, I, I, I, I, I, I, P, Z, P, Z, C.POINTER(I), C.POINTER(I), I, P]
+        L.vwb200_sgm_calc_disparity_ex.argtypes = [C.POINTER(SgmParams), P, I, I, Z, P, I, I, Z, P, Z, P, I, I, Z, P, I, I, Z, P, P, Z, P, Z, P,
+                                                   C.POINTER(I), C.POINTER(I), I, P]
+        L.vwb200_sgm_disp_bounds.argtypes = [C.POINTER(SgmParams), P, I, I, Z, P, Z, P, I, I, Z, I, I, P, I, P]
         L.vwb200_parabola_subpixel.argtypes = [P, I, I, P, Z, P, I, I, Z, I, I, I, F, I, I, I, I, P, Z, I, P]
         L.vwb200_cross_corr_consistency_check.argtypes = [P, I, I, Z, P, I, I, Z, F, I, P]
         L.vwb200_rm_outliers_using_thresh.argtypes = [P, I, I, I, I, D, D, P, I, P]
@@ -214,6 +228,68 @@ def calc_disparity_sgm_subpixel(left_in, right_in, search_volume, kernel_size, s
     if out.size:
         _check(lib().vwb200_sgm_calc_disparity_subpixel(*args, out.ctypes.data, ow.value, sub.ctypes.data, ow.value, C.byref(ow), C.byref(oh), 0, None))
     return out, sub
+
+
+def _sgm_params(search_volume, kernel_size, cost_type=CENSUS_TRANSFORM, use_mgm=False, subpixel_mode=SUBPIXEL_NONE, search_buffer=(2, 2),
+                memory_limit_mb=6000, p1=0, p2=0, ternary_threshold=5, conserve_level=-1, assumed_threads=4):
+    return SgmParams(int(search_volume[0]), int(search_volume[1]), int(kernel_size), int(cost_type), int(ternary_threshold), int(p1), int(p2),
+                     int(bool(use_mgm)), int(subpixel_mode), int(search_buffer[0]), int(search_buffer[1]), int(conserve_level),
+                     float(memory_limit_mb), int(assumed_threads), 0)
+
+
+def calc_disparity_sgm_ex(cost_type, left_in, right_in, search_volume, kernel_size, use_mgm=False, subpixel_mode=SUBPIXEL_NONE,
+                          search_buffer=(2, 2), memory_limit_mb=6000, left_mask=None, right_mask=None, prev_disparity=None,
+                          bounds=None, p1=0, p2=0, ternary_threshold=5, conserve_level=-1, assumed_threads=4, return_bounds=False):
+    """vw::stereo::calc_disparity_sgm with all its arguments (Stereo/SGM.h:361-376, SGM.cc:167-230): cost type
+    (CENSUS_TRANSFORM / TERNARY_CENSUS_TRANSFORM), SGM or MGM, sub-pixel mode, search buffer, memory limit, masks and the
+    previous pyramid level's disparity (which give every pixel its own search box).  `bounds` (h, w, 4) overrides the boxes.
+    Returns (int32 (h, w, 3), float32 (h, w, 3) sub-pixel disparity[, int32 (h, w, 4) boxes])."""
+    sp = _sgm_params(search_volume, kernel_size, cost_type, use_mgm, subpixel_mode, search_buffer, memory_limit_mb, p1, p2, ternary_threshold,
+                     conserve_level, assumed_threads)
+    l, r = _np(left_in, np.float32), _np(right_in, np.float32)
+    ow, oh = C.c_int(0), C.c_int(0)
+    head = (C.byref(sp), l.ctypes.data, l.shape[1], l.shape[0], l.shape[1], r.ctypes.data, r.shape[1], r.shape[0], r.shape[1])
+    _check(lib().vwb200_sgm_calc_disparity_ex(*head, None, 0, None, 0, 0, 0, None, 0, 0, 0, None, None, 0, None, 0, None, C.byref(ow), C.byref(oh), 0, None))
+    h, w = max(oh.value, 0), max(ow.value, 0)
+    out = np.zeros((h, w, 3), np.int32)
+    sub = np.zeros((h, w, 3), np.float32)
+    bo = np.zeros((h, w, 4), np.int32)
+    if out.size:
+        lm = _np(left_mask, np.uint8) if left_mask is not None else None
+        rm = _np(right_mask, np.uint8) if right_mask is not None else None
+        pv = _np(prev_disparity, np.int32) if prev_disparity is not None else None
+        bd = _np(bounds, np.int32) if bounds is not None else None
+        if lm is not None and lm.shape != (h, w):
+            raise LogicErr("Left mask size does not match the output size.")
+        if bd is not None and bd.shape != (h, w, 4):
+            raise ArgumentErr("sgm: bounds must be (out_h, out_w, 4)")
+        _check(lib().vwb200_sgm_calc_disparity_ex(
+            *head, lm.ctypes.data if lm is not None else None, w, rm.ctypes.data if rm is not None else None,
+            rm.shape[1] if rm is not None else 0, rm.shape[0] if rm is not None else 0, rm.shape[1] if rm is not None else 0,
+            pv.ctypes.data if pv is not None else None, pv.shape[1] if pv is not None else 0, pv.shape[0] if pv is not None else 0,
+            pv.shape[1] if pv is not None else 0, bd.ctypes.data if bd is not None else None,
+            out.ctypes.data, w, sub.ctypes.data, w, bo.ctypes.data if return_bounds else None, C.byref(ow), C.byref(oh), 0, None))
+    return (out, sub, bo) if return_bounds else (out, sub)
+
+
+def sgm_disp_bounds(shape, search_volume, search_buffer=(2, 2), prev_disparity=None, left_mask=None, right_mask=None, conserve_level=0,
+                    use_mgm=False, memory_limit_mb=6000, assumed_threads=4):
+    """SemiGlobalMatcher::populate_disp_bound_image + constrain_disp_bound_image (Stereo/SGM.cc:241-668): the search box
+    {min_x, min_y, max_x, max_y} of every pixel of an (h, w) output."""
+    h, w = int(shape[0]), int(shape[1])
+    sp = _sgm_params(search_volume, 5, CENSUS_TRANSFORM, use_mgm, 0, search_buffer, memory_limit_mb, conserve_level=conserve_level,
+                     assumed_threads=assumed_threads)
+    lm = _np(left_mask, np.uint8) if left_mask is not None else None
+    rm = _np(right_mask, np.uint8) if right_mask is not None else None
+    pv = _np(prev_disparity, np.int32) if prev_disparity is not None else None
+    if lm is not None and lm.shape != (h, w):
+        raise LogicErr("Left mask size does not match the output size.")
+    out = np.zeros((h, w, 4), np.int32)
+    _check(lib().vwb200_sgm_disp_bounds(
+        C.byref(sp), pv.ctypes.data if pv is not None else None, pv.shape[1] if pv is not None else 0, pv.shape[0] if pv is not None else 0,
+        pv.shape[1] if pv is not None else 0, lm.ctypes.data if lm is not None else None, w, rm.ctypes.data if rm is not None else None,
+        rm.shape[1] if rm is not None else 0, rm.shape[0] if rm is not None else 0, rm.shape[1] if rm is not None else 0, w, h, out.ctypes.data, 0, None))
+    return out
 
 
 def pyramid_down(img):

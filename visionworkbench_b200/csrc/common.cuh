@@ -6,6 +6,7 @@
 #include <string>
 #include <atomic>
 #include <vector>
+#include <algorithm>
 #include "../../include/vwb200.h"
 
 namespace vwb200 {
@@ -40,6 +41,22 @@ extern std::atomic<long long> g_launches;
   } while (0)
 
 int ensure_device();   // VWB200_ENODEVICE when there is no CUDA device
+
+// stream-ordered device buffers owned by one call
+struct Arena {
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  explicit Arena(cudaStream_t s) : st(s) {}
+  ~Arena() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+  template <class T> int alloc(T** out, size_t n) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st);
+    if (e != cudaSuccess) { set_error("cudaMallocAsync(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return VWB200_ENOMEM; }
+    ptrs.push_back(p);
+    *out = static_cast<T*>(p);
+    return VWB200_OK;
+  }
+};
 
 // ---- image descriptors (device pointers) ------------------------------------------------------
 struct ImgF { const float* p; int w, h; ptrdiff_t pitch; };
@@ -92,11 +109,7 @@ size_t k1_screen_workspace_bytes(int cost, int W, int H, int sx, int sy, int kx,
 int k1_screen_launch(int cost, ImgF left, ImgF right, int W, int H, int sx, int sy, int kx, int ky, float vmin, float vmax,
                      vwb200_dispi* out, ptrdiff_t opitch, void* workspace, cudaStream_t st, const KEvents* ev = nullptr,
                      const FastOrigin* org = nullptr);
-// ---- SemiGlobalMatcher core (k5_sgm.cu) ------------------------------------------------------
-int sgm_output_size(int lw, int lh, int rw, int rh, int sx, int sy, int k, int* ow, int* oh);
-size_t sgm_workspace_bytes(int lw, int lh, int rw, int rh, int sx, int sy, int k);
-int sgm_launch(ImgF left, ImgF right, int sx, int sy, int k, int p1, int p2, vwb200_dispi* out, ptrdiff_t opitch, void* workspace,
-               cudaStream_t st, int subpixel_mode = 0, float* out_sub = nullptr, ptrdiff_t sub_pitch = 0);
+// ---- SemiGlobalMatcher (k5_sgm.cu, k5_sgm_paths.cu; declarations in k5_sgm.cuh) ---------------
 // exact sequential re-evaluation of pixels flagged NaN by k1 (NCC zero-energy windows)
 int k1_nan_fixup_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, int nzones, int kx, int ky,
                         NccMaps ncc, vwb200_dispi* out, cudaStream_t st, int gridx = 8);

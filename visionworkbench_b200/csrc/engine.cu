@@ -6,6 +6,7 @@
 // owns a stream and stream-ordered allocations (VW calls prerasterize concurrently from its tile
 // thread pool, Image/ImageIO.h:228-235).
 #include "common.cuh"
+#include "k5_sgm.cuh"
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -58,24 +59,14 @@ int zone_post_launch(const Tile* d_tiles, int ntiles, const Zone* d_zones, const
 // ---------------------------------------------------------------------------------------------------
 // small RAII helpers: stream-ordered device buffers, an owned-or-borrowed stream
 // ---------------------------------------------------------------------------------------------------
-struct Arena {
-  cudaStream_t st;
-  std::vector<void*> ptrs;
-  explicit Arena(cudaStream_t s) : st(s) {}
-  ~Arena() { for (void* p : ptrs) cudaFreeAsync(p, st); }
-  template <class T> int alloc(T** out, size_t n) {
-    void* p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st);
-    if (e != cudaSuccess) { set_error("cudaMallocAsync(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return VWB200_ENOMEM; }
-    ptrs.push_back(p);
-    *out = static_cast<T*>(p);
-    return VWB200_OK;
-  }
-};
 struct StreamGuard {
   cudaStream_t st = nullptr; bool own = false;
-  int init(void* user) {
+  // device-resident inputs are produced on the caller's stream: a NULL stream then means the legacy default stream
+  // (which is what e.g. torch's default stream is), never a private one -- otherwise the kernels could start before the
+  // producer of their inputs has finished.  Host-resident calls with no stream get a private non-blocking stream.
+  int init(void* user, int device_resident = 0) {
     if (user) { st = static_cast<cudaStream_t>(user); return VWB200_OK; }
+    if (device_resident) { st = cudaStreamLegacy; return VWB200_OK; }
     VWB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     own = true;
     return VWB200_OK;
@@ -644,7 +635,7 @@ int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrd
   if (cost_type < 0 || cost_type > 2) { set_error("calc_disparity: unsupported cost type %d", cost_type); return VWB200_EARG; }
   if (!left || !right || !out) { set_error("calc_disparity: null pointer"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
-  StreamGuard sg; VWB_TRY(sg.init(stream));
+  StreamGuard sg; VWB_TRY(sg.init(stream, on_device));
   cudaStream_t st = sg.st;
   const long long launches0 = g_launches.load();
   KEvents kev;
@@ -705,7 +696,7 @@ int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrd
 int vwb200_pyramid_down(const float* in, int w, int h, ptrdiff_t pitch, float* out, ptrdiff_t opitch, int on_device, void* stream) {
   if (!in || !out || w <= 0 || h <= 0) { set_error("pyramid_down: bad arguments"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
-  StreamGuard sg; VWB_TRY(sg.init(stream));
+  StreamGuard sg; VWB_TRY(sg.init(stream, on_device));
   cudaStream_t st = sg.st;
   {
     Arena ar(st);
@@ -725,7 +716,7 @@ int vwb200_pyramid_down(const float* in, int w, int h, ptrdiff_t pitch, float* o
 int vwb200_prefilter(const float* in, int w, int h, ptrdiff_t pitch, int mode, float width, float* out, ptrdiff_t opitch, int on_device, void* stream) {
   if (!in || !out || w <= 0 || h <= 0) { set_error("prefilter: bad arguments"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
-  StreamGuard sg; VWB_TRY(sg.init(stream));
+  StreamGuard sg; VWB_TRY(sg.init(stream, on_device));
   cudaStream_t st = sg.st;
   {
     Arena ar(st);
@@ -739,59 +730,139 @@ int vwb200_prefilter(const float* in, int w, int h, ptrdiff_t pitch, int mode, f
   return VWB200_OK;
 }
 
-static int sgm_run(const float* left, int lw, int lh, ptrdiff_t lpitch, const float* right, int rw, int rh, ptrdiff_t rpitch,
-                   int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, vwb200_dispi* out, ptrdiff_t opitch,
-                   float* out_sub, ptrdiff_t sub_pitch, bool want_sub, int* out_w, int* out_h, int on_device, void* stream) {
-  if (!left || !right || lw <= 0 || lh <= 0 || rw <= 0 || rh <= 0 || !out_w || !out_h) { set_error("sgm_calc_disparity: bad arguments"); return VWB200_EARG; }
+// calc_disparity_sgm behind the C ABI: stage the inputs, run vwb200::sgm_run, copy the results back
+static int sgm_abi_run(const vwb200_sgm_params* sp, const float* left, int lw, int lh, ptrdiff_t lpitch, const float* right, int rw, int rh,
+                       ptrdiff_t rpitch, const uint8_t* lmask, ptrdiff_t lmpitch, const uint8_t* rmask, int rmw, int rmh, ptrdiff_t rmpitch,
+                       const vwb200_dispi* prev, int pw, int ph, ptrdiff_t ppitch, const int32_t* bounds, vwb200_dispi* out, ptrdiff_t opitch,
+                       float* out_sub, ptrdiff_t sub_pitch, int32_t* bounds_out, int* out_w, int* out_h, int on_device, void* stream) {
+  if (!sp || !left || !right || lw <= 0 || lh <= 0 || rw <= 0 || rh <= 0 || !out_w || !out_h) { set_error("sgm_calc_disparity: bad arguments"); return VWB200_EARG; }
+  const int kernel_size = sp->kernel_size, search_x = sp->search_x, search_y = sp->search_y;
   if (kernel_size % 2 != 1) { set_error("calc_disparity_sgm: Kernel input not sized with odd values."); return VWB200_EARG; }       // SGM.cc:184-185
   if (kernel_size > lw || kernel_size > lh) { set_error("calc_disparity_sgm: Kernel size too large of active region."); return VWB200_EARG; }
   if (search_x < 0 || search_y < 0) { set_error("calc_disparity_sgm: negative search volume"); return VWB200_EARG; }
-  if (want_sub && (subpixel_mode < 0 || subpixel_mode > 5)) { set_error("sgm: unknown sub-pixel mode %d", subpixel_mode); return VWB200_EARG; }
-  if (want_sub && subpixel_mode == 1) { set_error("sgm: SUBPIXEL_PARABOLA (2-D fit) is not implemented"); return VWB200_ENOIMPL; }
+  if (sp->cost_type != VWB200_CENSUS_TRANSFORM && sp->cost_type != VWB200_TERNARY_CENSUS_TRANSFORM) {
+    set_error("With SGM/MGM, only the census transform cost mode gives good results.");                                                // SGM.cc:1888-1892
+    return VWB200_ENOIMPL;
+  }
+  if (out_sub && (sp->subpixel_mode < 0 || sp->subpixel_mode > 5)) { set_error("sgm: unknown sub-pixel mode %d", sp->subpixel_mode); return VWB200_EARG; }
   VWB_TRY(sgm_output_size(lw, lh, rw, rh, search_x, search_y, kernel_size, out_w, out_h));
-  if (!out && !out_sub) return VWB200_OK;           // size query
+  if (!out && !out_sub && !bounds_out) return VWB200_OK;           // size query
   const int W = *out_w, H = *out_h;
   if ((out && opitch < W) || (out_sub && sub_pitch < W)) { set_error("sgm_calc_disparity: output pitch smaller than the output width"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
-  StreamGuard sg; VWB_TRY(sg.init(stream));
+  StreamGuard sg; VWB_TRY(sg.init(stream, on_device));
   cudaStream_t st = sg.st;
   {
     Arena ar(st);
+    SgmArgs a;
     const float *dl, *dr; ptrdiff_t dlp, drp;
     VWB_TRY(stage_in(left, lw, lh, lpitch, on_device, ar, st, &dl, &dlp));
     VWB_TRY(stage_in(right, rw, rh, rpitch, on_device, ar, st, &dr, &drp));
+    a.left = ImgF{dl, lw, lh, dlp}; a.right = ImgF{dr, rw, rh, drp};
+    a.sx = search_x; a.sy = search_y; a.k = kernel_size;
+    a.ternary = sp->cost_type == VWB200_TERNARY_CENSUS_TRANSFORM; a.ternary_threshold = sp->ternary_threshold;
+    a.p1 = sp->p1; a.p2 = sp->p2; a.use_mgm = sp->use_mgm; a.subpixel_mode = out_sub ? sp->subpixel_mode : 0;
+    a.buf_x = sp->search_buffer_x; a.buf_y = sp->search_buffer_y; a.conserve_level = sp->conserve_level;
+    a.memory_limit_mb = sp->memory_limit_mb > 0 ? sp->memory_limit_mb : 6000.0;
+    a.assumed_threads = sp->assumed_threads > 0 ? sp->assumed_threads : 4;
     if (W > 0 && H > 0) {
+      if (lmask) {
+        const uint8_t* d; ptrdiff_t dp;
+        VWB_TRY(stage_in(lmask, W, H, lmpitch, on_device, ar, st, &d, &dp));
+        a.lmask = ImgB{d, W, H, dp};
+      }
+      if (rmask) {
+        const uint8_t* d; ptrdiff_t dp;
+        VWB_TRY(stage_in(rmask, rmw, rmh, rmpitch, on_device, ar, st, &d, &dp));
+        a.rmask = ImgB{d, rmw, rmh, dp};
+      }
+      if (prev) {
+        if (pw <= 0 || ph <= 0) { set_error("sgm: empty previous disparity"); return VWB200_EARG; }
+        const vwb200_dispi* d; ptrdiff_t dp;
+        VWB_TRY(stage_in(prev, pw, ph, ppitch, on_device, ar, st, &d, &dp));
+        a.prev = d; a.pw = pw; a.ph = ph; a.ppitch = dp;
+      }
+      if (bounds) {
+        const int32_t* d; ptrdiff_t dp;
+        VWB_TRY(stage_in(bounds, W * 4, H, (ptrdiff_t)W * 4, on_device, ar, st, &d, &dp));
+        a.bounds_in = d;
+      }
       vwb200_dispi* dout = out; ptrdiff_t dop = opitch;
       if (!on_device || !out) { VWB_TRY(ar.alloc(&dout, (size_t)W * H)); dop = W; }
       float* dsub = out_sub; ptrdiff_t dsp = sub_pitch * 3;
       if (out_sub && !on_device) { VWB_TRY(ar.alloc(&dsub, (size_t)W * H * 3)); dsp = (ptrdiff_t)W * 3; }
-      unsigned char* ws;
-      VWB_TRY(ar.alloc(&ws, sgm_workspace_bytes(lw, lh, rw, rh, search_x, search_y, kernel_size)));
-      VWB_TRY(sgm_launch(ImgF{dl, lw, lh, dlp}, ImgF{dr, rw, rh, drp}, search_x, search_y, kernel_size, p1, p2, dout, dop, ws, st,
-                         subpixel_mode, out_sub ? dsub : nullptr, dsp));
+      int32_t* dbo = bounds_out;
+      if (bounds_out && !on_device) VWB_TRY(ar.alloc(&dbo, (size_t)W * H * 4));
+      a.out = dout; a.opitch = dop; a.out_sub = out_sub ? dsub : nullptr; a.sub_pitch = dsp; a.bounds_out = dbo;
+      VWB_TRY(sgm_run(a, ar, st));
       if (!on_device && out)
         VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch * sizeof(vwb200_dispi), dout, (size_t)W * sizeof(vwb200_dispi),
                                    (size_t)W * sizeof(vwb200_dispi), H, cudaMemcpyDeviceToHost, st));
       if (!on_device && out_sub)
         VWB_CUDA(cudaMemcpy2DAsync(out_sub, (size_t)sub_pitch * 12, dsub, (size_t)W * 12, (size_t)W * 12, H, cudaMemcpyDeviceToHost, st));
+      if (!on_device && bounds_out)
+        VWB_CUDA(cudaMemcpyAsync(bounds_out, dbo, (size_t)W * H * 16, cudaMemcpyDeviceToHost, st));
     }
     VWB_CUDA(cudaStreamSynchronize(st));
   }
   return VWB200_OK;
 }
 
+static vwb200_sgm_params sgm_default_params(int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode) {
+  vwb200_sgm_params sp{};
+  sp.search_x = search_x; sp.search_y = search_y; sp.kernel_size = kernel_size; sp.cost_type = VWB200_CENSUS_TRANSFORM; sp.ternary_threshold = 5;
+  sp.p1 = p1; sp.p2 = p2; sp.use_mgm = 0; sp.subpixel_mode = subpixel_mode; sp.search_buffer_x = 2; sp.search_buffer_y = 2; sp.conserve_level = -1;
+  sp.memory_limit_mb = 1e12; sp.assumed_threads = 4;
+  return sp;
+}
 int vwb200_sgm_calc_disparity(const float* left, int lw, int lh, ptrdiff_t lpitch, const float* right, int rw, int rh, ptrdiff_t rpitch,
                               int search_x, int search_y, int kernel_size, int p1, int p2, vwb200_dispi* out, ptrdiff_t opitch,
                               int* out_w, int* out_h, int on_device, void* stream) {
-  return sgm_run(left, lw, lh, lpitch, right, rw, rh, rpitch, search_x, search_y, kernel_size, p1, p2, 0, out, opitch, nullptr, 0, false,
-                 out_w, out_h, on_device, stream);
+  const vwb200_sgm_params sp = sgm_default_params(search_x, search_y, kernel_size, p1, p2, 0);
+  return sgm_abi_run(&sp, left, lw, lh, lpitch, right, rw, rh, rpitch, nullptr, 0, nullptr, 0, 0, 0, nullptr, 0, 0, 0, nullptr, out, opitch, nullptr, 0,
+                     nullptr, out_w, out_h, on_device, stream);
 }
 int vwb200_sgm_calc_disparity_subpixel(const float* left, int lw, int lh, ptrdiff_t lpitch, const float* right, int rw, int rh, ptrdiff_t rpitch,
                                        int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode,
                                        vwb200_dispi* out, ptrdiff_t opitch, float* out_sub, ptrdiff_t sub_pitch,
                                        int* out_w, int* out_h, int on_device, void* stream) {
-  return sgm_run(left, lw, lh, lpitch, right, rw, rh, rpitch, search_x, search_y, kernel_size, p1, p2, subpixel_mode, out, opitch, out_sub,
-                 sub_pitch, true, out_w, out_h, on_device, stream);
+  if (subpixel_mode < 0 || subpixel_mode > 5) { set_error("sgm: unknown sub-pixel mode %d", subpixel_mode); return VWB200_EARG; }
+  const vwb200_sgm_params sp = sgm_default_params(search_x, search_y, kernel_size, p1, p2, subpixel_mode);
+  return sgm_abi_run(&sp, left, lw, lh, lpitch, right, rw, rh, rpitch, nullptr, 0, nullptr, 0, 0, 0, nullptr, 0, 0, 0, nullptr, out, opitch, out_sub,
+                     sub_pitch, nullptr, out_w, out_h, on_device, stream);
+}
+int vwb200_sgm_calc_disparity_ex(const vwb200_sgm_params* params, const float* left, int lw, int lh, ptrdiff_t lpitch,
+                                 const float* right, int rw, int rh, ptrdiff_t rpitch,
+                                 const uint8_t* lmask, ptrdiff_t lmpitch, const uint8_t* rmask, int rmw, int rmh, ptrdiff_t rmpitch,
+                                 const vwb200_dispi* prev, int pw, int ph, ptrdiff_t ppitch, const int32_t* bounds,
+                                 vwb200_dispi* out, ptrdiff_t opitch, float* out_sub, ptrdiff_t sub_pitch, int32_t* bounds_out,
+                                 int* out_w, int* out_h, int on_device, void* stream) {
+  return sgm_abi_run(params, left, lw, lh, lpitch, right, rw, rh, rpitch, lmask, lmpitch, rmask, rmw, rmh, rmpitch, prev, pw, ph, ppitch, bounds, out,
+                     opitch, out_sub, sub_pitch, bounds_out, out_w, out_h, on_device, stream);
+}
+int vwb200_sgm_disp_bounds(const vwb200_sgm_params* sp, const vwb200_dispi* prev, int pw, int ph, ptrdiff_t ppitch,
+                           const uint8_t* lmask, ptrdiff_t lmpitch, const uint8_t* rmask, int rmw, int rmh, ptrdiff_t rmpitch,
+                           int ow, int oh, int32_t* bounds, int on_device, void* stream) {
+  if (!sp || !bounds || ow <= 0 || oh <= 0 || sp->search_x < 0 || sp->search_y < 0) { set_error("sgm_disp_bounds: bad arguments"); return VWB200_EARG; }
+  VWB_TRY(ensure_device());
+  StreamGuard sg; VWB_TRY(sg.init(stream, on_device));
+  cudaStream_t st = sg.st;
+  {
+    Arena ar(st);
+    SgmArgs a;
+    a.sx = sp->search_x; a.sy = sp->search_y; a.buf_x = sp->search_buffer_x; a.buf_y = sp->search_buffer_y; a.conserve_level = sp->conserve_level;
+    a.use_mgm = sp->use_mgm; a.memory_limit_mb = sp->memory_limit_mb > 0 ? sp->memory_limit_mb : 6000.0;
+    a.assumed_threads = sp->assumed_threads > 0 ? sp->assumed_threads : 4;
+    if (lmask) { const uint8_t* d; ptrdiff_t dp; VWB_TRY(stage_in(lmask, ow, oh, lmpitch, on_device, ar, st, &d, &dp)); a.lmask = ImgB{d, ow, oh, dp}; }
+    if (rmask) { const uint8_t* d; ptrdiff_t dp; VWB_TRY(stage_in(rmask, rmw, rmh, rmpitch, on_device, ar, st, &d, &dp)); a.rmask = ImgB{d, rmw, rmh, dp}; }
+    if (prev) { const vwb200_dispi* d; ptrdiff_t dp; VWB_TRY(stage_in(prev, pw, ph, ppitch, on_device, ar, st, &d, &dp)); a.prev = d; a.pw = pw; a.ph = ph; a.ppitch = dp; }
+    int32_t* db = bounds;
+    if (!on_device) VWB_TRY(ar.alloc(&db, (size_t)ow * oh * 4));
+    VWB_TRY(sgm_bounds_run(a, ow, oh, db, ar, st));
+    if (!on_device) VWB_CUDA(cudaMemcpyAsync(bounds, db, (size_t)ow * oh * 16, cudaMemcpyDeviceToHost, st));
+    VWB_CUDA(cudaStreamSynchronize(st));
+  }
+  return VWB200_OK;
 }
 
 int vwb200_parabola_subpixel(const float* disparity, int cols, int rows, const float* left, ptrdiff_t lpitch,
@@ -802,7 +873,7 @@ int vwb200_parabola_subpixel(const float* disparity, int cols, int rows, const f
   if (x1 <= x0 || y1 <= y0 || x0 < 0 || y0 < 0 || x1 > cols || y1 > rows) { set_error("parabola_subpixel: bbox outside the disparity image"); return VWB200_EARG; }
   if (kx % 2 != 1 || ky % 2 != 1 || kx < 1 || ky < 1) { set_error("parabola_subpixel: kernel size must be odd"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
-  StreamGuard sg; VWB_TRY(sg.init(stream));
+  StreamGuard sg; VWB_TRY(sg.init(stream, on_device));
   cudaStream_t st = sg.st;
   {
     Arena ar(st);
@@ -839,7 +910,7 @@ int vwb200_parabola_subpixel(const float* disparity, int cols, int rows, const f
 int vwb200_subsample_mask_by_two(const uint8_t* in, int w, int h, ptrdiff_t pitch, uint8_t* out, ptrdiff_t opitch, int on_device, void* stream) {
   if (!in || !out || w <= 0 || h <= 0) { set_error("subsample_mask_by_two: bad arguments"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
-  StreamGuard sg; VWB_TRY(sg.init(stream));
+  StreamGuard sg; VWB_TRY(sg.init(stream, on_device));
   cudaStream_t st = sg.st;
   {
     Arena ar(st);
@@ -860,7 +931,7 @@ int vwb200_cross_corr_consistency_check(vwb200_dispi* l2r, int lw, int lh, ptrdi
                                         ptrdiff_t rpitch, float threshold, int on_device, void* stream) {
   if (!l2r || !r2l) { set_error("cross_corr_consistency_check: null pointer"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
-  StreamGuard sg; VWB_TRY(sg.init(stream));
+  StreamGuard sg; VWB_TRY(sg.init(stream, on_device));
   cudaStream_t st = sg.st;
   {
     Arena ar(st);
@@ -883,7 +954,7 @@ static int filter_common(int which, const vwb200_dispi* in, int w, int h, int hx
                          const uint8_t* lm, const uint8_t* rm, int rmw, int rmh, vwb200_dispi* out, int on_device, void* stream) {
   if (!in || !out || w <= 0 || h <= 0) { set_error("disparity filter: bad arguments"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
-  StreamGuard sg; VWB_TRY(sg.init(stream));
+  StreamGuard sg; VWB_TRY(sg.init(stream, on_device));
   cudaStream_t st = sg.st;
   {
     Arena ar(st);
@@ -977,7 +1048,7 @@ int vwb200_corr_rasterize(vwb200_corr* h, int x0, int y0, int x1, int y1, float*
   if (x1 <= x0 || y1 <= y0) { set_error("corr_rasterize: empty bbox"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
   VWB_CUDA(cudaSetDevice(h->device));
-  StreamGuard sg; VWB_TRY(sg.init(stream));
+  StreamGuard sg; VWB_TRY(sg.init(stream, (h->owned ? dest_on_device : 1)));
   cudaStream_t st = sg.st;
   {
     Arena ar(st);

@@ -1,26 +1,21 @@
-// k5_sgm.cu -- SemiGlobalMatcher core on the device (first cut).
+// k5_sgm.cu -- SemiGlobalMatcher on the device: everything but the path accumulation.
 //
-// vw::stereo::calc_disparity_sgm (Stereo/SGM.cc:167-230) -> SemiGlobalMatcher::semi_global_matching_func (:2387-2448) for
-// CENSUS_TRANSFORM costs (kernel 3/5/7/9), plain SGM (not MGM), the same search box [0, sx] x [0, sy] for every pixel (no
-// masks, no previous disparity), integer winner (create_disparity_view, :1290-1346).  Everything is integer / bit
-// arithmetic except u8_convert's stretch and the tie smoothing of select_best_disparity, which use the reference's double
-// operations one by one; results are bit-identical to oracle/vw_sgm_oracle.c.
-//
-// Data in HBM: census signatures (8 B / pixel / image), cost volume cost[pixel][d] (uint8), accumulated costs
-// accum[pixel][d] (uint16), one more uint16 volume as the scratch of the tie smoothing.  d = dy * (sx + 1) + dx.
-//   sgm_u8_kernel       HBM bound   4 B read + 1 B written per pixel
-//   sgm_census_kernel   HBM bound   k*k L1/L2 reads, 8 B written per pixel
-//   sgm_cost_kernel     HBM bound   1 B written per (pixel, d); signatures come from L2
-//   sgm_path_kernel     latency bound: one CTA per scan line, threads = disparities, sequential along the line
-//                       (:1014-1141 evaluate_path, SSE flavour: unsigned 16-bit min, saturating add / subtract);
-//                       per (pixel, d, direction): 1 B + 2 B read, 2 B written = 40 B over the 8 directions
-//   sgm_wta_kernel      HBM bound   2 B read per (pixel, d); tie smoothing (:1196-1288) only for pixels with ties
-#include "common.cuh"
+// vw::stereo::calc_disparity_sgm (Stereo/SGM.cc:167-230) -> SemiGlobalMatcher::semi_global_matching_func (:2387-2448):
+//   u8_convert                       sgm_u8_kernel            HBM bound, 4 B read + 1 B written per pixel
+//   census / ternary census          sgm_census_kernel        k*k L1 reads, 8 B written per pixel (Image/CensusTransform.h)
+//   populate_disp_bound_image        sgm_rmask_*_kernel, sgm_populate_bounds_kernel   (:241-455)  per-pixel search boxes from
+//   constrain_disp_bound_image       sgm_hull_rows_kernel, sgm_hull_cols_kernel       (:502-668)  masks + previous disparity
+//   calc_main_buf_size               sgm_count_kernel, sgm_scan_blocks_kernel, sgm_meta_kernel (:677-731) exclusive scan
+//   get_hamming_distance_costs       sgm_cost_kernel          1 B written per (pixel, d), ragged (:39-73)
+//   accum_sgm / accum_mgm            k5_sgm_paths.cu
+//   create_disparity_view[_subpixel] sgm_wta_kernel           2 B read per (pixel, d) (:1159-1346, 1402-1614)
+// Everything is integer / bit arithmetic except u8_convert's stretch, the tie smoothing of select_best_disparity and
+// the sub-pixel models, which use the reference's double operations one by one.
+#include "k5_sgm.cuh"
+#include <cmath>
+#include <mutex>
 
 namespace vwb200 {
-
-typedef uint8_t cost_t;
-typedef uint16_t accum_t;
 
 // ---- vw::u8_convert (Image/ImageThresh.h:274-286, Image/Algorithms.h:106-126) --------------------------------------
 __global__ void sgm_u8_kernel(ImgF img, const float* __restrict__ stats /* min, max */, uint8_t* __restrict__ out) {
@@ -37,189 +32,284 @@ __global__ void sgm_u8_kernel(ImgF img, const float* __restrict__ stats /* min, 
   out[(size_t)y * img.w + x] = (uint8_t)n;
 }
 
-// ---- census signatures (Image/CensusTransform.h:64-160) ---------------------------------------------------------------
+// ---- census signatures (Image/CensusTransform.h:64-160 binary, :167-340 ternary) ---------------------------------------
 __constant__ int c_c9_cols[32] = {0, 4, 8, 1, 3, 5, 7, 2, 4, 6, 1, 4, 7, 0, 2, 3, 5, 6, 8, 1, 4, 7, 2, 4, 6, 1, 3, 5, 7, 0, 4, 8};
 __constant__ int c_c9_rows[32] = {0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8};
+__constant__ int c_t7_cols[32] = {0, 2, 3, 4, 6, 1, 3, 5, 0, 2, 3, 4, 6, 0, 1, 2, 4, 5, 6, 0, 2, 3, 4, 6, 1, 3, 5, 0, 2, 3, 4, 6};
+__constant__ int c_t7_rows[32] = {0, 0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 6, 6, 6, 6, 6};
 
-__global__ void sgm_census_kernel(const uint8_t* __restrict__ img, int w, int h, int k, unsigned long long* __restrict__ out) {
+// ternary: 2 bits per neighbour: 00 below centre - t, 01 inside the band, 11 above centre + t.  The reference stores the
+// signatures in the integer type the binary census of the same kernel needs: the 48-bit ternary 5x5 signature is truncated
+// to 32 bits (SGM.cc:1789-1803, ImageView<uint32>) -- kept.
+__global__ void sgm_census_kernel(const uint8_t* __restrict__ img, int w, int h, int k, int ternary, int thr,
+                                  unsigned long long* __restrict__ out) {
   const int hk = (k - 1) / 2, cw = w - 2 * hk, ch = h - 2 * hk;
   const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
   if (c >= cw || r >= ch) return;
   const int col = c + hk, row = r + hk;
   const int center = img[(size_t)row * w + col];
-  unsigned long long sig = 0, addend = 1;
-  if (k == 9) {
-    for (int i = 0; i < 32; ++i) {
-      if ((int)img[(size_t)(row + c_c9_rows[i] - 4) * w + (col + c_c9_cols[i] - 4)] > center) sig += addend;
-      addend *= 2;
-    }
-  } else {
-    for (int rr = row + hk; rr >= row - hk; --rr)
-      for (int cc = col + hk; cc >= col - hk; --cc) {
-        if (rr == row && cc == col) continue;
-        if ((int)img[(size_t)rr * w + cc] > center) sig += addend;
+  unsigned long long sig = 0;
+  if (!ternary) {
+    unsigned long long addend = 1;
+    if (k == 9) {
+      for (int i = 0; i < 32; ++i) {
+        if ((int)img[(size_t)(row + c_c9_rows[i] - 4) * w + (col + c_c9_cols[i] - 4)] > center) sig += addend;
         addend *= 2;
       }
+    } else {
+      for (int rr = row + hk; rr >= row - hk; --rr)
+        for (int cc = col + hk; cc >= col - hk; --cc) {
+          if (rr == row && cc == col) continue;
+          if ((int)img[(size_t)rr * w + cc] > center) sig += addend;
+          addend *= 2;
+        }
+    }
+  } else {
+    const int lo = center - thr, hi = center + thr;
+    int shift = 0;
+    auto code = [&](int val) {
+      if (val >= lo) sig += (val > hi ? 3ull : 1ull) << shift;
+      shift += 2;
+    };
+    if (k == 9 || k == 7) {
+      const int* cs = k == 9 ? c_c9_cols : c_t7_cols;
+      const int* rs = k == 9 ? c_c9_rows : c_t7_rows;
+      for (int i = 0; i < 32; ++i) code((int)img[(size_t)(row + rs[i] - hk) * w + (col + cs[i] - hk)]);
+    } else {
+      for (int rr = row + hk; rr >= row - hk; --rr)
+        for (int cc = col + hk; cc >= col - hk; --cc) {
+          if (rr == row && cc == col) continue;
+          if (shift < 64) code((int)img[(size_t)rr * w + cc]);
+        }
+      if (k == 5) sig &= 0xFFFFFFFFull;
+    }
   }
   out[(size_t)r * cw + c] = sig;
 }
 
-struct SgmGeom {
-  int ndx, ndy, nd;            // disparities dx in [0, ndx), dy in [0, ndy)
-  int p1, p2;
-  int ow, oh, min_col, min_row;
-  int lw, clw, crw, hk;        // left width, census widths, half kernel
+// ---- populate_disp_bound_image (SGM.cc:241-455) --------------------------------------------------------------------
+// extents of the valid right-mask pixels: ext[0] = min_valid_right_row (init rmh - 1), ext[1] = max_valid_right_row (init 0);
+// only the first ow columns are looked at and row 0 never counts as a maximum (:303-331, loops kept as they are)
+__global__ void sgm_rmask_cols_kernel(ImgB rm, int ow, int* __restrict__ ext) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ow) return;
+  for (int i = rm.h - 1; i > 0; --i)
+    if (rm.p[(ptrdiff_t)i * rm.pitch + c] > 0) { atomicMax(&ext[1], i); break; }
+  for (int i = 0; i < rm.h; ++i)
+    if (rm.p[(ptrdiff_t)i * rm.pitch + c] > 0) { atomicMin(&ext[0], i); break; }
+}
+// per output row: {min_valid_right_column, max_valid_right_column} = {-1, -2} when the row has no valid pixel right of
+// column 0 (:343-359); one warp per row
+__global__ void sgm_rmask_rows_kernel(ImgB rm, int oh, int2* __restrict__ rowext) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= oh) return;
+  const uint8_t* row = rm.p + (ptrdiff_t)r * rm.pitch;
+  int max_vc = -2, min_vc = -1;
+  for (int base = rm.w - 1; base > 0; base -= 32) {
+    const int i = base - lane;
+    const unsigned b = __ballot_sync(0xffffffffu, i > 0 && row[i] > 0);
+    if (b) { max_vc = base - (__ffs(b) - 1); break; }
+  }
+  if (max_vc > 0)
+    for (int base = 0; base < rm.w; base += 32) {
+      const int i = base + lane;
+      const unsigned b = __ballot_sync(0xffffffffu, i < rm.w && row[i] > 0);
+      if (b) { min_vc = base + (__ffs(b) - 1); break; }
+    }
+  if (lane == 0) rowext[r] = make_int2(min_vc, max_vc);
+}
+
+struct BoundsArgs {
+  int ow, oh, sx, sy, buf_x, buf_y;
+  const vwb200_dispi* prev; int pw, ph; ptrdiff_t ppitch;
+  ImgB lmask, rmask;
+  const int* ext; const int2* rowext;
 };
-
-// ---- Hamming costs (get_hamming_distance_costs, SGM.cc:39-73) ---------------------------------------------------------
-__global__ void sgm_cost_kernel(const unsigned long long* __restrict__ lc, const unsigned long long* __restrict__ rc, SgmGeom g,
-                                cost_t* __restrict__ cost) {
-  const size_t total = (size_t)g.ow * g.oh * g.nd;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int d = (int)(i % g.nd);
-    const size_t pix = i / g.nd;
-    const int c = (int)(pix % g.ow), r = (int)(pix / g.ow);
-    const int dy = d / g.ndx, dx = d - dy * g.ndx;
-    const int br = r + g.min_row - g.hk, bc = c + g.min_col - g.hk;
-    cost[i] = (cost_t)__popcll(lc[(size_t)br * g.clw + bc] ^ rc[(size_t)(br + dy) * g.crw + (bc + dx)]);
-  }
-}
-
-// ---- one scan line per CTA (PixelPassTask, SGMAssist.h:705-815; evaluate_path SSE flavour, SGM.cc:1014-1141) -----------
-__device__ __forceinline__ accum_t sat_add16(accum_t a, accum_t b) { const unsigned s = (unsigned)a + b; return (accum_t)(s > 65535u ? 65535u : s); }
-__device__ __forceinline__ accum_t sat_sub16(accum_t a, accum_t b) { return (accum_t)(a > b ? a - b : 0); }
-
-__global__ void sgm_path_kernel(const uint8_t* __restrict__ left, const cost_t* __restrict__ cost, accum_t* __restrict__ accum,
-                                SgmGeom g, int sc, int sr) {
-  extern __shared__ unsigned short sm[];
-  accum_t* prior = sm;                  // [nd]
-  accum_t* red = sm + g.nd;             // [32] per-warp minima
-  // line -> first pixel: the pixels whose predecessor (c - sc, r - sr) lies outside the raster
-  int c, r;
-  const int line = blockIdx.x;
-  if (sr == 0) { r = line; c = sc > 0 ? 0 : g.ow - 1; }
-  else if (sc == 0) { c = line; r = sr > 0 ? 0 : g.oh - 1; }
-  else if (line < g.ow) { c = line; r = sr > 0 ? 0 : g.oh - 1; }
-  else {
-    const int j = line - g.ow;          // the remaining oh - 1 rows of the side column
-    c = sc > 0 ? 0 : g.ow - 1;
-    r = sr > 0 ? 1 + j : j;
-  }
-  const int d = threadIdx.x;
-  const bool act = d < g.nd;
-  const int dy = act ? d / g.ndx : 0, dx = act ? d - dy * g.ndx : 0;
-  // the eight adjacent disparities, clamped at the search box (populate_adjacent_disp_lookup_table, :755-800)
-  const int yl = dy - 1 < 0 ? dy : dy - 1, ym = dy + 1 > g.ndy - 1 ? dy : dy + 1;
-  const int xl = dx - 1 < 0 ? dx : dx - 1, xm = dx + 1 > g.ndx - 1 ? dx : dx + 1;
-  const int a0 = yl * g.ndx + dx, a1 = dy * g.ndx + xl, a2 = dy * g.ndx + xm, a3 = ym * g.ndx + dx;
-  const int a4 = yl * g.ndx + xl, a5 = yl * g.ndx + xm, a6 = ym * g.ndx + xl, a7 = ym * g.ndx + xm;
-  const accum_t BAD = (accum_t)(255 + g.p2);                  // get_bad_accum_val (SGM.h:240)
-  int last_val = -1;
-  accum_t cur = 0;
-  // software pipeline: the next pixel's cost / accumulated cost / grey value are requested before the current pixel is
-  // evaluated (every step is a dependent chain otherwise: ncu showed 5.5 long-scoreboard stalls per issue)
-  bool in = c >= 0 && c < g.ow && r >= 0 && r < g.oh;
-  size_t base = in ? ((size_t)r * g.ow + c) * g.nd : 0;
-  accum_t local = (in && act) ? (accum_t)cost[base + d] : (accum_t)0;
-  accum_t acc_in = (in && act) ? accum[base + d] : (accum_t)0;
-  int cur_val = in ? (int)left[(size_t)(r + g.min_row) * g.lw + (c + g.min_col)] : 0;
-  while (in) {
-    const int cn = c + sc, rn = r + sr;
-    const bool in_n = cn >= 0 && cn < g.ow && rn >= 0 && rn < g.oh;
-    const size_t base_n = in_n ? ((size_t)rn * g.ow + cn) * g.nd : 0;
-    const accum_t local_n = (in_n && act) ? (accum_t)cost[base_n + d] : (accum_t)0;
-    const accum_t acc_n = (in_n && act) ? accum[base_n + d] : (accum_t)0;
-    const int val_n = in_n ? (int)left[(size_t)(rn + g.min_row) * g.lw + (cn + g.min_col)] : 0;
-    if (last_val >= 0) {
-      // block minimum of the previous pixel's path costs
-      accum_t m = act ? prior[d] : (accum_t)65535;
-      unsigned mm = m;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mm = min(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = (accum_t)mm;
-      __syncthreads();
-      unsigned mp = BAD;
-      for (int wdx = 0; wdx < (int)(blockDim.x >> 5); ++wdx) mp = min(mp, (unsigned)red[wdx]);
-      const accum_t min_prior = (accum_t)mp;
-      const int diff = abs(cur_val - last_val);
-      accum_t p2_mod = (accum_t)g.p2;
-      if (diff > 0) p2_mod = (accum_t)(p2_mod / diff);
-      if (p2_mod < g.p1) p2_mod = (accum_t)g.p1;
-      const accum_t dJ = (accum_t)(min_prior + p2_mod);
-      if (act) {
-        unsigned adj = min(min(min((unsigned)prior[a0], (unsigned)prior[a1]), min((unsigned)prior[a2], (unsigned)prior[a3])),
-                           min(min((unsigned)prior[a4], (unsigned)prior[a5]), min((unsigned)prior[a6], (unsigned)prior[a7])));
-        accum_t res = sat_add16((accum_t)adj, (accum_t)g.p1);
-        res = (accum_t)min((unsigned)res, min((unsigned)prior[d], (unsigned)dJ));
-        res = sat_add16(res, local);
-        cur = sat_sub16(res, min_prior);
-      }
-      __syncthreads();                    // everyone has read prior[]
+__global__ void sgm_populate_bounds_kernel(BoundsArgs a, short4* __restrict__ bounds, uint8_t* __restrict__ full, unsigned* __restrict__ nfull) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= a.ow || r >= a.oh) return;
+  const size_t pix = (size_t)r * a.ow + c;
+  const short4 ZERO = make_short4(0, 0, -1, -1);
+  uint8_t is_full = 0;
+  short4 res;
+  if (a.lmask.p && a.lmask.p[(ptrdiff_t)r * a.lmask.pitch + c] == 0) {                       // (:372-376)
+    res = ZERO;
+  } else {
+    const bool check_x_edge = a.sx + 1 >= 10, check_y_edge = a.sy + 1 >= 10;                 // (:286-289)
+    bool good = false;
+    int dxs = 0, dys = 0;
+    const int c_in = c / 2, r_in = r / 2;
+    if (a.prev && c_in < a.pw && r_in < a.ph) {                                              // (:385-403)
+      const vwb200_dispi d = a.prev[(ptrdiff_t)r_in * a.ppitch + c_in];
+      dxs = d.dx * 2; dys = d.dy * 2;
+      const bool on_edge = (check_x_edge && (dxs <= 0 || dxs >= a.sx)) || (check_y_edge && (dys <= 0 || dys >= a.sy));
+      good = d.valid != 0 && !on_edge;
+    }
+    int b0, b1, b2, b3;
+    if (good) {                                                                              // (:407-422)
+      b0 = max(dxs - a.buf_x, 0); b2 = min(dxs + a.buf_x, a.sx);
+      b1 = max(dys - a.buf_y, 0); b3 = min(dys + a.buf_y, a.sy);
     } else {
-      cur = local;                        // first pixel of the line (SGMAssist.h:756-759)
+      b0 = 0; b1 = 0; b2 = a.sx; b3 = a.sy;
+      is_full = 255;
     }
-    if (act) {
-      prior[d] = cur;
-      accum[base + d] = (accum_t)(acc_in + cur);                 // update_accum_buffer (SGMAssist.h:806-809), uint16 wrap
+    if (a.rmask.p) {                                                                         // (:431-452)
+      const int2 re = a.rowext[r];
+      const int v0 = max(re.x - c, b0), v1 = max(a.ext[0] - r, b1), v2 = min(re.y - c, b2), v3 = min(a.ext[1] - r, b3);
+      if (v0 > v2 || v1 > v3) { res = ZERO; is_full = 0; }
+      else res = make_short4((short)v0, (short)v1, (short)v2, (short)v3);
+    } else res = make_short4((short)b0, (short)b1, (short)b2, (short)b3);
+  }
+  bounds[pix] = res;
+  full[pix] = is_full;
+  if (is_full && a.prev) atomicAdd(nfull, 1u);      // one counter: "is there anything to constrain"
+}
+
+// ---- constrain_disp_bound_image (SGM.cc:502-668): hull of the boxes of the trusted pixels within +-range -----------
+// separable: rows first (every pixel), then columns (full-search pixels only).  Sentinel = BBox2i() (empty).
+__global__ void sgm_hull_rows_kernel(const short4* __restrict__ bounds, const uint8_t* __restrict__ full, int ow, int oh, int range,
+                                     short4* __restrict__ hull) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= ow) return;
+  int x0 = 32767, y0 = 32767, x1 = -32768, y1 = -32768;
+  const int c0 = max(c - range, 0), c1 = min(c + range, ow - 1);
+  const size_t row = (size_t)r * ow;
+  for (int cs = c0; cs <= c1; ++cs) {
+    if (full[row + cs]) continue;
+    const short4 v = bounds[row + cs];
+    if (v.x == 0 && v.y == 0 && v.z == -1 && v.w == -1) continue;
+    x0 = min(x0, (int)v.x); y0 = min(y0, (int)v.y); x1 = max(x1, (int)v.z); y1 = max(y1, (int)v.w);
+    // grow(min corner) and grow(max corner): the corners are ordered, so the hull's min comes from the mins
+    x0 = min(x0, (int)v.z); y0 = min(y0, (int)v.w); x1 = max(x1, (int)v.x); y1 = max(y1, (int)v.y);
+  }
+  hull[row + c] = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
+}
+__global__ void sgm_hull_cols_kernel(const short4* __restrict__ hull, const uint8_t* __restrict__ full, int ow, int oh, int range,
+                                     int conserve, int sx, int sy, short4* __restrict__ bounds) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= ow) return;
+  const size_t pix = (size_t)r * ow + c;
+  if (!full[pix]) return;
+  int x0 = 32767, y0 = 32767, x1 = -32768, y1 = -32768;
+  const int r0 = max(r - range, 0), r1 = min(r + range, oh - 1);
+  for (int rs = r0; rs <= r1; ++rs) {
+    const short4 v = hull[(size_t)rs * ow + c];
+    x0 = min(x0, (int)v.x); y0 = min(y0, (int)v.y); x1 = max(x1, (int)v.z); y1 = max(y1, (int)v.w);
+  }
+  if (x0 >= x1 || y0 >= y1) {                        // BBox2i::empty(): no estimate (also when all corners coincide in an axis)
+    if (conserve > 0) bounds[pix] = make_short4(0, 0, -1, -1);
+    return;
+  }
+  x0 = max(x0 - 2, 0); y0 = max(y0 - 2, 0); x1 = min(x1 + 2, sx); y1 = min(y1 + 2, sy);     // expand(2), crop(max range)
+  bounds[pix] = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
+}
+
+__global__ void sgm_bounds_from_ints_kernel(const int* __restrict__ in, size_t npix, int sx, int sy, short4* __restrict__ out, int* __restrict__ bad) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const int b0 = in[4 * i], b1 = in[4 * i + 1], b2 = in[4 * i + 2], b3 = in[4 * i + 3];
+  if (sgm_box_n(b0, b1, b2, b3) == 0) { out[i] = make_short4(0, 0, -1, -1); return; }
+  if (b0 < 0 || b1 < 0 || b2 > sx || b3 > sy) { *bad = 1; out[i] = make_short4(0, 0, -1, -1); return; }
+  out[i] = make_short4((short)b0, (short)b1, (short)b2, (short)b3);
+}
+__global__ void sgm_bounds_to_ints_kernel(const short4* __restrict__ in, size_t npix, int* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const short4 v = in[i];
+  out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+}
+__global__ void sgm_fill_bounds_kernel(short4* __restrict__ b, size_t npix, short4 v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npix) b[i] = v;
+}
+
+// ---- calc_main_buf_size (SGM.cc:677-731): exclusive scan of the box areas -> meta records ---------------------------
+static constexpr int SCAN_BLOCK = 1024;      // pixels per block (256 threads x 4)
+__device__ __forceinline__ unsigned box_n4(short4 v) { return (unsigned)sgm_box_n(v.x, v.y, v.z, v.w); }
+
+__global__ void __launch_bounds__(256) sgm_count_kernel(const short4* __restrict__ bounds, size_t npix, unsigned long long* __restrict__ block_sums) {
+  __shared__ unsigned long long red[8];
+  const size_t base = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+  unsigned long long s = 0;
+  for (int i = 0; i < 4; ++i) if (base + i < npix) s += box_n4(bounds[base + i]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned long long t = 0; for (int i = 0; i < 8; ++i) t += red[i]; block_sums[blockIdx.x] = t; }
+}
+// one CTA: exclusive scan of the block sums in place; totals[0] = total
+__global__ void __launch_bounds__(1024) sgm_scan_blocks_kernel(unsigned long long* __restrict__ block_sums, int nblocks, unsigned long long* __restrict__ totals) {
+  __shared__ unsigned long long part[1024];
+  const int per = (nblocks + 1023) / 1024, b0 = threadIdx.x * per, b1 = min(b0 + per, nblocks);
+  unsigned long long s = 0;
+  for (int i = b0; i < b1; ++i) s += block_sums[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned long long run = 0; for (int i = 0; i < 1024; ++i) { const unsigned long long t = part[i]; part[i] = run; run += t; } totals[0] = run; }
+  __syncthreads();
+  unsigned long long run = part[threadIdx.x];
+  for (int i = b0; i < b1; ++i) { const unsigned long long t = block_sums[i]; block_sums[i] = run; run += t; }
+}
+__global__ void __launch_bounds__(256) sgm_meta_kernel(const short4* __restrict__ bounds, size_t npix, const unsigned long long* __restrict__ block_offs,
+                                                       const uint8_t* __restrict__ left8, SgmGeom g, SgmMeta* __restrict__ meta,
+                                                       unsigned* __restrict__ max_n) {
+  __shared__ unsigned wsum[8];
+  const size_t base = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+  short4 v[4]; unsigned n[4], s = 0;
+  for (int i = 0; i < 4; ++i) {
+    v[i] = base + i < npix ? bounds[base + i] : make_short4(0, 0, -1, -1);
+    n[i] = base + i < npix ? box_n4(v[i]) : 0u;
+    s += n[i];
+  }
+  unsigned incl = s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  unsigned woff = 0;
+  for (int i = 0; i < wid; ++i) woff += wsum[i];
+  unsigned long long run = block_offs[blockIdx.x] + woff + (incl - s);
+  unsigned mx = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (base + i < npix) {
+      const size_t pix = base + i;
+      const int c = (int)(pix % g.ow), r = (int)(pix / g.ow);
+      SgmMeta m;
+      m.b0 = v[i].x; m.b1 = v[i].y; m.b2 = v[i].z; m.b3 = v[i].w;
+      m.start = (unsigned)run;
+      m.val_n = (unsigned)left8[(size_t)(r + g.min_row) * g.lw + (c + g.min_col)] | (n[i] << 8);
+      meta[pix] = m;
+      mx = max(mx, n[i]);
     }
-    __syncthreads();
-    last_val = cur_val;
-    c = cn; r = rn; in = in_n; base = base_n; local = local_n; acc_in = acc_n; cur_val = val_n;
+    run += n[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0 && mx) atomicMax(max_n, mx);
+}
+
+// ---- Hamming costs (get_hamming_distance_costs, SGM.cc:39-73): one warp per pixel, lanes = the pixel's disparities -------
+__global__ void __launch_bounds__(256) sgm_cost_kernel(const unsigned long long* __restrict__ lc, const unsigned long long* __restrict__ rc,
+                                                       const SgmMeta* __restrict__ meta, SgmGeom g, sgm_cost_t* __restrict__ cost) {
+  const int lane = threadIdx.x & 31;
+  const size_t npix = (size_t)g.ow * g.oh;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += nwarps) {
+    const uint4 mq = __ldg(reinterpret_cast<const uint4*>(meta) + pix);
+    const int b0 = (short)(mq.x & 0xffff), b1 = (short)(mq.x >> 16), b2 = (short)(mq.y & 0xffff);
+    const unsigned n = mq.w >> 8;
+    if (!n) continue;
+    const int w = b2 - b0 + 1;
+    const int c = (int)(pix % g.ow), r = (int)(pix / g.ow);
+    const int br = r + g.min_row - g.hk, bc = c + g.min_col - g.hk;
+    const unsigned long long l = lc[(size_t)br * g.clw + bc];
+    for (unsigned e = lane; e < n; e += 32) {
+      const int y = (int)e / w, x = (int)e - y * w;
+      cost[(size_t)mq.z + e] = (sgm_cost_t)__popcll(l ^ rc[(size_t)(br + b1 + y) * g.crw + (bc + b0 + x)]);
+    }
   }
 }
 
-// ---- create_disparity_view / select_best_disparity (SGM.cc:1159-1346) --------------------------------------------------
-__global__ void sgm_wta_kernel(accum_t* __restrict__ accum, accum_t* __restrict__ scratch, SgmGeom g, vwb200_dispi* __restrict__ out,
-                               ptrdiff_t opitch) {
-  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= (size_t)g.ow * g.oh) return;
-  accum_t* accum_vec = accum + pix * g.nd;
-  accum_t* buffer = scratch + pix * g.nd;
-  const int width = g.ndx, height = g.ndy, num = g.nd;
-  int min_count = 0, min_index = 0;
-  unsigned min_val = 65535;
-  for (int i = 0; i < num; ++i) {
-    const unsigned v = accum_vec[i];
-    buffer[i] = (accum_t)v;
-    if (v == min_val) ++min_count;
-    if (v < min_val) { min_index = i; min_val = v; min_count = 1; }
-  }
-  accum_t* input_array = accum_vec;
-  accum_t* output_array = buffer;
-  const double third = 1.0 / 3.0;
-  int iter_count = 0, index = 0;
-  while (min_count > 1) {
-    accum_t* sw = input_array; input_array = output_array; output_array = sw;
-    index = 0; min_count = 0; min_val = 65535; min_index = 0;
-    for (int row = 0; row < height; ++row)
-      for (int col = 0; col < width; ++col) {
-        int mn = -1, mx = 1;
-        double result = 0.0, weight_total = 0.0;
-        if (iter_count < 5) {
-          if (mn + col < 0) mn = 0;
-          if (mx + col >= width) mx = 0;
-          for (int k = mn; k <= mx; ++k) { result = __dadd_rn(result, __dmul_rn((double)input_array[index + k], third)); weight_total = __dadd_rn(weight_total, third); }
-        } else {
-          if (mn + row < 0) mn = 0;
-          if (mx + row >= height) mx = 0;
-          for (int k = mn; k <= mx; ++k) { result = __dadd_rn(result, __dmul_rn((double)input_array[index + k * width], third)); weight_total = __dadd_rn(weight_total, third); }
-        }
-        const unsigned v = (unsigned)(accum_t)round(__ddiv_rn(result, weight_total));
-        if (v == min_val) ++min_count;
-        if (v < min_val) { min_index = index; min_val = v; min_count = 1; }
-        output_array[index] = (accum_t)v;
-        ++index;
-      }
-    if (++iter_count >= 6) break;
-  }
-  if (iter_count > 0 && iter_count % 2 == 0)
-    for (int i = 0; i < index; ++i) input_array[i] = output_array[i];
-  vwb200_dispi o;
-  o.dy = min_index / width; o.dx = min_index - o.dy * width; o.valid = 1;        // disp_index_to_xy (:2737-2745)
-  out[(ptrdiff_t)(pix / g.ow) * opitch + (pix % g.ow)] = o;
-}
-
-// ---- create_disparity_view_subpixel (SGM.cc:1402-1480, 1497-1614): the 1-D models -----------------------------------
+// ---- create_disparity_view / select_best_disparity (SGM.cc:1159-1346) + create_disparity_view_subpixel (:1402-1614) ----
 __device__ __forceinline__ double sgm_fit(double x, int mode) {
   const double PI = 3.14159265359;
   const double lin = __ddiv_rn(x, 2.0);
@@ -241,31 +331,127 @@ __device__ __forceinline__ double sgm_subpixel_offset(int prev, int center, int 
   if (ld < rd) { x = __ddiv_rn(ld, rd); mult = 1.0; }
   return __dmul_rn(__dsub_rn(sgm_fit(x, mode), 0.5), mult);
 }
-__global__ void sgm_subpixel_kernel(const accum_t* __restrict__ accum, const vwb200_dispi* __restrict__ disp, ptrdiff_t dpitch, SgmGeom g,
-                                    int mode, float* __restrict__ out, ptrdiff_t opitch /* floats */) {
+// ParabolaFit2d::find_peak (SGMAssist.h:99-134): the 6x9 pseudo-inverse is stored as FLOAT (Matrix<float,6,9>) and
+// multiplied with the double z vector; the raw offset passes through a Vector2f
+__constant__ float c_pinv[54];
+static const double H_PINV[54] = {
+    1.0 / 6, -1.0 / 3, 1.0 / 6, 1.0 / 6, -1.0 / 3, 1.0 / 6, 1.0 / 6, -1.0 / 3, 1.0 / 6,
+    1.0 / 6, 1.0 / 6, 1.0 / 6, -1.0 / 3, -1.0 / 3, -1.0 / 3, 1.0 / 6, 1.0 / 6, 1.0 / 6,
+    1.0 / 4, 0.0, -1.0 / 4, 0.0, 0.0, 0.0, -1.0 / 4, 0.0, 1.0 / 4,
+    -1.0 / 6, 0.0, 1.0 / 6, -1.0 / 6, 0.0, 1.0 / 6, -1.0 / 6, 0.0, 1.0 / 6,
+    -1.0 / 6, -1.0 / 6, -1.0 / 6, 0.0, 0.0, 0.0, 1.0 / 6, 1.0 / 6, 1.0 / 6,
+    -1.0 / 9, 2.0 / 9, -1.0 / 9, 2.0 / 9, 5.0 / 9, 2.0 / 9, -1.0 / 9, 2.0 / 9, -1.0 / 9};
+__device__ __forceinline__ bool sgm_parabola_peak(const double* z, double* dx, double* dy) {
+  double vals[6];
+  for (int i = 0; i < 6; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < 9; ++j) s = __dadd_rn(s, __dmul_rn((double)c_pinv[i * 9 + j], z[j]));
+    vals[i] = s;
+  }
+  const double denom = __dsub_rn(__dmul_rn(__dmul_rn(4.0, vals[0]), vals[1]), __dmul_rn(vals[2], vals[2]));
+  if (fabs(denom) < 0.01) return false;
+  const float ox = (float)__ddiv_rn(__dsub_rn(__dmul_rn(vals[2], vals[4]), __dmul_rn(__dmul_rn(2.0, vals[1]), vals[3])), denom);
+  const float oy = (float)__ddiv_rn(__dsub_rn(__dmul_rn(vals[2], vals[3]), __dmul_rn(__dmul_rn(2.0, vals[0]), vals[4])), denom);
+  const double sX = 0.34574, sY = 0.38944;
+  double x = __ddiv_rn(erf(__ddiv_rn((double)ox, __dmul_rn(sX, sqrt(2.0)))), 2.0);
+  double y = __ddiv_rn(erf(__ddiv_rn((double)oy, __dmul_rn(sY, sqrt(2.0)))), 2.0);
+  const double nrm = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+  if (nrm >= 0.5) { const double scale = __ddiv_rn(nrm, 0.5); x = __ddiv_rn(x, scale); y = __ddiv_rn(y, scale); }
+  *dx = x; *dy = y;
+  return true;
+}
+
+__global__ void __launch_bounds__(128) sgm_wta_kernel(sgm_accum_t* __restrict__ accum, sgm_accum_t* __restrict__ scratch,
+                                                      const SgmMeta* __restrict__ meta, SgmGeom g, vwb200_dispi* __restrict__ out,
+                                                      ptrdiff_t opitch, int want_sub, int mode, float* __restrict__ out_sub, ptrdiff_t sub_pitch) {
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= (size_t)g.ow * g.oh) return;
-  const int i = (int)(pix % g.ow), j = (int)(pix / g.ow);
-  const vwb200_dispi d = disp[(ptrdiff_t)j * dpitch + i];
-  float* o = out + (ptrdiff_t)j * opitch + 3 * i;
-  o[2] = 1.0f;
-  if (mode == 0) { o[0] = (float)d.dx; o[1] = (float)d.dy; return; }
-  const int width = g.ndx, min_index = d.dy * width + d.dx;
+  const int oi = (int)(pix % g.ow), oj = (int)(pix / g.ow);
+  const uint4 mq = __ldg(reinterpret_cast<const uint4*>(meta) + pix);
+  const int b0 = (short)(mq.x & 0xffff), b1 = (short)(mq.x >> 16), b2 = (short)(mq.y & 0xffff), b3 = (short)(mq.y >> 16);
+  const int num = (int)(mq.w >> 8);
+  vwb200_dispi o;
+  float* f = want_sub ? out_sub + (ptrdiff_t)oj * sub_pitch + 3 * oi : nullptr;
+  if (num == 0) {                                                       // never valid (:1317-1321)
+    o.dx = 0; o.dy = 0; o.valid = 0;
+    if (out) out[(ptrdiff_t)oj * opitch + oi] = o;
+    if (f) { f[0] = 0.0f; f[1] = 0.0f; f[2] = 0.0f; }
+    return;
+  }
+  sgm_accum_t* accum_vec = accum + mq.z;
+  sgm_accum_t* buffer = scratch + mq.z;
+  const int width = b2 - b0 + 1, height = b3 - b1 + 1;
+  int min_count = 0, min_index = 0;
+  unsigned min_val = 65535;
+  for (int i = 0; i < num; ++i) {
+    const unsigned v = accum_vec[i];
+    if (v == min_val) ++min_count;
+    if (v < min_val) { min_index = i; min_val = v; min_count = 1; }
+  }
+  if (min_count > 1) {                                                  // tie smoothing (:1196-1288), rare
+    for (int i = 0; i < num; ++i) buffer[i] = accum_vec[i];
+    sgm_accum_t* input_array = accum_vec;
+    sgm_accum_t* output_array = buffer;
+    const double third = 1.0 / 3.0;
+    int iter_count = 0, index = 0;
+    while (min_count > 1) {
+      sgm_accum_t* sw = input_array; input_array = output_array; output_array = sw;
+      index = 0; min_count = 0; min_val = 65535; min_index = 0;
+      for (int row = 0; row < height; ++row)
+        for (int col = 0; col < width; ++col) {
+          int mn = -1, mx = 1;
+          double result = 0.0, weight_total = 0.0;
+          if (iter_count < 5) {
+            if (mn + col < 0) mn = 0;
+            if (mx + col >= width) mx = 0;
+            for (int k = mn; k <= mx; ++k) { result = __dadd_rn(result, __dmul_rn((double)input_array[index + k], third)); weight_total = __dadd_rn(weight_total, third); }
+          } else {
+            if (mn + row < 0) mn = 0;
+            if (mx + row >= height) mx = 0;
+            for (int k = mn; k <= mx; ++k) { result = __dadd_rn(result, __dmul_rn((double)input_array[index + k * width], third)); weight_total = __dadd_rn(weight_total, third); }
+          }
+          const unsigned v = (unsigned)(sgm_accum_t)round(__ddiv_rn(result, weight_total));
+          if (v == min_val) ++min_count;
+          if (v < min_val) { min_index = index; min_val = v; min_count = 1; }
+          output_array[index] = (sgm_accum_t)v;
+          ++index;
+        }
+      if (++iter_count >= 6) break;
+    }
+    if (iter_count > 0 && iter_count % 2 == 0)
+      for (int i = 0; i < index; ++i) input_array[i] = output_array[i];
+  }
+  const int dyi = min_index / width;
+  const int dx = min_index - dyi * width + b0, dy = dyi + b1;          // disp_index_to_xy (:2737-2745)
+  o.dx = dx; o.dy = dy; o.valid = 1;
+  if (out) out[(ptrdiff_t)oj * opitch + oi] = o;
+  if (!f) return;
+  f[2] = 1.0f;
+  if (mode == 0) { f[0] = (float)dx; f[1] = (float)dy; return; }
   int x_left = -1, x_right = 1, y_up = -width, y_down = width;
   bool lb = false, rb = false, tb = false, bb = false;
-  if (d.dx == 0) { x_left = 0; lb = true; }
-  if (d.dx == g.ndx - 1) { x_right = 0; rb = true; }
-  if (d.dy == 0) { y_up = 0; tb = true; }
-  if (d.dy == g.ndy - 1) { y_down = 0; bb = true; }
-  const accum_t* av = accum + pix * g.nd;
-  const double ddx = sgm_subpixel_offset(av[min_index + x_left], av[min_index], av[min_index + x_right], lb, rb, mode);
-  const double ddy = sgm_subpixel_offset(av[min_index + y_up], av[min_index], av[min_index + y_down], tb, bb, mode);
-  o[0] = (float)__dadd_rn((double)d.dx, ddx);
-  o[1] = (float)__dadd_rn((double)d.dy, ddy);
+  if (dx == b0) { x_left = 0; lb = true; }
+  if (dx == b2) { x_right = 0; rb = true; }
+  if (dy == b1) { y_up = 0; tb = true; }
+  if (dy == b3) { y_down = 0; bb = true; }
+  const sgm_accum_t* av = accum_vec;
+  double ddx, ddy;
+  if (mode == 1) {                                                      // SUBPIXEL_PARABOLA (:1566-1576)
+    double z[9];
+    z[0] = av[min_index + x_left + y_up];   z[1] = av[min_index + y_up];   z[2] = av[min_index + x_right + y_up];
+    z[3] = av[min_index + x_left];          z[4] = av[min_index];          z[5] = av[min_index + x_right];
+    z[6] = av[min_index + x_left + y_down]; z[7] = av[min_index + y_down]; z[8] = av[min_index + x_right + y_down];
+    if (!sgm_parabola_peak(z, &ddx, &ddy)) { f[0] = (float)dx; f[1] = (float)dy; return; }
+  } else {
+    ddx = sgm_subpixel_offset(av[min_index + x_left], av[min_index], av[min_index + x_right], lb, rb, mode);
+    ddy = sgm_subpixel_offset(av[min_index + y_up], av[min_index], av[min_index + y_down], tb, bb, mode);
+  }
+  f[0] = (float)__dadd_rn((double)dx, ddx);
+  f[1] = (float)__dadd_rn((double)dy, ddy);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
-static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+int image_stats_launch(ImgF img, float* d_result3, cudaStream_t st);
 
 int sgm_output_size(int lw, int lh, int rw, int rh, int sx, int sy, int k, int* ow, int* oh) {
   const int hk = (k - 1) / 2;                      // semi_global_matching_func (:2397-2420) with min_disp = 0
@@ -277,74 +463,216 @@ int sgm_output_size(int lw, int lh, int rw, int rh, int sx, int sy, int k, int* 
   return VWB200_OK;
 }
 
-size_t sgm_workspace_bytes(int lw, int lh, int rw, int rh, int sx, int sy, int k) {
-  int ow, oh;
-  sgm_output_size(lw, lh, rw, rh, sx, sy, k, &ow, &oh);
-  const size_t nd = (size_t)(sx + 1) * (sy + 1), vol = (size_t)ow * oh * nd;
-  return al256((size_t)lw * lh) + al256((size_t)rw * rh) + al256((size_t)lw * lh * 8) + al256((size_t)rw * rh * 8) + al256(vol) + 2 * al256(vol * 2) +
-         al256(64) + 1024;
+// search boxes into d_b (short4 per pixel) + full-search flags; returns the number of full-search pixels with a prior
+struct BoundsState { short4* b = nullptr; uint8_t* full = nullptr; short4* hull = nullptr; unsigned nfull = 0; bool derived = false; };
+
+static int bounds_populate(const SgmArgs& a, int ow, int oh, BoundsState& bs, Arena& ar, cudaStream_t st) {
+  const size_t npix = (size_t)ow * oh;
+  VWB_TRY(ar.alloc(&bs.b, npix));
+  if (a.bounds_in) {
+    int* d_bad;
+    VWB_TRY(ar.alloc(&d_bad, 1));
+    VWB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    sgm_bounds_from_ints_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(a.bounds_in, npix, a.sx, a.sy, bs.b, d_bad);
+    VWB_LAUNCH_CHECK();
+    int bad = 0;
+    VWB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VWB_CUDA(cudaStreamSynchronize(st));
+    if (bad) { set_error("sgm: a search box lies outside [0, search]"); return VWB200_EARG; }
+    return VWB200_OK;
+  }
+  if (a.lmask.p && (a.lmask.w != ow || a.lmask.h != oh)) { set_error("Left mask size does not match the output size."); return VWB200_ELOGIC; }   // :250-256
+  if (a.rmask.p && !(a.rmask.w >= ow + a.sx && a.rmask.h >= oh + a.sy)) {
+    set_error("Right mask size is not large enough to support search range.");                                                                      // :262-268
+    return VWB200_ELOGIC;
+  }
+  bs.derived = true;
+  VWB_TRY(ar.alloc(&bs.full, npix));
+  int* d_ext = nullptr; int2* d_rowext = nullptr; unsigned* d_nfull;
+  VWB_TRY(ar.alloc(&d_nfull, 1));
+  VWB_CUDA(cudaMemsetAsync(d_nfull, 0, sizeof(unsigned), st));
+  if (a.rmask.p) {
+    VWB_TRY(ar.alloc(&d_ext, 2));
+    VWB_TRY(ar.alloc(&d_rowext, (size_t)oh));
+    const int init[2] = {a.rmask.h - 1, 0};
+    VWB_CUDA(cudaMemcpyAsync(d_ext, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    VWB_CUDA(cudaStreamSynchronize(st));
+    sgm_rmask_cols_kernel<<<(ow + 127) / 128, 128, 0, st>>>(a.rmask, ow, d_ext);
+    VWB_LAUNCH_CHECK();
+    sgm_rmask_rows_kernel<<<(oh + 7) / 8, 256, 0, st>>>(a.rmask, oh, d_rowext);
+    VWB_LAUNCH_CHECK();
+  }
+  BoundsArgs ba{ow, oh, a.sx, a.sy, a.buf_x, a.buf_y, a.prev, a.pw, a.ph, a.ppitch, a.lmask, a.rmask, d_ext, d_rowext};
+  sgm_populate_bounds_kernel<<<dim3((ow + 31) / 32, (oh + 7) / 8), dim3(32, 8), 0, st>>>(ba, bs.b, bs.full, d_nfull);
+  VWB_LAUNCH_CHECK();
+  if (a.prev) {
+    VWB_CUDA(cudaMemcpyAsync(&bs.nfull, d_nfull, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    VWB_CUDA(cudaStreamSynchronize(st));
+  }
+  return VWB200_OK;
+}
+// one pass of constrain_disp_bound_image at a conservation level.  Re-running it at a higher level on its own output is
+// what the reference's retry loop does: trusted pixels never change and every full-search pixel is rewritten (level > 0).
+static int bounds_constrain(const SgmArgs& a, int ow, int oh, int level, BoundsState& bs, Arena& ar, cudaStream_t st) {
+  if (!bs.derived || !a.prev || bs.nfull == 0) return VWB200_OK;
+  const int range = level == 1 ? 25 : (level == 2 ? 3 : (level == 3 ? 0 : 10));
+  if (!bs.hull) VWB_TRY(ar.alloc(&bs.hull, (size_t)ow * oh));
+  sgm_hull_rows_kernel<<<dim3((ow + 127) / 128, oh), 128, 0, st>>>(bs.b, bs.full, ow, oh, range, bs.hull);
+  VWB_LAUNCH_CHECK();
+  sgm_hull_cols_kernel<<<dim3((ow + 127) / 128, oh), 128, 0, st>>>(bs.hull, bs.full, ow, oh, range, level, a.sx, a.sy, bs.b);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
 }
 
-int sgm_launch(ImgF left, ImgF right, int sx, int sy, int k, int p1, int p2, vwb200_dispi* out, ptrdiff_t opitch, void* workspace,
-               cudaStream_t st, int subpixel_mode, float* out_sub, ptrdiff_t sub_pitch) {
+struct ScanState { unsigned long long* block_sums = nullptr; unsigned long long* totals = nullptr; int nblocks = 0; };
+static int bounds_total(const short4* b, size_t npix, ScanState& ss, unsigned long long* total, Arena& ar, cudaStream_t st) {
+  ss.nblocks = (int)((npix + SCAN_BLOCK - 1) / SCAN_BLOCK);
+  if (!ss.block_sums) { VWB_TRY(ar.alloc(&ss.block_sums, (size_t)ss.nblocks)); VWB_TRY(ar.alloc(&ss.totals, 2)); }
+  sgm_count_kernel<<<ss.nblocks, 256, 0, st>>>(b, npix, ss.block_sums);
+  VWB_LAUNCH_CHECK();
+  sgm_scan_blocks_kernel<<<1, 1024, 0, st>>>(ss.block_sums, ss.nblocks, ss.totals);
+  VWB_LAUNCH_CHECK();
+  VWB_CUDA(cudaMemcpyAsync(total, ss.totals, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  VWB_CUDA(cudaStreamSynchronize(st));
+  return VWB200_OK;
+}
+// calc_main_buf_size's memory check (SGM.cc:693-729)
+static bool fits_memory(const SgmArgs& a, int ow, int oh, unsigned long long main_buf) {
+  if (main_buf < 6) main_buf = 6;
+  const double nd = (double)(a.sx + 1) * (a.sy + 1);
+  double small_elems;
+  if (a.use_mgm) {
+    const double v = std::min((double)oh * nd, (double)main_buf), h = std::min((double)ow * nd, (double)main_buf);
+    small_elems = v * 4 + h * 4;
+  } else {
+    const int line = (int)(std::sqrt((double)(ow * ow + oh * oh)) + 1);       // int arithmetic of one_buf_size (SGMAssist.h:565-583)
+    small_elems = std::min((double)line * nd, (double)main_buf) * a.assumed_threads;
+  }
+  const double mb = 1024.0 * 1024.0;
+  return (double)main_buf * (3.0 / mb) + small_elems * (2.0 / mb) <= a.memory_limit_mb;
+}
+
+// derive the boxes like populate_disp_bound_image incl. its retry loop; returns total entries (or ok = false when even
+// the most conservative level does not fit)
+static int bounds_derive(const SgmArgs& a, int ow, int oh, BoundsState& bs, ScanState& ss, unsigned long long* total, bool* ok,
+                         Arena& ar, cudaStream_t st) {
+  const size_t npix = (size_t)ow * oh;
+  VWB_TRY(bounds_populate(a, ow, oh, bs, ar, st));
+  *ok = true;
+  if (!bs.derived) return bounds_total(bs.b, npix, ss, total, ar, st);
+  if (a.conserve_level >= 0) {
+    VWB_TRY(bounds_constrain(a, ow, oh, a.conserve_level, bs, ar, st));
+    return bounds_total(bs.b, npix, ss, total, ar, st);
+  }
+  for (int level = 0; level <= 3; ++level) {
+    VWB_TRY(bounds_constrain(a, ow, oh, level, bs, ar, st));
+    VWB_TRY(bounds_total(bs.b, npix, ss, total, ar, st));
+    if (fits_memory(a, ow, oh, *total)) return VWB200_OK;
+  }
+  *ok = false;
+  return VWB200_OK;
+}
+
+int sgm_bounds_run(const SgmArgs& a, int ow, int oh, int* d_bounds, Arena& ar, cudaStream_t st) {
+  if (a.sx > 32767 || a.sy > 32767) { set_error("sgm: search range exceeds 32767"); return VWB200_ENOIMPL; }
+  BoundsState bs; ScanState ss; unsigned long long total = 0; bool ok = true;
+  VWB_TRY(bounds_derive(a, ow, oh, bs, ss, &total, &ok, ar, st));
+  const size_t npix = (size_t)ow * oh;
+  sgm_bounds_to_ints_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(bs.b, npix, d_bounds);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
+int sgm_run(const SgmArgs& a, Arena& ar, cudaStream_t st) {
+  const int k = a.k;
   if (k != 3 && k != 5 && k != 7 && k != 9) {
     set_error("Census transforms are only available in size 3, 5, 7, and 9.");       // SGM.cc:1885-1888
     return VWB200_ENOIMPL;
   }
-  if (sx < 0 || sy < 0) { set_error("sgm: negative search volume"); return VWB200_EARG; }
-  const long long nd = (long long)(sx + 1) * (sy + 1);
-  if (nd > 1024) { set_error("sgm: %lld disparities per pixel exceed the 1024 this kernel handles", nd); return VWB200_ENOIMPL; }
-  if (p1 <= 0) p1 = k == 3 ? 3 : k == 5 ? 15 : k == 7 ? 30 : 20;                       // set_parameters (:112-122)
-  if (p2 <= 0) p2 = k == 3 ? 70 : k == 5 ? 750 : k == 7 ? 1500 : 1000;                 // (:141-151)
+  if (a.sx < 0 || a.sy < 0) { set_error("sgm: negative search volume"); return VWB200_EARG; }
+  if (a.sx > 32767 || a.sy > 32767) { set_error("sgm: search range exceeds 32767"); return VWB200_ENOIMPL; }
+  int p1 = a.p1, p2 = a.p2;
+  if (p1 <= 0) p1 = a.ternary ? (k == 3 ? 12 : k == 5 ? 30 : 40) : (k == 3 ? 3 : k == 5 ? 15 : k == 7 ? 30 : 20);            // set_parameters (:106-130)
+  if (p2 <= 0) p2 = a.ternary ? (k == 3 ? 600 : k == 5 ? 1500 : 2000) : (k == 3 ? 70 : k == 5 ? 750 : k == 7 ? 1500 : 1000);   // (:135-157)
   SgmGeom g;
-  g.ndx = sx + 1; g.ndy = sy + 1; g.nd = (int)nd; g.p1 = p1; g.p2 = p2;
-  g.hk = (k - 1) / 2; g.min_col = g.hk; g.min_row = g.hk; g.lw = left.w;
-  sgm_output_size(left.w, left.h, right.w, right.h, sx, sy, k, &g.ow, &g.oh);
+  g.sx = a.sx; g.sy = a.sy; g.ndx = a.sx + 1; g.ndy = a.sy + 1;
+  const long long nd = (long long)g.ndx * g.ndy;
+  if (nd > (1ll << 24) - 1) { set_error("Number of disparities is too large for data type."); return VWB200_ENOIMPL; }       // (:102-103)
+  g.nd = (int)nd; g.p1 = p1; g.p2 = p2;
+  g.hk = (k - 1) / 2; g.min_col = g.hk; g.min_row = g.hk; g.lw = a.left.w;
+  sgm_output_size(a.left.w, a.left.h, a.right.w, a.right.h, a.sx, a.sy, k, &g.ow, &g.oh);
   if (g.ow <= 0 || g.oh <= 0) return VWB200_OK;
-  g.clw = left.w - 2 * g.hk; g.crw = right.w - 2 * g.hk;
-  // carve the workspace
-  unsigned char* p = static_cast<unsigned char*>(workspace);
-  auto take = [&](size_t bytes) { unsigned char* q = p; p += al256(bytes); return q; };
-  const size_t vol = (size_t)g.ow * g.oh * g.nd;
-  uint8_t* l8 = take((size_t)left.w * left.h);
-  uint8_t* r8 = take((size_t)right.w * right.h);
-  unsigned long long* lc = (unsigned long long*)take((size_t)left.w * left.h * 8);
-  unsigned long long* rc = (unsigned long long*)take((size_t)right.w * right.h * 8);
-  cost_t* cost = take(vol);
-  accum_t* accum = (accum_t*)take(vol * 2);
-  accum_t* scratch = (accum_t*)take(vol * 2);
-  float* stats = (float*)take(64);
-  dim3 b(32, 8);
-  VWB_TRY(image_stats_launch(left, stats, st));
-  VWB_TRY(image_stats_launch(right, stats + 3, st));
-  sgm_u8_kernel<<<dim3((left.w + 31) / 32, (left.h + 7) / 8), b, 0, st>>>(left, stats, l8);
-  VWB_LAUNCH_CHECK();
-  sgm_u8_kernel<<<dim3((right.w + 31) / 32, (right.h + 7) / 8), b, 0, st>>>(right, stats + 3, r8);
-  VWB_LAUNCH_CHECK();
-  sgm_census_kernel<<<dim3((g.clw + 31) / 32, (left.h - 2 * g.hk + 7) / 8), b, 0, st>>>(l8, left.w, left.h, k, lc);
-  VWB_LAUNCH_CHECK();
-  sgm_census_kernel<<<dim3((g.crw + 31) / 32, (right.h - 2 * g.hk + 7) / 8), b, 0, st>>>(r8, right.w, right.h, k, rc);
-  VWB_LAUNCH_CHECK();
-  sgm_cost_kernel<<<148 * 8, 256, 0, st>>>(lc, rc, g, cost);
-  VWB_LAUNCH_CHECK();
-  VWB_CUDA(cudaMemsetAsync(accum, 0, vol * 2, st));
-  // the eight directions of accum_sgm_multithread (:2462-2611), one launch each (a pixel lies on one line per direction)
-  static const int DIRS[8][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
-  const int threads = ((g.nd + 31) / 32) * 32;
-  const size_t smem = (size_t)(g.nd + 32) * sizeof(accum_t);
-  for (int i = 0; i < 8; ++i) {
-    const int sc = DIRS[i][0], sr = DIRS[i][1];
-    const int lines = sr == 0 ? g.oh : (sc == 0 ? g.ow : g.ow + g.oh - 1);
-    sgm_path_kernel<<<lines, threads, smem, st>>>(l8, cost, accum, g, sc, sr);
-    VWB_LAUNCH_CHECK();
-  }
+  g.clw = a.left.w - 2 * g.hk; g.crw = a.right.w - 2 * g.hk;
   const size_t npix = (size_t)g.ow * g.oh;
-  sgm_wta_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, scratch, g, out, opitch);
+  if (p1 > p2 || p2 > 30000) {     // the kernels rely on every path cost staying <= 255 + P2 (no uint16 wrap in dJ)
+    set_error("sgm: penalties outside the supported range (need p1 <= p2 <= 30000), got p1 = %d, p2 = %d", p1, p2);
+    return VWB200_ENOIMPL;
+  }
+  {
+    static float pf[54];
+    static std::once_flag pinv_once;
+    std::call_once(pinv_once, [] { for (int i = 0; i < 54; ++i) pf[i] = (float)H_PINV[i]; });
+    VWB_CUDA(cudaMemcpyToSymbolAsync(c_pinv, pf, sizeof(pf), 0, cudaMemcpyHostToDevice, st));
+  }
+  // u8 stretch + census signatures
+  uint8_t *l8, *r8; unsigned long long *lc, *rc; float* stats;
+  VWB_TRY(ar.alloc(&l8, (size_t)a.left.w * a.left.h));
+  VWB_TRY(ar.alloc(&r8, (size_t)a.right.w * a.right.h));
+  VWB_TRY(ar.alloc(&lc, (size_t)a.left.w * a.left.h));
+  VWB_TRY(ar.alloc(&rc, (size_t)a.right.w * a.right.h));
+  VWB_TRY(ar.alloc(&stats, 8));
+  const dim3 b(32, 8);
+  VWB_TRY(image_stats_launch(a.left, stats, st));
+  VWB_TRY(image_stats_launch(a.right, stats + 3, st));
+  sgm_u8_kernel<<<dim3((a.left.w + 31) / 32, (a.left.h + 7) / 8), b, 0, st>>>(a.left, stats, l8);
   VWB_LAUNCH_CHECK();
-  if (out_sub) {
-    sgm_subpixel_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, out, opitch, g, subpixel_mode, out_sub, sub_pitch);
+  sgm_u8_kernel<<<dim3((a.right.w + 31) / 32, (a.right.h + 7) / 8), b, 0, st>>>(a.right, stats + 3, r8);
+  VWB_LAUNCH_CHECK();
+  sgm_census_kernel<<<dim3((g.clw + 31) / 32, (a.left.h - 2 * g.hk + 7) / 8), b, 0, st>>>(l8, a.left.w, a.left.h, k, a.ternary, a.ternary_threshold, lc);
+  VWB_LAUNCH_CHECK();
+  sgm_census_kernel<<<dim3((g.crw + 31) / 32, (a.right.h - 2 * g.hk + 7) / 8), b, 0, st>>>(r8, a.right.w, a.right.h, k, a.ternary, a.ternary_threshold, rc);
+  VWB_LAUNCH_CHECK();
+  // search boxes -> ragged layout
+  BoundsState bs; ScanState ss; unsigned long long total = 0; bool ok = true;
+  VWB_TRY(bounds_derive(a, g.ow, g.oh, bs, ss, &total, &ok, ar, st));
+  if (a.bounds_out) {
+    sgm_bounds_to_ints_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(bs.b, npix, a.bounds_out);
     VWB_LAUNCH_CHECK();
   }
+  auto all_invalid = [&]() -> int {                                    // (:2430-2436)
+    if (a.out) VWB_CUDA(cudaMemset2DAsync(a.out, (size_t)a.opitch * sizeof(vwb200_dispi), 0, (size_t)g.ow * sizeof(vwb200_dispi), g.oh, st));
+    if (a.out_sub) VWB_CUDA(cudaMemset2DAsync(a.out_sub, (size_t)a.sub_pitch * 4, 0, (size_t)g.ow * 12, g.oh, st));
+    return VWB200_OK;
+  };
+  if (!ok) return all_invalid();
+  if (total > 0xFFFFFFF0ull) {
+    set_error("SGM: %llu (pixel, disparity) entries exceed the 2^32 this engine indexes; reduce the search range or the tile", total);
+    return VWB200_ENOMEM;
+  }
+  if (total == 0) return all_invalid();
+  SgmMeta* meta; unsigned* d_maxn; sgm_cost_t* cost; sgm_accum_t *accum, *scratch;
+  VWB_TRY(ar.alloc(&meta, npix));
+  VWB_TRY(ar.alloc(&d_maxn, 1));
+  VWB_CUDA(cudaMemsetAsync(d_maxn, 0, sizeof(unsigned), st));
+  sgm_meta_kernel<<<ss.nblocks, 256, 0, st>>>(bs.b, npix, ss.block_sums, l8, g, meta, d_maxn);
+  VWB_LAUNCH_CHECK();
+  unsigned max_n = 0;
+  VWB_CUDA(cudaMemcpyAsync(&max_n, d_maxn, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  VWB_TRY(ar.alloc(&cost, (size_t)total + 64));
+  VWB_TRY(ar.alloc(&accum, (size_t)total + 64));
+  VWB_TRY(ar.alloc(&scratch, (size_t)total + 64));
+  sgm_cost_kernel<<<148 * 8, 256, 0, st>>>(lc, rc, meta, g, cost);
+  VWB_LAUNCH_CHECK();
+  VWB_CUDA(cudaStreamSynchronize(st));                                  // max_n
+  if (a.use_mgm) {
+    VWB_CUDA(cudaMemsetAsync(accum, 0, ((size_t)total + 64) * sizeof(sgm_accum_t), st));
+    VWB_TRY(mgm_paths_launch(meta, cost, accum, l8, g, (size_t)total, ar, st));
+  } else {
+    VWB_TRY(sgm_paths_launch(meta, cost, accum, g, max_n, ar, st));
+  }
+  sgm_wta_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, scratch, meta, g, a.out, a.opitch, a.out_sub != nullptr, a.subpixel_mode,
+                                                                 a.out_sub, a.sub_pitch);
+  VWB_LAUNCH_CHECK();
   return VWB200_OK;
 }
 

@@ -66,3 +66,36 @@ def make_rasters(W, H, search_volume, kernel, seed, bits=12):
     rw, rh = lw + sx - 1, lh + sy - 1
     left, right, _, _, _ = make_pair(rw, rh, (0, 0, sx, sy), seed, bits=bits, dropout=0)
     return np.ascontiguousarray(left[:lh, :lw]), right
+
+
+def make_sgm_case(size, search, kernel, seed=104):
+    """BASELINE config 4: the cropped left_region / right_region rasters of calc_disparity_sgm for a
+    size x size output-ish pair, 8-bit-like imagery, a smooth true disparity inside [0, search]^2, and the synthetic
+    half-resolution prior (true / 2, all valid) from which search_buffer (2, 2) gives 5 x 5 boxes.
+    Returns left (size, size), right (size + search, size + search), prev ((oh+1)//2, (ow+1)//2, 3) int32,
+    true (size, size, 2) int32 (the disparity in the left raster's coordinates)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    H = W = size
+    base = np.floor(rng.random((H + search + 2, W + search + 2), dtype=np.float32) * 256)
+    p = np.pad(base, 1, mode="edge")
+    acc = np.zeros_like(base)
+    for dy in range(3):
+        for dx in range(3):
+            acc += p[dy:dy + base.shape[0], dx:dx + base.shape[1]]
+    right = np.floor(acc / 9.0).astype(np.float32)[:H + search, :W + search]
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    # even disparities between 8 and search - 8 so that the half-resolution prior doubles back exactly
+    lo, hi = 8, max(search - 8, 10)
+    dxf = 2 * np.rint((0.5 * (lo + hi) + 0.4 * (hi - lo) * np.sin(2 * np.pi * (1.3 * xx + 0.7 * yy) / max(W, 64))) / 2).astype(np.int32)
+    dyf = 2 * np.rint((0.5 * (lo + hi) + 0.4 * (hi - lo) * np.cos(2 * np.pi * (0.9 * xx - 1.1 * yy) / max(H, 64))) / 2).astype(np.int32)
+    dxf = np.clip(dxf, 2, search - 2); dyf = np.clip(dyf, 2, search - 2)
+    left = right[np.arange(H)[:, None] + dyf, np.arange(W)[None, :] + dxf]          # left(c, r) = right(c + dx, r + dy)
+    noise = np.random.Generator(np.random.PCG64(seed + 1)).integers(-2, 3, size=left.shape).astype(np.float32)
+    left = np.clip(left + noise, 0, 255).astype(np.float32)
+    hk = (kernel - 1) // 2
+    oh, ow = H - 2 * hk, W - 2 * hk
+    prev = np.zeros(((oh + 1) // 2, (ow + 1) // 2, 3), np.int32)
+    prev[..., 0] = dxf[hk:hk + oh:2, hk:hk + ow:2] // 2
+    prev[..., 1] = dyf[hk:hk + oh:2, hk:hk + ow:2] // 2
+    prev[..., 2] = 1
+    return np.ascontiguousarray(left), np.ascontiguousarray(right), prev, np.stack([dxf, dyf], -1)
