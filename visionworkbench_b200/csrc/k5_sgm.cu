@@ -287,25 +287,49 @@ __global__ void __launch_bounds__(256) sgm_meta_kernel(const short4* __restrict_
   if (lane == 0 && mx) atomicMax(max_n, mx);
 }
 
-// ---- Hamming costs (get_hamming_distance_costs, SGM.cc:39-73): one warp per pixel, lanes = the pixel's disparities -------
+// ---- Hamming costs (get_hamming_distance_costs, SGM.cc:39-73) ---------------------------------------------------------
+// one warp per 32 consecutive pixels: lane i fetches record i (coalesced), then the warp walks the 32 pixels with
+// lanes = the pixel's disparities (coalesced byte stores into the ragged volume); 4 pixels in flight per iteration
 __global__ void __launch_bounds__(256) sgm_cost_kernel(const unsigned long long* __restrict__ lc, const unsigned long long* __restrict__ rc,
                                                        const SgmMeta* __restrict__ meta, SgmGeom g, sgm_cost_t* __restrict__ cost) {
   const int lane = threadIdx.x & 31;
   const size_t npix = (size_t)g.ow * g.oh;
-  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += nwarps) {
-    const uint4 mq = __ldg(reinterpret_cast<const uint4*>(meta) + pix);
-    const int b0 = (short)(mq.x & 0xffff), b1 = (short)(mq.x >> 16), b2 = (short)(mq.y & 0xffff);
-    const unsigned n = mq.w >> 8;
-    if (!n) continue;
-    const int w = b2 - b0 + 1;
-    const int c = (int)(pix % g.ow), r = (int)(pix / g.ow);
-    const int br = r + g.min_row - g.hk, bc = c + g.min_col - g.hk;
-    const unsigned long long l = lc[(size_t)br * g.clw + bc];
-    for (unsigned e = lane; e < n; e += 32) {
-      const int y = (int)e / w, x = (int)e - y * w;
-      cost[(size_t)mq.z + e] = (sgm_cost_t)__popcll(l ^ rc[(size_t)(br + b1 + y) * g.crw + (bc + b0 + x)]);
+  const size_t p0 = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  if (p0 >= npix) return;
+  const size_t mine = p0 + lane;
+  uint4 mq = make_uint4(0xffff0000u, 0xffffu, 0u, 0u);
+  unsigned long long l = 0;
+  int br = 0, bc = 0;
+  if (mine < npix) {
+    mq = __ldg(reinterpret_cast<const uint4*>(meta) + mine);
+    const int c = (int)(mine % g.ow), r = (int)(mine / g.ow);
+    br = r + g.min_row - g.hk; bc = c + g.min_col - g.hk;
+    l = lc[(size_t)br * g.clw + bc];
+  }
+  const unsigned lhi = (unsigned)(l >> 32), llo = (unsigned)l;
+  for (int j0 = 0; j0 < 32; j0 += 4) {
+    unsigned long long v[4]; size_t dst[4]; bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      const unsigned bx = __shfl_sync(0xffffffffu, mq.x, j), by = __shfl_sync(0xffffffffu, mq.y, j);
+      const unsigned st = __shfl_sync(0xffffffffu, mq.z, j), n = __shfl_sync(0xffffffffu, mq.w, j) >> 8;
+      const int pbr = __shfl_sync(0xffffffffu, br, j), pbc = __shfl_sync(0xffffffffu, bc, j);
+      const unsigned long long pl = ((unsigned long long)__shfl_sync(0xffffffffu, lhi, j) << 32) | __shfl_sync(0xffffffffu, llo, j);
+      const int b0 = (short)(bx & 0xffff), b1 = (short)(bx >> 16), b2 = (short)(by & 0xffff);
+      const int w = max(b2 - b0 + 1, 1);
+      ok[u] = (unsigned)lane < n;
+      const int y = lane / w, x = lane - y * w;
+      dst[u] = (size_t)st + lane;
+      v[u] = ok[u] ? (pl ^ rc[(size_t)(pbr + b1 + y) * g.crw + (pbc + b0 + x)]) : 0ull;
+      if (n > 32u)                                                     // a large box: finish it warp-strided right here
+        for (unsigned e = lane + 32; e < n; e += 32) {
+          const int yy = (int)e / w, xx = (int)e - yy * w;
+          cost[(size_t)st + e] = (sgm_cost_t)__popcll(pl ^ rc[(size_t)(pbr + b1 + yy) * g.crw + (pbc + b0 + xx)]);
+        }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (ok[u]) cost[dst[u]] = (sgm_cost_t)__popcll(v[u]);
   }
 }
 
@@ -661,7 +685,7 @@ int sgm_run(const SgmArgs& a, Arena& ar, cudaStream_t st) {
   VWB_TRY(ar.alloc(&cost, (size_t)total + 64));
   VWB_TRY(ar.alloc(&accum, (size_t)total + 64));
   VWB_TRY(ar.alloc(&scratch, (size_t)total + 64));
-  sgm_cost_kernel<<<148 * 8, 256, 0, st>>>(lc, rc, meta, g, cost);
+  sgm_cost_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(lc, rc, meta, g, cost);
   VWB_LAUNCH_CHECK();
   VWB_CUDA(cudaStreamSynchronize(st));                                  // max_n
   if (a.use_mgm) {

@@ -72,11 +72,60 @@ __device__ __forceinline__ void eval_path_general(const MetaR& m, int pb0, int p
   }
 }
 
-template <int PF>
-__global__ void __launch_bounds__(256) sgm_lines_kernel(const SgmMeta* __restrict__ meta, const sgm_cost_t* __restrict__ cost,
-                                                        sgm_accum_t* __restrict__ accum, SgmGeom g, int sc, int sr, int first_dir,
-                                                        sgm_accum_t* __restrict__ scratch, unsigned scratch_per_warp) {
+// ---- the general step: a box with more than 32 disparities is involved (rare: full-search pixels) ---------------------
+struct LineState {
+  unsigned pv;                 // previous pixel's path cost of this lane's entry (layout of ITS box); BAD = no entry
+  int pn;                      // previous pixel's number of entries (0 also stands for "line starts here")
+  int pb0, pb1, pb2, pb3;      // previous pixel's box
+  int prev_in_buf;             // pn > 32: the previous costs live in bufA
+  sgm_accum_t *bufA, *bufB;
+};
+__device__ __noinline__ void sgm_general_step(LineState* s, uint4 mq, const sgm_cost_t* __restrict__ cost, sgm_accum_t* __restrict__ accum,
+                                              unsigned p1, unsigned p2_mod, unsigned BAD, int first_dir, int lane) {
+  const MetaR m = unpack_meta(mq);
+  if (!s->prev_in_buf) { if (lane < s->pn) s->bufA[lane] = (sgm_accum_t)s->pv; __syncwarp(); }
+  sgm_accum_t* bufB = s->bufB;
+  eval_path_general<false>(m, s->pb0, s->pb1, s->pb2, s->pb3, s->pn, s->bufA, cost, p1, p2_mod, BAD, lane, [&](int e, unsigned v) {
+    bufB[e] = (sgm_accum_t)v;
+    const unsigned a0 = first_dir ? 0u : (unsigned)accum[(size_t)m.start + e];
+    accum[(size_t)m.start + e] = (sgm_accum_t)(a0 + v);
+  });
+  __syncwarp();
+  s->bufB = s->bufA; s->bufA = bufB;
+  s->prev_in_buf = m.n > 32;
+  s->pv = (m.n <= 32 && lane < m.n) ? (unsigned)bufB[lane] : BAD;
+  s->pn = m.n; s->pb0 = m.b0; s->pb1 = m.b1; s->pb2 = m.b2; s->pb3 = m.b3;
+}
+
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(unsigned addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+// Per-warp shared-memory rings: 64 meta records (the current and the next 32-pixel epoch; lane i fetches the record of pixel
+// 32 * epoch + i two epochs ahead) and DR data slots (cost byte | accumulated cost << 16 of this lane's entry), filled
+// DR - 1 pixels ahead through a two-step register delay so that the loads have landed when they are written to the ring.
+// The loop is not unrolled: the body is ~90 instructions and the kernel is issue bound, not latency bound.
+// A line start is handled as "the previous pixel had no search area": with every predecessor cost = BAD the recurrence
+// returns exactly the local cost (BAD + cost - BAD), which is what the reference does for the first pixel (SGMAssist.h:756-759).
+// MODE: 0 horizontal lines, 1 vertical, 2 diagonal (wrapped).  FIRST: the first direction writes accum without reading it.
+__device__ __forceinline__ unsigned opaque(unsigned v) { asm volatile("mov.u32 %0, %0;" : "+r"(v)); return v; }   // pin in a register
+template <class T> __device__ __forceinline__ T* opaque_ptr(T* p) { asm volatile("mov.u64 %0, %0;" : "+l"(p)); return p; }
+template <int WARPS, int MODE, bool FIRST>
+__global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sgm_lines_kernel(const SgmMeta* __restrict__ meta, const sgm_cost_t* __restrict__ cost,
+                                                               sgm_accum_t* __restrict__ accum, SgmGeom g, int sc, int sr,
+                                                               sgm_accum_t* __restrict__ scratch, unsigned scratch_per_warp) {
+  constexpr int first_dir = FIRST ? 1 : 0;
+  constexpr int DR = 16, P = DR - 1;
   __shared__ unsigned short s_p2mod[256];
+  __shared__ uint4 s_ring[WARPS][64];
+  __shared__ unsigned s_data[WARPS][DR][32];
   for (unsigned d = threadIdx.x; d < 256; d += blockDim.x) {          // p2_mod as a function of the grey-value step (:1026-1031)
     const unsigned p2u = (unsigned)g.p2 & 0xffffu;                   // (accum_t)p2
     unsigned v = d ? p2u / d : p2u;
@@ -84,153 +133,144 @@ __global__ void __launch_bounds__(256) sgm_lines_kernel(const SgmMeta* __restric
     s_p2mod[d] = (unsigned short)v;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const bool horiz = sr == 0;
-  const int NL = horiz ? g.oh : g.ow, NS = horiz ? g.ow : g.oh;
+  const int lane = (int)opaque(threadIdx.x & 31), wid = threadIdx.x >> 5;
+  const int line = blockIdx.x * WARPS + wid;
+  constexpr bool horiz = MODE == 0;
+  const int ow = g.ow, oh = g.oh;
+  const int NL = horiz ? oh : ow, NS = horiz ? ow : oh;
   if (line >= NL) return;
-  const unsigned BAD = (unsigned)((255 + g.p2) & 0xffff);            // get_bad_accum_val (SGM.h:240) as accum_t
-  const unsigned p1 = (unsigned)g.p1;
+  const unsigned BAD = opaque((unsigned)((255 + g.p2) & 0xffff));    // get_bad_accum_val (SGM.h:240) as accum_t
+  const unsigned p1 = opaque((unsigned)g.p1);
+  const unsigned ring_s = opaque((unsigned)__cvta_generic_to_shared(&s_ring[wid][0]));
+  const unsigned data_s = opaque((unsigned)__cvta_generic_to_shared(&s_data[wid][0][lane]));
+  const unsigned p2mod_s = opaque((unsigned)__cvta_generic_to_shared(&s_p2mod[0]));
+  const sgm_cost_t* cost_l = opaque_ptr(cost + lane);
+  sgm_accum_t* accum_l = opaque_ptr(accum + lane);
+  const uint4 MZ = make_uint4(0xffff0000u, 0xffffu, 0u, 0u);         // box (0,0,-1,-1), n = 0
+
+  // pixel of step t on this line: horizontal (line, t) or the wrapped column (line + sc * t) mod ow of row t
+  const int edge_c = sc > 0 ? 0 : ow - 1;
+  int lc;                                                             // this lane's column cursor for the meta fetches
+  if (horiz) lc = sc > 0 ? lane : ow - 1 - lane;
+  else { lc = (line + sc * lane) % ow; if (lc < 0) lc += ow; }
+  auto fetch_meta = [&](int epoch) -> uint4 {                        // record of step 32 * epoch + lane; advances the cursor by 32 steps
+    const int t = 32 * epoch + lane;
+    uint4 q = MZ;
+    if (t < NS) {
+      const int r = horiz ? line : (sr > 0 ? t : oh - 1 - t);
+      q = __ldg(reinterpret_cast<const uint4*>(meta) + ((size_t)r * ow + lc));
+    }
+    lc += 32 * sc;
+    if (!horiz) { while (lc >= ow) lc -= ow; while (lc < 0) lc += ow; }
+    return q;
+  };
+  s_ring[wid][lane] = fetch_meta(0);
+  s_ring[wid][32 + lane] = fetch_meta(1);
+  uint4 mnext = fetch_meta(2);
+  __syncwarp();
+
+  auto load_data = [&](int t) -> unsigned {                           // cost | accum << 16 of this lane's entry of the pixel of step t
+    const uint2 q = lds64(ring_s + ((t & 63) << 4) + 8);              // (its record is in the meta ring)
+    unsigned v = 0u;
+    if ((unsigned)lane < (q.y >> 8) && q.y < (33u << 8)) {
+      unsigned c, a = 0u;
+      asm("ld.global.nc.u8 %0, [%1];" : "=r"(c) : "l"(cost_l + q.x));
+      if (!first_dir) asm volatile("ld.global.u16 %0, [%1];" : "=r"(a) : "l"(accum_l + q.x) : "memory");
+      v = c | (a << 16);
+    }
+    return v;
+  };
+  for (int t = 0; t < P - 2; ++t) asm volatile("st.shared.u32 [%0], %1;" ::"r"(data_s + ((t & (DR - 1)) << 7)), "r"(load_data(t)));
+  unsigned d1 = load_data(P - 2), d0 = load_data(P - 1);              // written to the ring at steps 0 and 1
+
+  // chain state (see LineState); x, y, w, h: this lane's position in the previous pixel's box; o?: 0xffff where the
+  // neighbour on that side is outside the box (a masked neighbour may read as 0xffff instead of BAD: the result is the
+  // same because min(.., centre, dJ) never exceeds BAD < BAD + P1)
+  unsigned pv = BAD, pkx = 0xffffffffu, pky = 0xffffffffu;
+  int pn = 0, last_val = 0, pb0 = 0, pb1 = 0, pb2 = -1, pb3 = -1, w = 1;
+  unsigned oL = 0xffffu, oR = 0xffffu, oU = 0xffffffffu, oD = 0xffffffffu;
+  int prev_in_buf = 0;
   sgm_accum_t* bufA = scratch ? scratch + (size_t)line * scratch_per_warp : nullptr;
   sgm_accum_t* bufB = bufA ? bufA + scratch_per_warp / 2 : nullptr;
+  // wrapped diagonals: steps until the line reaches the image edge and restarts
+  constexpr bool wraps = MODE == 2;
+  int to_edge = wraps ? (sc > 0 ? ow - line : line + 1) : 0x7fffffff;
 
-  // cursors of the three pipeline stages: meta loads run 2*PF pixels ahead, data loads PF pixels ahead
-  int cM, rM;
-  if (horiz) { rM = line; cM = sc > 0 ? 0 : g.ow - 1; }
-  else { cM = line; rM = sr > 0 ? 0 : g.oh - 1; }
-  auto adv = [&](int& c, int& r) {
-    r += sr; c += sc;
-    if (!horiz) { if (c >= g.ow) c = 0; else if (c < 0) c = g.ow - 1; }
-  };
-  auto in_img = [&](int c, int r) { return c >= 0 && c < g.ow && r >= 0 && r < g.oh; };
-  uint4 mA[PF], mB[PF], mC[PF];
-  unsigned dcA[PF], daA[PF], dcB[PF], daB[PF];
-  const uint4 MZ = make_uint4(0xffff0000u, 0xffffu, 0u, 0u);       // box (0,0,-1,-1), n = 0
-  auto load_meta = [&](uint4* dst, int t0) {
-#pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      dst[i] = (t0 + i < NS && in_img(cM, rM)) ? __ldg(reinterpret_cast<const uint4*>(meta) + ((size_t)rM * g.ow + cM)) : MZ;
-      adv(cM, rM);
+#pragma unroll 1
+  for (int t = 0; t < NS; ++t) {
+    if ((t & 31) == 0 && t) {              // epoch start: publish the records of the next epoch, start fetching the one after
+      s_ring[wid][((t + 32) & 63) + lane] = mnext;
+      mnext = fetch_meta((t >> 5) + 2);
+      __syncwarp();
     }
-  };
-  auto load_data = [&](const uint4* m, unsigned* dc, unsigned* da) {
-#pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      const unsigned n = m[i].w >> 8;
-      const bool act = (unsigned)lane < n && n <= 32u;
-      dc[i] = act ? (unsigned)cost[(size_t)m[i].z + lane] : 0u;
-      da[i] = (act && !first_dir) ? (unsigned)accum[(size_t)m[i].z + lane] : 0u;
-    }
-  };
-  load_meta(mA, 0);
-  load_meta(mB, PF);
-  load_data(mA, dcA, daA);
-
-  // chain state
-  int last_val = -1;
-  unsigned pv = 0xffffu;                 // previous pixel's path cost of this lane's entry (its box layout); 0xffff = no entry
-  int pn = 0;                            // previous pixel's number of entries
-  unsigned pkx = 0xffffffffu, pky = 0xffffffffu;     // previous pixel's packed box
-  int pb0 = 0, pb1 = 0, pb2 = -1, pb3 = -1, x = 0, y = 0, w = 1, h = 1;   // previous box and this lane's position in it
-  bool prev_in_buf = false;              // pn > 32: the previous costs live in bufA
-
-  // compute cursor only for the "line restarts" test of wrapped diagonals
-  int cC = horiz ? (sc > 0 ? 0 : g.ow - 1) : line;
-
-  for (int t0 = 0; t0 < NS; t0 += PF) {
-    load_meta(mC, t0 + 2 * PF);
-    load_data(mB, dcB, daB);
-#pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      const int t = t0 + i;
-      if (t < NS) {                      // warp-uniform
-        const MetaR m = unpack_meta(mA[i]);
-        const bool restart = (t == 0) || (!horiz && sc != 0 && cC == (sc > 0 ? 0 : g.ow - 1));
-        if (restart) last_val = -1;
-        const bool changed = mA[i].x != pkx || mA[i].y != pky;
-        int nx = x, ny = y, nw = w, nh = h;
-        if (changed && m.n <= 32) {
-          nw = max(m.b2 - m.b0 + 1, 1); nh = m.b3 - m.b1 + 1;
-          ny = (lane * (int)c_recip[min(nw, 32)]) >> 10; nx = lane - ny * nw;
-        }
-        const bool act = lane < m.n;
-        unsigned cur = 0xffffu;
-        if (m.n <= 32 && (last_val < 0 || pn <= 32)) {
-          // ---------------- register path ----------------
-          const unsigned local = dcA[i];
-          if (last_val < 0) {
-            cur = local;                                                // first pixel of a line (SGMAssist.h:756-759)
-          } else {
-            const unsigned p2_mod = s_p2mod[abs(m.val - last_val)];
-            const unsigned mp = min(__reduce_min_sync(0xffffffffu, pv), BAD);
-            const unsigned dJ = (mp + p2_mod) & 0xffffu;
-            // separable 3 x 3 minimum in the previous box's layout (lanes >= pn hold 0xffff and are never addressed)
-            const unsigned vl = __shfl_up_sync(0xffffffffu, pv, 1), vr = __shfl_down_sync(0xffffffffu, pv, 1);
-            const unsigned hmin = min(min(x > 0 ? vl : BAD, pv), x < w - 1 ? vr : BAD);
-            unsigned nb, centre;
-            if (!changed) {
-              const unsigned hu = __shfl_up_sync(0xffffffffu, hmin, w), hd = __shfl_down_sync(0xffffffffu, hmin, w);
-              nb = min(min(y > 0 ? hu : BAD, hmin), y < h - 1 ? hd : BAD);
-              centre = pv;
-            } else {
-              const unsigned BB = BAD | (BAD << 16);
-              const unsigned q = (pv & 0xffffu) | (hmin << 16);
-              unsigned qu = __shfl_up_sync(0xffffffffu, q, w), qd = __shfl_down_sync(0xffffffffu, q, w);
-              if (y == 0) qu = BB;
-              if (y >= h - 1) qd = BB;
-              const unsigned wm = __vimin3_u16x2(qu, q, qd);           // lo: column min3 of v, hi: 3 x 3 min
-              const int X = m.b0 + nx, Y = m.b1 + ny;
-              const int sxp = min(max(X, pb0), pb2), syp = min(max(Y, pb1), pb3);
-              const int ddx = X - sxp, ddy = Y - syp;
-              const int src = ((syp - pb1) * w + (sxp - pb0)) & 31;
-              const unsigned g1 = __shfl_sync(0xffffffffu, q, src), g2 = __shfl_sync(0xffffffffu, wm, src);
-              const bool reach = pn > 0 && ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1;
-              centre = BAD;
-              if (!reach) nb = BAD;
-              else if (ddx == 0 && ddy == 0) { nb = g2 >> 16; centre = g1 & 0xffffu; }
-              else if (ddy == 0) nb = g2 & 0xffffu;
-              else if (ddx == 0) nb = g1 >> 16;
-              else nb = g1 & 0xffffu;
-            }
-            unsigned res = sat_add16(nb, p1);
-            res = min(res, min(centre, dJ));
-            res = sat_add16(res, local);
-            cur = sat_sub16(res, mp);
-          }
-          if (act) accum[(size_t)m.start + lane] = (sgm_accum_t)(daA[i] + cur);      // update_accum_buffer, uint16 wrap
-          if (!act) cur = 0xffffu;
-          prev_in_buf = false;
-        } else {
-          // ---------------- general path: a box with more than 32 disparities is involved ----------------
-          if (!prev_in_buf && last_val >= 0) { if (lane < pn) bufA[lane] = (sgm_accum_t)pv; __syncwarp(); }
-          if (last_val < 0) {
-            for (int e = lane; e < m.n; e += 32) {
-              const unsigned c0 = cost[(size_t)m.start + e];
-              bufB[e] = (sgm_accum_t)c0;
-              const unsigned a0 = first_dir ? 0u : (unsigned)accum[(size_t)m.start + e];
-              accum[(size_t)m.start + e] = (sgm_accum_t)(a0 + c0);
-            }
-          } else {
-            const unsigned p2_mod = s_p2mod[abs(m.val - last_val)];
-            eval_path_general<false>(m, pb0, pb1, pb2, pb3, pn, bufA, cost, p1, p2_mod, BAD, lane, [&](int e, unsigned v) {
-              bufB[e] = (sgm_accum_t)v;
-              const unsigned a0 = first_dir ? 0u : (unsigned)accum[(size_t)m.start + e];
-              accum[(size_t)m.start + e] = (sgm_accum_t)(a0 + v);
-            });
-          }
-          __syncwarp();
-          sgm_accum_t* sw = bufA; bufA = bufB; bufB = sw;
-          prev_in_buf = m.n > 32;
-          cur = (m.n <= 32 && act) ? (unsigned)bufA[lane] : 0xffffu;
-        }
-        // this pixel becomes the predecessor
-        pv = cur; pn = m.n; last_val = m.val;
-        if (changed) { pkx = mA[i].x; pky = mA[i].y; pb0 = m.b0; pb1 = m.b1; pb2 = m.b2; pb3 = m.b3; x = nx; y = ny; w = nw; h = nh; }
-        if (horiz) cC += sc; else { cC += sc; if (cC >= g.ow) cC = 0; else if (cC < 0) cC = g.ow - 1; }
+    // data ring: the loads issued two steps ago go in, the loads for pixel t + P go out
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(data_s + (((t + P - 2) & (DR - 1)) << 7)), "r"(d1));
+    d1 = d0;
+    d0 = load_data(t + P);
+    const uint4 mq = lds128(ring_s + ((t & 63) << 4));
+    unsigned dat;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dat) : "r"(data_s + ((t & (DR - 1)) << 7)));
+    const int n = (int)(mq.w >> 8), val = (int)(mq.w & 255u);
+    if (wraps && to_edge == 0) { pv = BAD; pn = 0; prev_in_buf = 0; to_edge = ow; }      // the line restarts at the image edge
+    unsigned p2_mod;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(p2_mod) : "r"(p2mod_s + 2u * (unsigned)abs(val - last_val)));
+    if (n <= 32 && pn <= 32) {
+      // ---------------- register path ----------------
+      const unsigned mp = __reduce_min_sync(0xffffffffu, pv);      // lanes without an entry hold BAD
+      const unsigned dJ = (mp + p2_mod) & 0xffffu;
+      const unsigned vl = __shfl_up_sync(0xffffffffu, pv, 1), vr = __shfl_down_sync(0xffffffffu, pv, 1);
+      const unsigned hmin = min(min(vl | oL, pv), vr | oR);
+      unsigned nb, centre;
+      if (mq.x == pkx && mq.y == pky) {                              // same box as the previous pixel
+        const unsigned hu = __shfl_up_sync(0xffffffffu, hmin, w), hd = __shfl_down_sync(0xffffffffu, hmin, w);
+        nb = min(min(hu | oU, hmin), hd | oD);
+        centre = pv;
+      } else {
+        const MetaR m = unpack_meta(mq);
+        const unsigned q = pv | (hmin << 16);
+        const unsigned qu = __shfl_up_sync(0xffffffffu, q, w) | oU, qd = __shfl_down_sync(0xffffffffu, q, w) | oD;
+        const unsigned wm = __vimin3_u16x2(qu, q, qd);             // lo: column min3 of v, hi: 3 x 3 min
+        const int nw = max(m.b2 - m.b0 + 1, 1), nh = m.b3 - m.b1 + 1;
+        const int ny = (lane * (int)c_recip[min(nw, 32)]) >> 10, nx = lane - ny * nw;
+        const int X = m.b0 + nx, Y = m.b1 + ny;
+        const int sxp = min(max(X, pb0), pb2), syp = min(max(Y, pb1), pb3);
+        const int ddx = X - sxp, ddy = Y - syp;
+        const int src = ((syp - pb1) * w + (sxp - pb0)) & 31;
+        const unsigned g1 = __shfl_sync(0xffffffffu, q, src), g2 = __shfl_sync(0xffffffffu, wm, src);
+        const bool reach = pn > 0 && (unsigned)(ddx + 1) <= 2u && (unsigned)(ddy + 1) <= 2u;
+        centre = BAD;
+        if (!reach) nb = BAD;
+        else if (ddx == 0 && ddy == 0) { nb = g2 >> 16; centre = g1 & 0xffffu; }
+        else if (ddy == 0) nb = g2 & 0xffffu;
+        else if (ddx == 0) nb = g1 >> 16;
+        else nb = g1 & 0xffffu;
+        // the new box becomes the layout
+        pkx = mq.x; pky = mq.y; pb0 = m.b0; pb1 = m.b1; pb2 = m.b2; pb3 = m.b3; w = nw;
+        oL = nx > 0 ? 0u : 0xffffu; oR = nx < nw - 1 ? 0u : 0xffffu;
+        oU = ny > 0 ? 0u : 0xffffffffu; oD = ny < nh - 1 ? 0u : 0xffffffffu;
       }
+      unsigned res = sat_add16(nb, p1);
+      res = min(res, min(centre, dJ));
+      res = sat_add16(res, dat & 0xffu);
+      const unsigned cur = sat_sub16(res, mp);
+      pv = BAD;
+      if (lane < n) {                                                  // update_accum_buffer, uint16 wrap
+        asm volatile("st.global.u16 [%0], %1;" ::"l"(accum_l + mq.z), "r"((dat >> 16) + cur) : "memory");
+        pv = cur;
+      }
+      pn = n;
+    } else {
+      LineState st{pv, pn, pb0, pb1, pb2, pb3, prev_in_buf, bufA, bufB};
+      sgm_general_step(&st, mq, cost, accum, p1, p2_mod, BAD, first_dir, lane);
+      pv = st.pv; pn = st.pn; pb0 = st.pb0; pb1 = st.pb1; pb2 = st.pb2; pb3 = st.pb3; prev_in_buf = st.prev_in_buf; bufA = st.bufA; bufB = st.bufB;
+      pkx = mq.x; pky = mq.y;
+      w = max(pb2 - pb0 + 1, 1);
+      const int h = pb3 - pb1 + 1, y = (lane * (int)c_recip[min(w, 32)]) >> 10, x = lane - y * w;
+      oL = x > 0 ? 0u : 0xffffu; oR = x < w - 1 ? 0u : 0xffffu;
+      oU = y > 0 ? 0u : 0xffffffffu; oD = y < h - 1 ? 0u : 0xffffffffu;
     }
-#pragma unroll
-    for (int i = 0; i < PF; ++i) { mA[i] = mB[i]; mB[i] = mC[i]; dcA[i] = dcB[i]; daA[i] = daB[i]; }
+    last_val = val;
+    if (wraps) --to_edge;
   }
 }
 
@@ -247,8 +287,12 @@ int sgm_paths_launch(const SgmMeta* meta, const sgm_cost_t* cost, sgm_accum_t* a
   for (int i = 0; i < 8; ++i) {
     const int sc = DIRS[i][0], sr = DIRS[i][1];
     const int lines = sr == 0 ? g.oh : g.ow;
-    const int wpb = 4;                                                 // warps per CTA
-    sgm_lines_kernel<2><<<(lines + wpb - 1) / wpb, wpb * 32, 0, st>>>(meta, cost, accum, g, sc, sr, i == 0, scratch, per_warp);
+    constexpr int WPB = 4;                                             // warps (= neighbouring lines) per CTA
+    const dim3 grid((lines + WPB - 1) / WPB), blk(WPB * 32);
+    if (i == 0) sgm_lines_kernel<WPB, 0, true><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp);
+    else if (sr == 0) sgm_lines_kernel<WPB, 0, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp);
+    else if (sc == 0) sgm_lines_kernel<WPB, 1, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp);
+    else sgm_lines_kernel<WPB, 2, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp);
     VWB_LAUNCH_CHECK();
   }
   return VWB200_OK;
