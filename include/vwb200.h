@@ -200,8 +200,15 @@ typedef struct {
   int32_t max_pyramid_levels;
   int32_t collar_size;
   int32_t corr_timeout; double seconds_per_op;          /* accepted; timeouts never trigger on the GPU */
-  int32_t algorithm;                                    /* 0 = VW_CORRELATION_BM (only one implemented) */
-  int32_t blob_filter_area;                             /* must be 0 (CorrelationView.cc:249-250) */
+  int32_t algorithm;                                    /* CorrelationAlgorithm: BM, SGM, MGM, FINAL_MGM */
+  int32_t blob_filter_area;                             /* > 0: disparity_blob_filter (CorrelationView.cc:242-271) */
+  /* the remaining constructor arguments (CorrelationView.h:61-69) */
+  int32_t sgm_subpixel_mode;                            /* SgmSubpixelMode, default SUBPIXEL_LC_BLEND = 5 */
+  int32_t sgm_search_buffer_x, sgm_search_buffer_y;     /* default (2, 2) */
+  int32_t region_ul_x, region_ul_y;                     /* image position of lr_disp_diff's pixel (0, 0) */
+  int32_t write_debug_images;                           /* accepted, ignored: the engine writes no files */
+  int32_t sgm_threads;                                  /* vw_settings().default_num_threads() of SGM's memory estimate; <= 0: 4 */
+  double  memory_limit_mb;                              /* <= 0: 6000 */
 } vwb200_corr_params;
 
 typedef struct vwb200_corr vwb200_corr;
@@ -214,12 +221,21 @@ int  vwb200_corr_set_inputs(vwb200_corr* h,
                             const float* right, int rcols, int rrows, ptrdiff_t rpitch,
                             const uint8_t* lmask, ptrdiff_t lmpitch,
                             const uint8_t* rmask, ptrdiff_t rmpitch, int on_device);
+/* the optional lr_disp_diff output (CorrelationView.h:67-68, .cc:276-283,848-857): a caller-owned cols x rows image of
+ * PixelMask<float> = {value, valid} float pairs (row pitch in pixels) whose pixel (0, 0) sits at params.region_ul.
+ * rasterize() writes max(|dx_lr + dx_rl|, |dy_lr + dy_rl|) where the L/R check passes (level 0) and invalidates where the
+ * final disparity is invalid; other pixels keep their content.  A processed box outside the image -> VWB200_EARG.
+ * diff == NULL switches the output off. */
+int  vwb200_corr_set_lr_disp_diff(vwb200_corr* h, float* diff, int cols, int rows, ptrdiff_t pitch, int on_device);
 int  vwb200_corr_cols(const vwb200_corr* h);
 int  vwb200_corr_rows(const vwb200_corr* h);
 /* rasterize(dest, bbox): dest receives (x1-x0) x (y1-y0) float disparity pixels (3 floats each),
  * row pitch dest_pitch in PIXELS.  Collar handling as in CorrelationView.h:123-133. */
 int  vwb200_corr_rasterize(vwb200_corr* h, int x0, int y0, int x1, int y1,
                            float* dest, ptrdiff_t dest_pitch, int dest_on_device, void* stream);
+/* prerasterize(bbox) (CorrelationView.cc:273-886): like rasterize() but processes exactly bbox, without the collar */
+int  vwb200_corr_prerasterize(vwb200_corr* h, int x0, int y0, int x1, int y1,
+                              float* dest, ptrdiff_t dest_pitch, int dest_on_device, void* stream);
 /* levels prerasterize() would use for a bbox of this size (CorrelationView.cc:301-310) */
 int  vwb200_corr_num_levels(const vwb200_corr* h, int bw, int bh);
 void vwb200_corr_destroy(vwb200_corr* h);

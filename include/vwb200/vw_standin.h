@@ -13,6 +13,7 @@
 //   vw::rasterize               Image/ImageViewBase.h:283-316
 //   Exception hierarchy         Core/Exception.h:201-253
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -155,7 +156,23 @@ template <class SrcT, class DestT> inline void rasterize(SrcT const& src, DestT 
   src.rasterize(dest, bbox);
 }
 
+// Image/PixelAccessors.h:119-156: the accessor of views whose pixels are computed by operator()
+template <class ViewT> class ProceduralPixelAccessor {
+  ViewT const& m_view; int32 m_c, m_r, m_p;
+public:
+  typedef typename ViewT::pixel_type pixel_type; typedef typename ViewT::result_type result_type;
+  ProceduralPixelAccessor(ViewT const& view) : m_view(view), m_c(0), m_r(0), m_p(0) {}
+  ProceduralPixelAccessor(ViewT const& view, int32 c, int32 r, int32 p = 0) : m_view(view), m_c(c), m_r(r), m_p(p) {}
+  ProceduralPixelAccessor& next_col() { ++m_c; return *this; } ProceduralPixelAccessor& prev_col() { --m_c; return *this; }
+  ProceduralPixelAccessor& next_row() { ++m_r; return *this; } ProceduralPixelAccessor& prev_row() { --m_r; return *this; }
+  ProceduralPixelAccessor& advance(int32 dc, int32 dr, ptrdiff_t dp = 0) { m_c += dc; m_r += dr; m_p += int32(dp); return *this; }
+  result_type operator*() const { return m_view(m_c, m_r, m_p); }
+};
+
 namespace stereo {
+struct SemiGlobalMatcher {                                                                    // Stereo/SGM.h:93-99
+  enum SgmSubpixelMode { SUBPIXEL_NONE = 0, SUBPIXEL_PARABOLA = 1, SUBPIXEL_LINEAR = 2, SUBPIXEL_POLY4 = 3, SUBPIXEL_COSINE = 4, SUBPIXEL_LC_BLEND = 5 };
+};
 enum CostFunctionType { ABSOLUTE_DIFFERENCE, SQUARED_DIFFERENCE, CROSS_CORRELATION, CENSUS_TRANSFORM, TERNARY_CENSUS_TRANSFORM };  // Stereo/CostFunctions.h:143-149
 enum PrefilterModeType { PREFILTER_NONE = 0, PREFILTER_LOG = 1, PREFILTER_MEANSUB = 2 };                                           // Stereo/PrefilterEnum.h:24-28
 enum CorrelationAlgorithm { VW_CORRELATION_BM = 0, VW_CORRELATION_SGM = 1, VW_CORRELATION_MGM = 2, VW_CORRELATION_FINAL_MGM = 3 };

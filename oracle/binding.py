@@ -26,7 +26,10 @@ class CorrParams(C.Structure):
                 ("kernel_x", C.c_int32), ("kernel_y", C.c_int32), ("cost_type", C.c_int32),
                 ("prefilter_mode", C.c_int32), ("prefilter_width", C.c_float),
                 ("consistency_threshold", C.c_float), ("min_consistency_level", C.c_int32),
-                ("filter_half_kernel", C.c_int32), ("max_pyramid_levels", C.c_int32), ("collar_size", C.c_int32)]
+                ("filter_half_kernel", C.c_int32), ("max_pyramid_levels", C.c_int32), ("collar_size", C.c_int32),
+                ("algorithm", C.c_int32), ("sgm_subpixel_mode", C.c_int32), ("sgm_search_buffer_x", C.c_int32),
+                ("sgm_search_buffer_y", C.c_int32), ("blob_filter_area", C.c_int32), ("sgm_threads", C.c_int32),
+                ("memory_limit_mb", C.c_double)]
 
 
 class CorrInputs(C.Structure):
@@ -194,11 +197,13 @@ def subdivide_regions(d, kernel, max_zones=65536):
 
 def make_params(search, kernel, cost=COST_ABS, prefilter_mode=PREFILTER_NONE, prefilter_width=0.0,
                 consistency_threshold=-1.0, min_consistency_level=0, filter_half_kernel=0,
-                max_pyramid_levels=0, collar_size=0):
+                max_pyramid_levels=0, collar_size=0, algorithm=0, sgm_subpixel_mode=5, sgm_search_buffer=(2, 2),
+                blob_filter_area=0, sgm_threads=4, memory_limit_mb=6000.0):
     """search = (x0, y0, x1, y1) half-open BBox2i; kernel = (kx, ky)."""
     return CorrParams(search[0], search[1], search[2], search[3], kernel[0], kernel[1], cost,
                       prefilter_mode, prefilter_width, consistency_threshold, min_consistency_level,
-                      filter_half_kernel, max_pyramid_levels, collar_size)
+                      filter_half_kernel, max_pyramid_levels, collar_size, algorithm, sgm_subpixel_mode,
+                      sgm_search_buffer[0], sgm_search_buffer[1], blob_filter_area, sgm_threads, memory_limit_mb)
 
 
 class _Inputs:
@@ -216,19 +221,66 @@ def num_levels(params, bw, bh):
     return lib().vwo_num_levels(C.byref(params), bw, bh)
 
 
-def pyramid_correlate(params, left, right, lmask=None, rmask=None, bbox=None):
+def pyramid_correlate(params, left, right, lmask=None, rmask=None, bbox=None, lr_disp_diff=None, region_ul=(0, 0)):
     """PyramidCorrelationView::rasterize over bbox (default: the whole left image).
-    Returns float32 (h, w, 3) {dx, dy, valid}."""
+    Returns float32 (h, w, 3) {dx, dy, valid}.  lr_disp_diff: float32 (rows, cols, 2) PixelMask<float> image, updated in place."""
     inp = _Inputs(left, right, lmask, rmask)
     if bbox is None:
         bbox = (0, 0, inp.l.shape[1], inp.l.shape[0])
     w, h = bbox[2] - bbox[0], bbox[3] - bbox[1]
     out = np.empty((h, w, 3), np.float32)
-    rc = lib().vwo_pyramid_correlate_rasterize(C.byref(params), C.byref(inp.c), bbox[0], bbox[1], bbox[2], bbox[3],
-                                               _p(out), w, None)
+    f = lib().vwo_pyramid_correlate_rasterize_ex
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                  C.c_int, C.c_int]
+    if lr_disp_diff is not None:
+        assert lr_disp_diff.dtype == np.float32 and lr_disp_diff.flags.c_contiguous and lr_disp_diff.shape[2] == 2
+    rc = f(C.byref(params), C.byref(inp.c), bbox[0], bbox[1], bbox[2], bbox[3], _p(out), w, None,
+           _p(lr_disp_diff) if lr_disp_diff is not None else None, 0 if lr_disp_diff is None else lr_disp_diff.shape[1],
+           0 if lr_disp_diff is None else lr_disp_diff.shape[0], region_ul[0], region_ul[1])
     if rc:
         raise ValueError(f"vwo_pyramid_correlate_rasterize rc={rc}")
     return out
+
+
+def disparity_blob_filter(disp, area):
+    """PyramidCorrelationView::disparity_blob_filter (CorrelationView.cc:242-271) at a given area threshold."""
+    d = np.ascontiguousarray(disp, np.int32).copy()
+    lib().vwo_disparity_blob_filter(_p(d), d.shape[1], d.shape[0], int(area))
+    return d
+
+
+def census_value(img, col, row, k, ternary=False, thr=5):
+    a = np.ascontiguousarray(img, np.uint8)
+    f = lib().vwo_census_value
+    f.restype = C.c_uint64
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    return int(f(_p(a), a.shape[1], col, row, k, int(ternary), thr))
+
+
+def calc_disparity_sgm(left, right, search, kernel_size, cost_type=3, use_mgm=False, subpixel_mode=0, search_buffer=(2, 2),
+                       memory_limit_mb=6000.0, threads=4, lmask=None, rmask=None, prev=None, bounds=None, p1=0, p2=0):
+    """The whole of vw::stereo::calc_disparity_sgm (SGM.cc:167-230).  Returns (int32 (h, w, 3), float32 (h, w, 3), boxes (h, w, 4))."""
+    l, r = _f32(left), _f32(right)
+    oh, ow = sgm_output_shape(l, r, search, kernel_size)
+    out = np.zeros((oh, ow, 3), np.int32)
+    sub = np.zeros((oh, ow, 3), np.float32)
+    b = np.zeros((oh, ow, 4), np.int32) if bounds is None else np.ascontiguousarray(bounds, np.int32).copy()
+    lm = None if lmask is None else np.ascontiguousarray(lmask, np.uint8)
+    rm = None if rmask is None else np.ascontiguousarray(rmask, np.uint8)
+    pv = None if prev is None else np.ascontiguousarray(prev, np.int32)
+    f = lib().vwo_calc_disparity_sgm
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    cw, ch = C.c_int(0), C.c_int(0)
+    rc = f(_p(l), l.shape[1], l.shape[0], l.shape[1], _p(r), r.shape[1], r.shape[0], r.shape[1], search[0], search[1], kernel_size, cost_type, 5,
+           p1, p2, int(use_mgm), subpixel_mode, search_buffer[0], search_buffer[1], float(memory_limit_mb), threads,
+           None if lm is None else _p(lm), None if rm is None else _p(rm), 0 if rm is None else rm.shape[1], 0 if rm is None else rm.shape[0],
+           None if pv is None else _p(pv), 0 if pv is None else pv.shape[1], 0 if pv is None else pv.shape[0],
+           _p(b), int(bounds is not None), _p(out), _p(sub), C.byref(cw), C.byref(ch))
+    if rc:
+        raise ValueError(f"vwo_calc_disparity_sgm rc={rc}")
+    return out, sub, b
 
 
 def pyramid_correlate_tiled(params, left, right, lmask=None, rmask=None, tile=1024, nthreads=0):

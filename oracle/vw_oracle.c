@@ -293,8 +293,9 @@ int vwo_pyramid_down(const float* in, int w, int h, float* out) {               
 
 /* ------------------------------------------------------------------ consistency check */
 /* Stereo/Correlate.cc:1441-1502 */
-int vwo_cross_corr_consistency_check(vwo_disp_t* l2r, int lw, int lh, int lpitch,
-                                     const vwo_disp_t* r2l, int rw, int rh, float threshold) {
+/* diff (optional): PixelMask<float> pairs, row pitch diff_pitch pixels; pixel (c + offx, r + offy) receives disp_diff */
+static int consistency_check_diff(vwo_disp_t* l2r, int lw, int lh, int lpitch, const vwo_disp_t* r2l, int rw, int rh, float threshold,
+                                  float* diff, int diff_pitch, int offx, int offy) {
   for (int r = 0; r < lh; ++r)
     for (int c = 0; c < lw; ++c) {
       vwo_disp_t* p = l2r + (size_t)r * lpitch + c;
@@ -304,9 +305,43 @@ int vwo_cross_corr_consistency_check(vwo_disp_t* l2r, int lw, int lh, int lpitch
       if (!p->valid || !q->valid) { p->valid = 0; continue; }
       /* std::max(fabs(int+int), fabs(int+int)) -> float disp_diff */
       double a = fabs((double)(p->dx + q->dx)), b = fabs((double)(p->dy + q->dy));
-      float diff = (float)(a > b ? a : b);
-      if (!(threshold >= diff)) p->valid = 0;
+      float dd = (float)(a > b ? a : b);
+      if (!(threshold >= dd)) p->valid = 0;
+      else if (diff) { float* o = diff + ((size_t)(r + offy) * diff_pitch + (c + offx)) * 2; o[0] = dd; o[1] = 1.0f; }
     }
+  return 0;
+}
+int vwo_cross_corr_consistency_check(vwo_disp_t* l2r, int lw, int lh, int lpitch,
+                                     const vwo_disp_t* r2l, int rw, int rh, float threshold) {
+  return consistency_check_diff(l2r, lw, lh, lpitch, r2l, rw, rh, threshold, NULL, 0, 0, 0);
+}
+
+/* disparity_blob_filter: labels = 8-connected components of the valid pixels (the two-pass labelling of blob::BlobIndex,
+ * Image/BlobIndex.h:113-305, yields exactly the connected components); blobs of size <= area are eroded. */
+static int uf_find(int* parent, int i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; }
+int vwo_disparity_blob_filter(vwo_disp_t* d, int w, int h, int area) {
+  if (area < 1 || w <= 0 || h <= 0) return 0;                                     /* CorrelationView.cc:249-250 */
+  const size_t n = (size_t)w * h;
+  int* parent = (int*)malloc(n * sizeof(int));
+  int* size = (int*)calloc(n, sizeof(int));
+  for (size_t i = 0; i < n; ++i) parent[i] = (int)i;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      if (!d[(size_t)y * w + x].valid) continue;
+      const int i = y * w + x;
+      static const int NX[4] = {-1, -1, 0, 1}, NY[4] = {0, -1, -1, -1};
+      for (int k = 0; k < 4; ++k) {
+        const int xx = x + NX[k], yy = y + NY[k];
+        if (xx < 0 || xx >= w || yy < 0) continue;
+        if (!d[(size_t)yy * w + xx].valid) continue;
+        const int a = uf_find(parent, i), b = uf_find(parent, yy * w + xx);
+        if (a != b) parent[a > b ? a : b] = a > b ? b : a;
+      }
+    }
+  for (size_t i = 0; i < n; ++i) if (d[i].valid) size[uf_find(parent, (int)i)]++;
+  for (size_t i = 0; i < n; ++i)
+    if (d[i].valid && size[uf_find(parent, (int)i)] <= area) { d[i].dx = 0; d[i].dy = 0; d[i].valid = 0; }   /* result_type() */
+  free(parent); free(size);
   return 0;
 }
 
@@ -881,7 +916,13 @@ static int zone_cmp(const void* a, const void* b) {                             
 }
 
 /* Stereo/CorrelationView.cc:273-886, block-matching branch only. out: bw*bh {dx,dy,valid} floats. */
-static int prerasterize(const vwo_corr_params* p, const vwo_corr_inputs* in, box_t bbox, float* out, int* levels_out) {
+typedef struct { float* d; int cols, rows, ulx, uly; } diff_t;
+static int prerasterize_sgm(const vwo_corr_params* p, const vwo_corr_inputs* in, box_t bbox, float* out, int* levels_out, const diff_t* df);
+static int prerasterize(const vwo_corr_params* p, const vwo_corr_inputs* in, box_t bbox, float* out, int* levels_out, const diff_t* df) {
+  if (df && df->d) {                                                              /* :276-283 */
+    if (!(bbox.x0 >= df->ulx && bbox.y0 >= df->uly && bbox.x1 <= df->ulx + df->cols && bbox.y1 <= df->uly + df->rows)) return -1;
+  }
+  if (p->algorithm != 0) return prerasterize_sgm(p, in, bbox, out, levels_out, df);
   const int bw = bbox.x1 - bbox.x0, bh = bbox.y1 - bbox.y0;
   const int kx = p->kernel_x, ky = p->kernel_y, hkx = kx / 2, hky = ky / 2;
   const int ssx = p->search_x1 - p->search_x0, ssy = p->search_y1 - p->search_y0;
@@ -935,7 +976,11 @@ static int prerasterize(const vwo_corr_params* p, const vwo_corr_inputs* in, box
         rc = vwo_calc_disparity(p->cost_type, rcq.d, rcq.w, rcq.h, rcq.w, l2.d, l2.w, l2.h, l2.w, dsx, dsy, kx, ky, rl);
         if (rc) { free(l2.d); free(rl); free(lc.d); free(rcq.d); free(zd); free(disparity); free(zones.z); pyr_free(&py); return -40 + rc; }
         for (size_t i = 0; i < (size_t)rlw * rlh; ++i) { rl[i].dx -= dsx; rl[i].dy -= dsy; }
-        vwo_cross_corr_consistency_check(zd, zw, zh, zw, rl, rlw, rlh, p->consistency_threshold);
+        if (df && df->d)                                                          /* :669-676: offset = zone min + bbox.min - region_ul */
+          consistency_check_diff(zd, zw, zh, zw, rl, rlw, rlh, p->consistency_threshold, df->d, df->cols,
+                                 z.img.x0 + bbox.x0 - df->ulx, z.img.y0 + bbox.y0 - df->uly);
+        else
+          vwo_cross_corr_consistency_check(zd, zw, zh, zw, rl, rlw, rlh, p->consistency_threshold);
         free(l2.d); free(rl);
       }
       for (int y = 0; y < zh; ++y)                                                /* :698 */
@@ -954,6 +999,7 @@ static int prerasterize(const vwo_corr_params* p, const vwo_corr_inputs* in, box
       vwo_disparity_mask(t, dw, dh, py.lm[level].d, py.rm[level].d, py.rm[level].w, py.rm[level].h, disparity);
       free(t);
     }
+    vwo_disparity_blob_filter(disparity, dw, dh, p->blob_filter_area / scaling);    /* :746-749, :242-271 */
     if (level != 0) {                                                             /* :754-799 */
       zones.n = 0;
       subdivide(disparity, dw, dh, box_xywh(0, 0, dw, dh), &zones, kx, ky, 0);
@@ -973,6 +1019,10 @@ static int prerasterize(const vwo_corr_params* p, const vwo_corr_inputs* in, box
     }
   }
   if (dw != bw || dh != bh) { free(disparity); free(zones.z); pyr_free(&py); return -50; }   /* :832-834 */
+  if (df && df->d)                                                                /* :848-857 */
+    for (int r = 0; r < bh; ++r)
+      for (int c = 0; c < bw; ++c)
+        if (!disparity[(size_t)r * bw + c].valid) df->d[((size_t)(r + bbox.y0 - df->uly) * df->cols + (c + bbox.x0 - df->ulx)) * 2 + 1] = 0.0f;
   for (size_t i = 0; i < (size_t)bw * bh; ++i) {                                  /* :880-884 */
     out[3 * i + 0] = (float)(disparity[i].dx + p->search_x0);
     out[3 * i + 1] = (float)(disparity[i].dy + p->search_y0);
@@ -982,10 +1032,123 @@ static int prerasterize(const vwo_corr_params* p, const vwo_corr_inputs* in, box
   return 0;
 }
 
+/* Stereo/CorrelationView.cc:273-886, the SGM / MGM / FINAL_MGM branch (:392-595, 700-750, 859-871): one
+ * calc_disparity_sgm per level over the whole (padded) tile, seeded by the previous level's filtered disparity; R->L pass +
+ * consistency check at the levels >= min_consistency_level; the sub-pixel view is made at level 0 BEFORE the check and the
+ * filters, whose invalidations are copied onto it at the end. */
+static int prerasterize_sgm(const vwo_corr_params* p, const vwo_corr_inputs* in, box_t bbox, float* out, int* levels_out, const diff_t* df) {
+  const int bw = bbox.x1 - bbox.x0, bh = bbox.y1 - bbox.y0;
+  const int kx = p->kernel_x, ky = p->kernel_y, hkx = kx / 2, hky = ky / 2;
+  const int ssx = p->search_x1 - p->search_x0, ssy = p->search_y1 - p->search_y0;
+  vwo_corr_params q = *p;
+  q.prefilter_mode = VWO_PREFILTER_NONE;                                          /* CorrelationView.h:96-97 */
+  int levels = vwo_num_levels(&q, bw, bh);
+  if (levels_out) *levels_out = levels;
+  const int up = 1 << levels;
+  pyr_t py;
+  int rc = build_pyramids(&q, in, bbox, levels, &py);
+  if (rc < 0) return -20;
+  if (rc == 0) { memset(out, 0, (size_t)bw * bh * 3 * sizeof(float)); return 0; }
+  vwo_disp_t *disparity = NULL, *disparity_rl = NULL, *prev = NULL, *prev_rl = NULL;
+  int dw = 0, dh = 0, pw = 0, ph = 0, rlw = 0, rlh = 0, prlw = 0, prlh = 0;
+  float* sub = NULL;
+  const int threads = p->sgm_threads > 0 ? p->sgm_threads : 4;
+  const double mem = p->memory_limit_mb > 0 ? p->memory_limit_mb : 6000.0;
+  int err = 0;
+  for (int level = levels; level >= 0 && !err; --level) {
+    const int use_mgm = p->algorithm == 2 || (p->algorithm == 3 && level == 0);    /* :366-367 */
+    const int scaling = 1 << level;
+    free(prev); prev = disparity; pw = dw; ph = dh;                                /* :373-376 */
+    free(prev_rl); prev_rl = disparity_rl; prlw = rlw; prlh = rlh;
+    disparity = NULL; disparity_rl = NULL;
+    dw = py.lm[level].w; dh = py.lm[level].h;
+    const int rox = up * hkx / scaling, roy = up * hky / scaling;
+    const int dsx = ssx / scaling, dsy = ssy / scaling;                            /* :395-396: BBox2i(0,0,w/scaling,h/scaling).size() */
+    box_t zone = box_xywh(0, 0, dw, dh);
+    box_t lr = box_expand(box_shift(zone, rox, roy), hkx, hky);                    /* :404-405 */
+    box_t rr = lr; rr.x1 += dsx; rr.y1 += dsy;                                     /* :406-407 */
+    imgf_t lc = crop_const_f(py.l[level].d, py.l[level].w, py.l[level].h, py.l[level].w, lr);
+    imgf_t rcq = crop_const_f(py.r[level].d, py.r[level].w, py.r[level].h, py.r[level].w, rr);
+    disparity = (vwo_disp_t*)calloc((size_t)lc.w * lc.h + 1, sizeof(vwo_disp_t));
+    int ow = 0, oh = 0;
+    if (level == 0) sub = (float*)calloc((size_t)lc.w * lc.h * 3 + 1, sizeof(float));
+    rc = vwo_calc_disparity_sgm(lc.d, lc.w, lc.h, lc.w, rcq.d, rcq.w, rcq.h, rcq.w, dsx, dsy, kx, p->cost_type, 5, 0, 0, use_mgm,
+                                p->sgm_subpixel_mode, p->sgm_search_buffer_x, p->sgm_search_buffer_y, mem, threads,
+                                py.lm[level].d, py.rm[level].d, py.rm[level].w, py.rm[level].h,
+                                level < levels ? (const int*)prev : NULL, pw, ph, NULL, 0, (int*)disparity, level == 0 ? sub : NULL, &ow, &oh);
+    if (rc || ow != dw || oh != dh) { err = rc ? rc : -60; free(lc.d); free(rcq.d); break; }
+    int check_rl = 0;
+    imgb_t rrm = { NULL, 0, 0 }, lrm = { NULL, 0, 0 };
+    if (p->consistency_threshold >= 0.0f && level >= p->min_consistency_level) {   /* :438-590 */
+      check_rl = 1;
+      box_t llr = box_shift(lr, -dsx, -dsy); llr.x1 += 2 * dsx; llr.y1 += 2 * dsy; /* :453-455 */
+      imgf_t l2 = crop_const_f(py.l[level].d, py.l[level].w, py.l[level].h, py.l[level].w, llr);
+      /* masks of the reversed problem (:496-508), zero edge extension */
+      box_t rmb = box_xywh(0, 0, (rr.x1 - rr.x0) - 2 * hkx, (rr.y1 - rr.y0) - 2 * hky);
+      box_t lmb = box_shift(box_xywh(0, 0, (llr.x1 - llr.x0) - 2 * hkx, (llr.y1 - llr.y0) - 2 * hky), -dsx, -dsy);
+      rrm = crop_b(py.rm[level].d, py.rm[level].w, py.rm[level].h, py.rm[level].w, rmb, 1);
+      lrm = crop_b(py.lm[level].d, py.lm[level].w, py.lm[level].h, py.lm[level].w, lmb, 1);
+      disparity_rl = (vwo_disp_t*)calloc((size_t)rcq.w * rcq.h + 1, sizeof(vwo_disp_t));
+      rc = vwo_calc_disparity_sgm(rcq.d, rcq.w, rcq.h, rcq.w, l2.d, l2.w, l2.h, l2.w, dsx, dsy, kx, p->cost_type, 5, 0, 0, use_mgm,
+                                  p->sgm_subpixel_mode, p->sgm_search_buffer_x, p->sgm_search_buffer_y, mem, threads,
+                                  rrm.d, lrm.d, lrm.w, lrm.h, level < levels ? (const int*)prev_rl : NULL, prlw, prlh, NULL, 0,
+                                  (int*)disparity_rl, NULL, &rlw, &rlh);
+      free(l2.d);
+      if (rc) { err = rc; free(lc.d); free(rcq.d); free(rrm.d); free(lrm.d); break; }
+      for (size_t i = 0; i < (size_t)rlw * rlh; ++i) { disparity_rl[i].dx -= dsx; disparity_rl[i].dy -= dsy; }      /* :548-549 */
+      if (level == 0 && df && df->d)
+        consistency_check_diff(disparity, dw, dh, dw, disparity_rl, rlw, rlh, p->consistency_threshold, df->d, df->cols,
+                               bbox.x0 - df->ulx, bbox.y0 - df->uly);
+      else
+        vwo_cross_corr_consistency_check(disparity, dw, dh, dw, disparity_rl, rlw, rlh, p->consistency_threshold);
+      for (size_t i = 0; i < (size_t)rlw * rlh; ++i) { disparity_rl[i].dx += dsx; disparity_rl[i].dy += dsy; }      /* :586 */
+    }
+    free(lc.d); free(rcq.d);
+    if (p->filter_half_kernel > 0) {                                              /* :713-744 */
+      const int fh = p->filter_half_kernel;
+      vwo_disp_t* t = (vwo_disp_t*)malloc((size_t)dw * dh * sizeof(vwo_disp_t));
+      if (level != 0) vwo_disparity_cleanup_using_thresh(disparity, dw, dh, fh, fh, 3.0, 0.5, t);
+      else            vwo_rm_outliers_using_thresh(disparity, dw, dh, fh, fh, 3.0, 0.5, t);
+      vwo_disparity_mask(t, dw, dh, py.lm[level].d, py.rm[level].d, py.rm[level].w, py.rm[level].h, disparity);
+      free(t);
+      if (level != 0 && check_rl) {
+        vwo_disp_t* t2 = (vwo_disp_t*)malloc((size_t)rlw * rlh * sizeof(vwo_disp_t));
+        vwo_disparity_cleanup_using_thresh(disparity_rl, rlw, rlh, fh, fh, 3.0, 0.5, t2);
+        vwo_disparity_mask(t2, rlw, rlh, rrm.d, lrm.d, lrm.w, lrm.h, disparity_rl);
+        free(t2);
+      }
+    }
+    vwo_disparity_blob_filter(disparity, dw, dh, p->blob_filter_area / scaling);     /* :747-749 */
+    if (check_rl && level != 0) vwo_disparity_blob_filter(disparity_rl, rlw, rlh, p->blob_filter_area / scaling);
+    free(rrm.d); free(lrm.d);
+  }
+  if (!err && (dw != bw || dh != bh)) err = -50;
+  if (!err) {
+    if (df && df->d)                                                              /* :848-857 */
+      for (int r = 0; r < bh; ++r)
+        for (int c = 0; c < bw; ++c)
+          if (!disparity[(size_t)r * bw + c].valid) df->d[((size_t)(r + bbox.y0 - df->uly) * df->cols + (c + bbox.x0 - df->ulx)) * 2 + 1] = 0.0f;
+    for (size_t i = 0; i < (size_t)bw * bh; ++i) {                                /* :859-871: PixelMask sum keeps the child values */
+      out[3 * i + 0] = sub[3 * i + 0] + (float)p->search_x0;
+      out[3 * i + 1] = sub[3 * i + 1] + (float)p->search_y0;
+      out[3 * i + 2] = (sub[3 * i + 2] != 0.0f && disparity[i].valid) ? 1.0f : 0.0f;
+    }
+  }
+  free(disparity); free(disparity_rl); free(prev); free(prev_rl); free(sub); pyr_free(&py);
+  return err;
+}
+
 /* PyramidCorrelationView::rasterize, Stereo/CorrelationView.h:123-133 */
 int vwo_pyramid_correlate_rasterize(const vwo_corr_params* p, const vwo_corr_inputs* in,
                                     int bx0, int by0, int bx1, int by1,
                                     float* dest, int dest_pitch, int* levels_out) {
+  return vwo_pyramid_correlate_rasterize_ex(p, in, bx0, by0, bx1, by1, dest, dest_pitch, levels_out, NULL, 0, 0, 0, 0);
+}
+int vwo_pyramid_correlate_rasterize_ex(const vwo_corr_params* p, const vwo_corr_inputs* in,
+                                       int bx0, int by0, int bx1, int by1, float* dest, int dest_pitch, int* levels_out,
+                                       float* diff, int diff_cols, int diff_rows, int region_ul_x, int region_ul_y) {
+  const diff_t dfv = { diff, diff_cols, diff_rows, region_ul_x, region_ul_y };
+  const diff_t* df = diff ? &dfv : NULL;
   if (bx1 <= bx0 || by1 <= by0) return -1;
   box_t bbox = { bx0, by0, bx1, by1 };
   box_t proc = bbox;
@@ -993,7 +1156,7 @@ int vwo_pyramid_correlate_rasterize(const vwo_corr_params* p, const vwo_corr_inp
   int pw = proc.x1 - proc.x0, ph = proc.y1 - proc.y0;
   float* buf = (float*)malloc((size_t)pw * ph * 3 * sizeof(float));
   if (!buf) return -2;
-  int rc = prerasterize(p, in, proc, buf, levels_out);
+  int rc = prerasterize(p, in, proc, buf, levels_out, df);
   if (rc == 0) {
     int ox = bbox.x0 - proc.x0, oy = bbox.y0 - proc.y0;
     for (int y = 0; y < by1 - by0; ++y)

@@ -95,6 +95,13 @@ typedef struct {
   int32_t filter_half_kernel;
   int32_t max_pyramid_levels;
   int32_t collar_size;
+  /* the rest of the constructor (CorrelationView.h:60-69) */
+  int32_t algorithm;                 /* CorrelationAlgorithm: 0 BM, 1 SGM, 2 MGM, 3 FINAL_MGM */
+  int32_t sgm_subpixel_mode;         /* SgmSubpixelMode (SGM.h:93-99) */
+  int32_t sgm_search_buffer_x, sgm_search_buffer_y;
+  int32_t blob_filter_area;
+  int32_t sgm_threads;               /* vw_settings().default_num_threads() of the SGM memory estimate */
+  double  memory_limit_mb;
 } vwo_corr_params;
 
 typedef struct {
@@ -110,6 +117,26 @@ typedef struct {
 int vwo_pyramid_correlate_rasterize(const vwo_corr_params* p, const vwo_corr_inputs* in,
                                     int bx0, int by0, int bx1, int by1,
                                     float* dest, int dest_pitch, int* levels_out);
+
+/* ... with the optional lr_disp_diff output (CorrelationView.h:67-68, .cc:276-283,848-857): diff is a caller-owned
+ * diff_cols x diff_rows image of PixelMask<float> = {value, valid} float pairs whose (0,0) sits at region_ul in image
+ * coordinates; it receives max(|dx_lr + dx_rl|, |dy_lr + dy_rl|) at the pixels that pass the L/R check (level 0) and is
+ * invalidated where the final disparity is invalid.  Returns -1 (ArgumentErr) when the processed box is not inside. */
+int vwo_pyramid_correlate_rasterize_ex(const vwo_corr_params* p, const vwo_corr_inputs* in,
+                                       int bx0, int by0, int bx1, int by1, float* dest, int dest_pitch, int* levels_out,
+                                       float* diff, int diff_cols, int diff_rows, int region_ul_x, int region_ul_y);
+
+/* PyramidCorrelationView::disparity_blob_filter (CorrelationView.cc:242-271; BlobIndexThreaded, Image/BlobIndex.h:385-454;
+ * ErodeView, Image/ErodeView.h:196-218): 8-connected blobs of valid pixels with at most `area` pixels become {0,0,invalid}. */
+int vwo_disparity_blob_filter(vwo_disp_t* d, int w, int h, int area);
+
+/* the whole of calc_disparity_sgm (vw_sgm_oracle.c) */
+int vwo_calc_disparity_sgm(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
+                           int search_x, int search_y, int kernel_size, int cost_type, int ternary_threshold, int p1, int p2, int use_mgm,
+                           int subpixel_mode, int buffer_x, int buffer_y, double memory_limit_mb, int threads,
+                           const uint8_t* lmask, const uint8_t* rmask, int rmw, int rmh, const int* prev, int pw, int ph,
+                           int* bounds_io, int use_given_bounds, int* out, float* out_sub, int* out_w, int* out_h);
+uint64_t vwo_census_value(const uint8_t* img, int w, int col, int row, int k, int ternary, int thr);
 
 /* Debug/intermediate taps for kernel-level parity tests: build the per-tile pyramids
  * exactly as build_image_pyramids does (Stereo/CorrelationView.cc:67-239).

@@ -56,6 +56,39 @@ static void u8_convert(const float* in, int w, int h, int pitch, uint8_t* out) {
 static const int C9_COLS[32] = {0, 4, 8, 1, 3, 5, 7, 2, 4, 6, 1, 4, 7, 0, 2, 3, 5, 6, 8, 1, 4, 7, 2, 4, 6, 1, 3, 5, 7, 0, 4, 8};
 static const int C9_ROWS[32] = {0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8};
 
+/* ternary census (Image/CensusTransform.h:167-340): 2 bits per neighbour: 00 below centre - t, 01 inside the band, 11 above
+ * centre + t; 3x3 / 5x5: all neighbours in reverse raster order; 7x7: the custom 32-position pattern (:222-275); 9x9: the
+ * same 32 positions as the binary 9x9 census (:277-340).  The reference stores the signatures in the integer type the BINARY
+ * census of the same kernel uses, so the 48-bit ternary 5x5 signature is truncated to 32 bits (SGM.cc:1789-1803) -- kept. */
+static const int T7_COLS[32] = {0, 2, 3, 4, 6, 1, 3, 5, 0, 2, 3, 4, 6, 0, 1, 2, 4, 5, 6, 0, 2, 3, 4, 6, 1, 3, 5, 0, 2, 3, 4, 6};
+static const int T7_ROWS[32] = {0, 0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 6, 6, 6, 6, 6};
+static uint64_t census_value_ternary(const uint8_t* img, int w, int col, int row, int k, int thr) {
+  const int hk = (k - 1) / 2;
+  const int center = img[(size_t)row * w + col];
+  const int lo = center - thr, hi = center + thr;
+  uint64_t out = 0, addend = 1;
+  if (k == 7 || k == 9) {
+    const int* cs = k == 9 ? C9_COLS : T7_COLS;
+    const int* rs = k == 9 ? C9_ROWS : T7_ROWS;
+    for (int i = 0; i < 32; ++i) {
+      const int val = img[(size_t)(row + rs[i] - hk) * w + (col + cs[i] - hk)];
+      if (val >= lo) { out += addend; if (val > hi) out += addend * 2; }
+      addend *= 4;
+    }
+    return out;
+  }
+  for (int r = row + hk; r >= row - hk; --r)
+    for (int c = col + hk; c >= col - hk; --c) {
+      if (r == row && c == col) continue;
+      const int val = img[(size_t)r * w + c];
+      if (val >= lo) { out += addend; if (val > hi) out += addend * 2; }
+      addend *= 4;
+    }
+  if (k == 5) out &= 0xFFFFFFFFull;        /* ImageView<uint32> (SGM.cc:1789-1790) */
+  if (k == 3) out &= 0xFFFFull;            /* uint16 (:1762) -- 16 bits, nothing is lost */
+  return out;
+}
+uint64_t vwo_census_value(const uint8_t* img, int w, int col, int row, int k, int ternary, int thr);
 static uint64_t census_value(const uint8_t* img, int w, int col, int row, int k) {
   const int hk = (k - 1) / 2;
   const int center = img[(size_t)row * w + col];
@@ -74,6 +107,9 @@ static uint64_t census_value(const uint8_t* img, int w, int col, int row, int k)
       addend *= 2;
     }
   return out;
+}
+uint64_t vwo_census_value(const uint8_t* img, int w, int col, int row, int k, int ternary, int thr) {
+  return ternary ? census_value_ternary(img, w, col, row, k, thr) : census_value(img, w, col, row, k);
 }
 static inline int popcount64(uint64_t v) { return __builtin_popcountll(v); }
 
@@ -198,6 +234,35 @@ static double subpixel_offset(accum_t prev, accum_t center, accum_t next, int le
     default: value = linear_fit(x); break;
   }
   return (value - 0.5) * mult;
+}
+
+/* ParabolaFit2d::find_peak (SGMAssist.h:36-134): the 6x9 pseudo-inverse is held in a Matrix<FLOAT,6,9> (:139) and multiplied
+ * with the double z vector; the raw offset passes through a Vector2f (:116-117) before the erf correction. */
+static int parabola_peak(double z1, double z2, double z3, double z4, double z5, double z6, double z7, double z8, double z9, double* dx, double* dy) {
+  static const double pd[54] = {
+     1.0/6, -1.0/3,  1.0/6,  1.0/6, -1.0/3,  1.0/6,   1.0/6, -1.0/3,  1.0/6,
+     1.0/6,  1.0/6,  1.0/6, -1.0/3, -1.0/3, -1.0/3,   1.0/6,  1.0/6,  1.0/6,
+     1.0/4,    0.0, -1.0/4,    0.0,    0.0,    0.0,  -1.0/4,    0.0,  1.0/4,
+    -1.0/6,    0.0,  1.0/6, -1.0/6,    0.0,  1.0/6,  -1.0/6,    0.0,  1.0/6,
+    -1.0/6, -1.0/6, -1.0/6,    0.0,    0.0,    0.0,   1.0/6,  1.0/6,  1.0/6,
+    -1.0/9,  2.0/9, -1.0/9,  2.0/9,   5.0/9, 2.0/9,  -1.0/9,  2.0/9, -1.0/9 };
+  const double z[9] = {z1, z2, z3, z4, z5, z6, z7, z8, z9};
+  double vals[6];
+  for (int i = 0; i < 6; ++i) {
+    double acc = 0.0;                                              /* Math/Matrix.h product: sum of m(i,j) * v(j) in double */
+    for (int j = 0; j < 9; ++j) acc += (double)(float)pd[i * 9 + j] * z[j];
+    vals[i] = acc;
+  }
+  const double denom = 4.0 * vals[0] * vals[1] - (vals[2] * vals[2]);
+  if (fabs(denom) < 0.01) return 0;
+  const float ox = (float)((vals[2] * vals[4] - 2.0 * vals[1] * vals[3]) / denom);
+  const float oy = (float)((vals[2] * vals[3] - 2.0 * vals[0] * vals[4]) / denom);
+  const double sX = 0.34574, sY = 0.38944;
+  double x = erf(ox / (sX * sqrt(2.0))) / 2.0, y = erf(oy / (sY * sqrt(2.0))) / 2.0;
+  const double nrm = sqrt(x * x + y * y);
+  if (nrm >= 0.5) { const double scale = nrm / 0.5; x /= scale; y /= scale; }
+  *dx = x; *dy = y;
+  return 1;
 }
 
 static int sgm_core(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
@@ -431,6 +496,8 @@ static void mgm_sweep(const SgmB* s, const MgmTask* t, accum_t* path /* ragged, 
     }
 }
 
+/* cost type of the current call: 0 = CENSUS_TRANSFORM, 1 = TERNARY_CENSUS_TRANSFORM (+ its threshold) */
+static __thread int t_ternary = 0, t_ternary_thr = 5;
 static int sgm_bounds_core(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
                            int search_x, int search_y, int kernel_size, int p1, int p2, int subpixel_mode, const int* bounds,
                            int* out, float* out_sub, int* out_w, int* out_h, int use_mgm);
@@ -452,9 +519,15 @@ static int sgm_bounds_core(const float* left_f, int lw, int lh, int lpitch, cons
                            int* out, float* out_sub, int* out_w, int* out_h, int use_mgm) {
   if (kernel_size != 3 && kernel_size != 5 && kernel_size != 7 && kernel_size != 9) return -2;
   if (search_x < 0 || search_y < 0 || !bounds) return -1;
-  if (out_sub && (subpixel_mode == 1 || subpixel_mode < 0 || subpixel_mode > 5)) return -2;
-  if (p1 <= 0) p1 = kernel_size == 3 ? 3 : kernel_size == 5 ? 15 : kernel_size == 7 ? 30 : 20;
-  if (p2 <= 0) p2 = kernel_size == 3 ? 70 : kernel_size == 5 ? 750 : kernel_size == 7 ? 1500 : 1000;
+  if (out_sub && (subpixel_mode < 0 || subpixel_mode > 5)) return -2;
+  const int ternary = t_ternary, tern_thr = t_ternary_thr;
+  if (!ternary) {                                                                           /* set_parameters (SGM.cc:106-157) */
+    if (p1 <= 0) p1 = kernel_size == 3 ? 3 : kernel_size == 5 ? 15 : kernel_size == 7 ? 30 : 20;
+    if (p2 <= 0) p2 = kernel_size == 3 ? 70 : kernel_size == 5 ? 750 : kernel_size == 7 ? 1500 : 1000;
+  } else {
+    if (p1 <= 0) p1 = kernel_size == 3 ? 12 : kernel_size == 5 ? 30 : 40;
+    if (p2 <= 0) p2 = kernel_size == 3 ? 600 : kernel_size == 5 ? 1500 : 2000;
+  }
   const int hk = (kernel_size - 1) / 2;
   SgmB s;
   s.ndx = search_x + 1; s.ndy = search_y + 1; s.nd = s.ndx * s.ndy; s.p1 = p1; s.p2 = p2; s.lw = lw;
@@ -484,8 +557,8 @@ static int sgm_bounds_core(const float* left_f, int lw, int lh, int lpitch, cons
   const int clw = lw - 2 * hk, clh = lh - 2 * hk, crw = rw - 2 * hk, crh = rh - 2 * hk;
   uint64_t* lc = (uint64_t*)malloc((size_t)clw * clh * 8);
   uint64_t* rc = (uint64_t*)malloc((size_t)crw * crh * 8);
-  for (int r = 0; r < clh; ++r) for (int c = 0; c < clw; ++c) lc[(size_t)r * clw + c] = census_value(left, lw, c + hk, r + hk, kernel_size);
-  for (int r = 0; r < crh; ++r) for (int c = 0; c < crw; ++c) rc[(size_t)r * crw + c] = census_value(right, rw, c + hk, r + hk, kernel_size);
+  for (int r = 0; r < clh; ++r) for (int c = 0; c < clw; ++c) lc[(size_t)r * clw + c] = vwo_census_value(left, lw, c + hk, r + hk, kernel_size, ternary, tern_thr);
+  for (int r = 0; r < crh; ++r) for (int c = 0; c < crw; ++c) rc[(size_t)r * crw + c] = vwo_census_value(right, rw, c + hk, r + hk, kernel_size, ternary, tern_thr);
   cost_t* cost = (cost_t*)malloc(total);
   accum_t* accum = (accum_t*)calloc(total, sizeof(accum_t));
   size_t ci = 0;
@@ -570,8 +643,15 @@ static int sgm_bounds_core(const float* left_f, int lw, int lh, int lpitch, cons
         if (dy == b[1]) { y_up = 0; tb = 1; }
         if (dy == b[3]) { y_down = 0; bb = 1; }
         const accum_t* av = accum + starts[pix];
-        const double ddx = subpixel_offset(av[min_index + x_left], av[min_index], av[min_index + x_right], lb, rb, subpixel_mode);
-        const double ddy = subpixel_offset(av[min_index + y_up], av[min_index], av[min_index + y_down], tb, bb, subpixel_mode);
+        double ddx, ddy;
+        if (subpixel_mode == 1) {                                          /* SUBPIXEL_PARABOLA (:1566-1576) */
+          if (!parabola_peak(av[min_index + x_left + y_up], av[min_index + y_up], av[min_index + x_right + y_up], av[min_index + x_left],
+                             av[min_index], av[min_index + x_right], av[min_index + x_left + y_down], av[min_index + y_down],
+                             av[min_index + x_right + y_down], &ddx, &ddy)) { f[0] = (float)dx; f[1] = (float)dy; continue; }
+        } else {
+          ddx = subpixel_offset(av[min_index + x_left], av[min_index], av[min_index + x_right], lb, rb, subpixel_mode);
+          ddy = subpixel_offset(av[min_index + y_up], av[min_index], av[min_index + y_down], tb, bb, subpixel_mode);
+        }
         f[0] = (float)(dx + ddx); f[1] = (float)(dy + ddy);
       }
   }
@@ -694,4 +774,76 @@ int vwo_sgm_disp_bounds(const int* prev, int pw, int ph, const uint8_t* lmask, c
   free(full);
   area /= num_pixels;
   return !(area <= 0 || percent_masked >= 100);                                          /* (:664-666) */
+}
+
+/* ------------------------------------------------------------------------------------------------------------------------
+ * The whole of vw::stereo::calc_disparity_sgm (SGM.cc:167-230) with its optional arguments: cost type (3 = CENSUS_TRANSFORM,
+ * 4 = TERNARY_CENSUS_TRANSFORM, CostFunctions.h:143-149; anything else -> -4, the NoImplErr of :1888-1892), SGM / MGM,
+ * sub-pixel mode, search buffer, masks, previous disparity and the memory-limit retry loop of populate_disp_bound_image
+ * (:476-497; calc_main_buf_size :677-731 with `threads` = vw_settings().default_num_threads()).  bounds_io != NULL and
+ * use_given_bounds != 0: take the boxes from there; otherwise the derived boxes are written there (if not NULL).
+ * ---------------------------------------------------------------------------------------------------------------------- */
+static int mem_fits(size_t main_buf, int ow, int oh, int search_x, int search_y, int use_mgm, int threads, double limit_mb) {
+  if (main_buf < 6) main_buf = 6;
+  const size_t nd = (size_t)(search_x + 1) * (search_y + 1);
+  size_t small;
+  if (use_mgm) {                                                    /* (:709-713), MultiAccumRowBuffer::multi_buf_size */
+    size_t v = (size_t)oh * nd, h = (size_t)ow * nd;
+    if (v > main_buf) v = main_buf;
+    if (h > main_buf) h = main_buf;
+    small = v * 4 + h * 4;
+  } else {                                                          /* OneLineBuffer::one_buf_size (SGMAssist.h:565-583) */
+    const int line = (int)(sqrt((double)(ow * ow + oh * oh)) + 1);
+    size_t one = (size_t)line * nd;
+    if (one > main_buf) one = main_buf;
+    small = one * (size_t)threads;
+  }
+  const double mb = 1024.0 * 1024.0;
+  return (double)main_buf * (3.0 / mb) + (double)small * (2.0 / mb) <= limit_mb;
+}
+
+int vwo_calc_disparity_sgm(const float* left_f, int lw, int lh, int lpitch, const float* right_f, int rw, int rh, int rpitch,
+                           int search_x, int search_y, int kernel_size, int cost_type, int ternary_threshold, int p1, int p2, int use_mgm,
+                           int subpixel_mode, int buffer_x, int buffer_y, double memory_limit_mb, int threads,
+                           const uint8_t* lmask, const uint8_t* rmask, int rmw, int rmh, const int* prev, int pw, int ph,
+                           int* bounds_io, int use_given_bounds, int* out, float* out_sub, int* out_w, int* out_h) {
+  if (cost_type != 3 && cost_type != 4) return -4;
+  if (kernel_size != 3 && kernel_size != 5 && kernel_size != 7 && kernel_size != 9) return -4;
+  if (search_x < 0 || search_y < 0) return -1;
+  const int hk = (kernel_size - 1) / 2;
+  int max_row = (lh - 1 - hk) < (rh - 1 - (hk + search_y)) ? (lh - 1 - hk) : (rh - 1 - (hk + search_y));
+  int max_col = (lw - 1 - hk) < (rw - 1 - (hk + search_x)) ? (lw - 1 - hk) : (rw - 1 - (hk + search_x));
+  if (max_row > lh - 1) max_row = lh - 1;
+  if (max_col > lw - 1) max_col = lw - 1;
+  const int ow = max_col - hk + 1, oh = max_row - hk + 1;
+  *out_w = ow > 0 ? ow : 0; *out_h = oh > 0 ? oh : 0;
+  if (ow <= 0 || oh <= 0) return 0;
+  const size_t npix = (size_t)ow * oh;
+  int* bounds = (int*)malloc(npix * 4 * sizeof(int));
+  int ok = 1;
+  if (use_given_bounds && bounds_io) memcpy(bounds, bounds_io, npix * 4 * sizeof(int));
+  else {
+    ok = 0;
+    for (int level = 0; level <= 3 && !ok; ++level) {
+      const int rc = vwo_sgm_disp_bounds(prev, pw, ph, lmask, rmask, rmw, rmh, ow, oh, search_x, search_y, buffer_x, buffer_y, level, bounds);
+      if (rc < 0) { free(bounds); return rc; }
+      size_t total = 0;
+      for (size_t i = 0; i < npix; ++i) total += (size_t)nb_disp(bounds + 4 * i);
+      ok = mem_fits(total, ow, oh, search_x, search_y, use_mgm, threads, memory_limit_mb);
+    }
+    if (bounds_io) memcpy(bounds_io, bounds, npix * 4 * sizeof(int));
+  }
+  int rc = 0;
+  if (!ok) {                                                        /* invalidate_mask(disparity) (:2430-2436) */
+    memset(out, 0, npix * 3 * sizeof(int));
+    if (out_sub) memset(out_sub, 0, npix * 3 * sizeof(float));
+  } else {
+    t_ternary = cost_type == 4; t_ternary_thr = ternary_threshold;
+    int w2, h2;
+    rc = sgm_bounds_core(left_f, lw, lh, lpitch, right_f, rw, rh, rpitch, search_x, search_y, kernel_size, p1, p2, subpixel_mode, bounds, out, out_sub,
+                         &w2, &h2, use_mgm);
+    t_ternary = 0; t_ternary_thr = 5;
+  }
+  free(bounds);
+  return rc;
 }

@@ -36,8 +36,13 @@ int main() {
     catch (ArgumentErr const&) { threw = true; }
     if (!threw) { std::printf("FAIL: even kernel accepted\n"); return 1; }
 
+    // all 24 positional arguments, in the reference's order (CorrelationView.h:195-218)
+    ImageView<PixelMask<float>> lr_diff(W, H);
     B200PyramidCorrelationView view = b200_pyramid_correlate(left, right, lmask, rmask, PREFILTER_NONE, 0.f, search, kernel,
-                                                             SQUARED_DIFFERENCE, 0, 0.0, 2.f, 0, 3, 3);
+                                                             SQUARED_DIFFERENCE, 0, 0.0, 2.f, 0, 3, 3, VW_CORRELATION_BM, 0,
+                                                             SemiGlobalMatcher::SUBPIXEL_LC_BLEND, Vector2i(2, 2), size_t(6000), 0,
+                                                             &lr_diff, Vector2i(0, 0), false);
+    { B200PyramidCorrelationView::pixel_accessor acc = view.origin(); acc.next_col(); acc.advance(1, 1); (void)acc; }
     if (view.cols() != W || view.rows() != H || view.planes() != 1) { std::printf("FAIL: dims\n"); return 1; }
     threw = false;
     try { view(0, 0); } catch (NoImplErr const&) { threw = true; }
@@ -55,10 +60,12 @@ int main() {
     vwo_corr_inputs in = {reinterpret_cast<const float*>(left.data()), W, H, W, reinterpret_cast<const float*>(right.data()), W, H, W,
                           lmask.data(), W, rmask.data(), W};
     long bad = 0, valid = 0;
+    std::vector<float> ref_diff(size_t(W) * H * 2, 0.f);
     for (size_t i = 0; i < boxes.size(); ++i) {
       const BBox2i& b = boxes[i];
       std::vector<float> ref(size_t(b.width()) * b.height() * 3);
-      if (vwo_pyramid_correlate_rasterize(&p, &in, b.min()[0], b.min()[1], b.max()[0], b.max()[1], ref.data(), b.width(), nullptr)) return 1;
+      if (vwo_pyramid_correlate_rasterize_ex(&p, &in, b.min()[0], b.min()[1], b.max()[0], b.max()[1], ref.data(), b.width(), nullptr,
+                                             ref_diff.data(), W, H, 0, 0)) return 1;
       for (int y = 0; y < b.height(); ++y)
         for (int x = 0; x < b.width(); ++x) {
           const PixelMask<Vector2f>& g = tiles[i](x, y);
@@ -67,8 +74,16 @@ int main() {
           if (is_valid(g)) ++valid;
         }
     }
-    std::printf("shim: %ld mismatches, %ld valid of %d\n", bad, valid, W * H);
-    if (bad) return 1;
+    long dvalid = 0;
+    for (int y = 0; y < H; ++y)                                     // the lr_disp_diff side output (CorrelationView.cc:848-857)
+      for (int x = 0; x < W; ++x) {
+        const PixelMask<float>& g = lr_diff(x, y);
+        const float* r = &ref_diff[(size_t(y) * W + x) * 2];
+        if (g.child() != r[0] || (is_valid(g) ? 1.f : 0.f) != r[1]) ++bad;
+        if (is_valid(g)) ++dvalid;
+      }
+    std::printf("shim: %ld mismatches, %ld valid of %d, %ld lr_disp_diff pixels\n", bad, valid, W * H, dvalid);
+    if (bad || !dvalid) return 1;
 
     // sub-pixel refinement through the second shim (Stereo/ParabolaSubpixelView.h:28-117)
     ImageView<PixelMask<Vector2f>> disp = crop(view, BBox2i(0, 0, W, H));

@@ -59,8 +59,10 @@ def test_argument_validation(vwb):
     m = np.full((11, 11), 255, np.uint8)
     with pytest.raises(vwb.ArgumentErr):       # even kernel in the view
         vwb.PyramidCorrelationView(l, l, m, m, 0, 0, (0, 0, 4, 4), (4, 4), 0, 0, 0.0, -1, 0, 0, 0)
-    with pytest.raises(vwb.NoImplErr):         # SGM is not this engine's algorithm
-        vwb.PyramidCorrelationView(l, l, m, m, 0, 0, (0, 0, 4, 4), (5, 5), 0, 0, 0.0, -1, 0, 0, 0, algorithm=1)
+    with pytest.raises(vwb.ArgumentErr):       # unknown algorithm / cost type
+        vwb.PyramidCorrelationView(l, l, m, m, 0, 0, (0, 0, 4, 4), (5, 5), 0, 0, 0.0, -1, 0, 0, 0, algorithm=7)
+    with pytest.raises(vwb.ArgumentErr):
+        vwb.PyramidCorrelationView(l, l, m, m, 0, 0, (0, 0, 4, 4), (5, 5), 9, 0, 0.0, -1, 0, 0, 0)
 
 
 def test_no_device_means_loud_failure(vwb):

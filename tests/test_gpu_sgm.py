@@ -145,3 +145,97 @@ def test_sgm_memory_limit_retry(vwb, oracle):
     assert np.array_equal(got, totals[target][1]), target
     got = vwb.sgm_disp_bounds((oh, ow), search, buf, prev_disparity=prev, conserve_level=-1, memory_limit_mb=1e9, assumed_threads=1)
     assert np.array_equal(got, totals[0][1])
+
+
+@pytest.mark.parametrize("kernel", [3, 5, 7, 9])
+def test_sgm_ternary_census_and_parabola(vwb, oracle, kernel):
+    """TERNARY_CENSUS_TRANSFORM costs (incl. the 32-bit truncation of the 5x5 signature) and the 2-D parabola sub-pixel mode"""
+    search = (10, 7)
+    left, right = _pair(60 + kernel, 110, 90, search, (3, 2))
+    ri, rf, rb = oracle.calc_disparity_sgm(left, right, search, kernel, cost_type=4, subpixel_mode=1)
+    gi, gf = vwb.calc_disparity_sgm_ex(vwb.TERNARY_CENSUS_TRANSFORM, left, right, search, kernel, subpixel_mode=vwb.SUBPIXEL_PARABOLA)
+    assert np.array_equal(gi, ri), int((gi != ri).any(-1).sum())
+    assert np.abs(gf - rf).max() <= 1e-5
+    with pytest.raises(vwb.NoImplErr):
+        vwb.calc_disparity_sgm_ex(vwb.ABSOLUTE_DIFFERENCE, left, right, search, kernel)
+
+
+def test_blob_filter_matches_oracle(vwb, oracle):
+    """disparity_blob_filter through the view: BM, one level, blob_filter_area > 0"""
+    from visionworkbench_b200.synth import make_pair
+    search, kernel = (-6, -4, 7, 5), (7, 7)
+    left, right, lm, rm, _ = make_pair(200, 160, search, seed=12, dropout=0.1)
+    rng = np.random.default_rng(1)
+    lm[rng.random(lm.shape) < 0.35] = 0                      # many small islands of valid pixels
+    for area in (3, 25):
+        view = vwb.pyramid_correlate(left, right, lm, rm, vwb.PREFILTER_NONE, 0.0, search, kernel, vwb.ABSOLUTE_DIFFERENCE, 0, 0.0, 2.0, 0, 2, 2,
+                                     blob_filter_area=area)
+        got = view.rasterize(None, (10, 8, 190, 150))
+        p = oracle.make_params(search, kernel, cost=0, consistency_threshold=2.0, filter_half_kernel=2, max_pyramid_levels=2, blob_filter_area=area)
+        ref = oracle.pyramid_correlate(p, left, right, lm, rm, bbox=(10, 8, 190, 150))
+        assert np.array_equal(got, ref), (area, int((got != ref).any(-1).sum()))
+    p0 = oracle.make_params(search, kernel, cost=0, consistency_threshold=2.0, filter_half_kernel=2, max_pyramid_levels=2)
+    assert not np.array_equal(ref, oracle.pyramid_correlate(p0, left, right, lm, rm, bbox=(10, 8, 190, 150)))   # the filter did something
+
+
+def test_lr_disp_diff_output(vwb, oracle):
+    """lr_disp_diff (CorrelationView.cc:276-283, 669-676, 848-857): two tiles write disjoint windows of one image"""
+    from visionworkbench_b200.synth import make_pair
+    search, kernel = (-5, -3, 6, 4), (7, 7)
+    left, right, lm, rm, _ = make_pair(220, 150, search, seed=3)
+    ul = (16, 8)
+    gd = np.zeros((120, 180, 2), np.float32); rd = np.zeros((120, 180, 2), np.float32)
+    gd[..., 0] = -7.0; rd[..., 0] = -7.0                      # untouched pixels keep their content
+    args = (vwb.PREFILTER_NONE, 0.0, search, kernel, vwb.ABSOLUTE_DIFFERENCE, 0, 0.0, 1.0, 0, 2, 1)
+    view = vwb.pyramid_correlate(left, right, lm, rm, *args, lr_disp_diff=gd, region_ul=ul)
+    p = oracle.make_params(search, kernel, cost=0, consistency_threshold=1.0, filter_half_kernel=2, max_pyramid_levels=1)
+    for bbox in [(20, 10, 100, 100), (100, 10, 190, 120)]:
+        got = view.rasterize(None, bbox)
+        ref = oracle.pyramid_correlate(p, left, right, lm, rm, bbox=bbox, lr_disp_diff=rd, region_ul=ul)
+        assert np.array_equal(got, ref)
+    assert np.array_equal(gd, rd)
+    assert (gd[..., 1] == 1).sum() > 1000 and (gd[..., 0] == -7.0).sum() > 1000
+    with pytest.raises(vwb.ArgumentErr):
+        view.rasterize(None, (0, 0, 64, 64))                   # not inside the diff image
+
+
+@pytest.mark.parametrize("algorithm,cost,levels,thr,minlev,fhk,mode", [
+    (1, 3, 2, 2.0, 0, 3, 5),        # SGM, census, R->L check at every level, filters, lc_blend
+    (1, 3, 3, 1.0, 2, 0, 2),        # check only at the coarse levels, no filters, linear sub-pixel
+    (2, 3, 1, -1.0, 0, 2, 1),       # MGM, no check, parabola
+    (3, 4, 2, 2.0, 0, 2, 4),        # FINAL_MGM, ternary census, cosine
+    (1, 3, 0, 2.0, 0, 3, 0),        # single level, no sub-pixel
+])
+def test_view_sgm_branch(vwb, oracle, algorithm, cost, levels, thr, minlev, fhk, mode):
+    """PyramidCorrelationView with algorithm != BM (CorrelationView.cc:392-595): per-level calc_disparity_sgm seeded by the
+    previous level, R->L + consistency check, filters, sub-pixel view: integer part bit-identical, floats within 1e-5."""
+    from visionworkbench_b200.synth import make_pair
+    search, kernel = (-9, -6, 10, 7), (5, 5)
+    left, right, lm, rm, _ = make_pair(260, 200, search, seed=40 + algorithm, bits=8, dropout=0.04)
+    view = vwb.pyramid_correlate(left, right, lm, rm, vwb.PREFILTER_LOG, 1.4, search, kernel, cost, 0, 0.0, thr, minlev, fhk, levels, algorithm, 0,
+                                 mode, (2, 2), 6000, 4 if algorithm == 3 else 0)
+    p = oracle.make_params(search, kernel, cost=cost, prefilter_mode=1, prefilter_width=1.4, consistency_threshold=thr, min_consistency_level=minlev,
+                           filter_half_kernel=fhk, max_pyramid_levels=levels, algorithm=algorithm, sgm_subpixel_mode=mode,
+                           blob_filter_area=4 if algorithm == 3 else 0)
+    for bbox in [(0, 0, 260, 200), (33, 21, 200, 150)]:
+        got = view.rasterize(None, bbox)
+        ref = oracle.pyramid_correlate(p, left, right, lm, rm, bbox=bbox)
+        assert np.array_equal(got[..., 2], ref[..., 2]), f"validity differs at {int((got[..., 2] != ref[..., 2]).sum())} pixels"
+        assert np.abs(got - ref).max() <= 1e-5, float(np.abs(got - ref).max())
+        assert np.array_equal(np.floor(got[..., :2] + 0.5), np.floor(ref[..., :2] + 0.5))
+        assert (ref[..., 2] == 1).mean() > 0.5
+    with pytest.raises(vwb.ArgumentErr):                       # SGM with a block-matching cost type (SGM.cc:1888-1892 via :221-226)
+        vwb.pyramid_correlate(left, right, lm, rm, 0, 0.0, search, kernel, 0, 0, 0.0, thr, minlev, fhk, levels, algorithm).rasterize(None, (0, 0, 64, 64))
+
+
+def test_view_prerasterize_ignores_collar(vwb, oracle):
+    """prerasterize(bbox) processes exactly bbox; rasterize() adds the collar (CorrelationView.h:123-133)"""
+    from visionworkbench_b200.synth import make_pair
+    search, kernel = (-6, -4, 7, 5), (7, 7)
+    left, right, lm, rm, _ = make_pair(200, 160, search, seed=2)
+    view = vwb.pyramid_correlate(left, right, lm, rm, 0, 0.0, search, kernel, 0, 0, 0.0, 2.0, 0, 2, 2, 0, 16)
+    p0 = oracle.make_params(search, kernel, cost=0, consistency_threshold=2.0, filter_half_kernel=2, max_pyramid_levels=2, collar_size=0)
+    p16 = oracle.make_params(search, kernel, cost=0, consistency_threshold=2.0, filter_half_kernel=2, max_pyramid_levels=2, collar_size=16)
+    bbox = (40, 30, 140, 120)
+    assert np.array_equal(view.prerasterize(bbox), oracle.pyramid_correlate(p0, left, right, lm, rm, bbox=bbox))
+    assert np.array_equal(view.rasterize(None, bbox), oracle.pyramid_correlate(p16, left, right, lm, rm, bbox=bbox))

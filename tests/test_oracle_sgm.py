@@ -151,3 +151,95 @@ def test_mgm_accumulation(oracle):
     b = full.copy(); b[10:20, 10:30] = (0, 0, -1, -1); b[40:50, :, 0] = 4; b[40:50, :, 1] = 3
     ri, _ = oracle.sgm_calc_disparity_bounds(left, right, (8, 8), 3, b, use_mgm=True)
     assert (ri[10:20, 10:30] == 0).all() and (ri[45, :, 0] >= 4).all()
+
+
+# ---- the reference's own known-answer vectors for the pieces the SGM branch of the view adds ---------------------------------
+_CENSUS_SRC = np.array([[1, 2, 7, 2, 2, 8, 5, 2], [1, 4, 2, 9, 8, 8, 2, 6], [5, 2, 7, 2, 2, 2, 4, 6], [1, 2, 2, 2, 1, 4, 5, 2],
+                        [6, 6, 3, 7, 2, 2, 5, 5], [1, 2, 9, 2, 2, 2, 2, 2], [7, 9, 2, 8, 5, 2, 3, 2], [1, 2, 2, 2, 2, 2, 2, 1]], np.uint8)
+
+
+def test_census_reference_kat(oracle):
+    """Image/tests/TestCensusTransform.cxx:25-46 (src(col,row) listed row by row)."""
+    cv = lambda c, r, k: oracle.census_value(_CENSUS_SRC, c, r, k)
+    assert cv(2, 2, 3) == 0x20 and cv(4, 5, 3) == 0x86 and cv(6, 1, 3) == 0xDB
+    assert cv(4, 4, 5) == 0x0088F60D and cv(2, 3, 5) == 0x005D03C4
+    assert cv(3, 4, 7) == 0x00001C0000041400
+
+
+def test_ternary_census_semantics(oracle):
+    """Image/CensusTransform.h:167-220: per neighbour 00 / 01 / 11 in reverse raster order, centre skipped; the band is
+    [centre - t, centre + t].  Checked against a direct evaluation of the definition; 5x5 keeps 32 of its 48 bits (SGM.cc:1789-1803)."""
+    img = _CENSUS_SRC
+    def direct(c, r, k, t):
+        hk = k // 2
+        out, shift = 0, 0
+        for rr in range(r + hk, r - hk - 1, -1):
+            for cc in range(c + hk, c - hk - 1, -1):
+                if rr == r and cc == c:
+                    continue
+                v, ce = int(img[rr, cc]), int(img[r, c])
+                if v >= ce - t:
+                    out |= (3 if v > ce + t else 1) << shift
+                shift += 2
+        return out
+    for (c, r) in [(2, 2), (4, 5), (3, 3)]:
+        assert oracle.census_value(img, c, r, 3, True, 2) == direct(c, r, 3, 2)
+        assert oracle.census_value(img, c, r, 5, True, 1) == direct(c, r, 5, 1) & 0xFFFFFFFF
+    assert direct(3, 3, 5, 1) > 0xFFFFFFFF          # the truncation does drop bits here
+
+
+def test_blob_filter_reference_kat(oracle):
+    """Image/tests/TestBlobIndex.cxx:42-59 (three 8-connected blobs) and :101-124 (blob sizes 7, 2, 3) through
+    disparity_blob_filter's rule: blobs of at most `area` pixels are eroded (BlobIndex.h:444-453, CorrelationView.cc:242-271)."""
+    m = np.zeros((5, 7), np.int32)
+    m[1, 1:4] = 1; m[3, 2:4] = 1; m[1:4, 5] = 1; m[2, 6] = 1          # sizes 3, 2, 4 (the last joined through the (6,2) pixel)
+    d = np.zeros((5, 7, 3), np.int32); d[..., 0] = 9; d[..., 1] = 7; d[..., 2] = m
+    assert (oracle.disparity_blob_filter(d, 1)[..., 2] == m).all()
+    assert oracle.disparity_blob_filter(d, 2)[..., 2].sum() == 7 and oracle.disparity_blob_filter(d, 2)[3, 2:4, 2].sum() == 0
+    assert oracle.disparity_blob_filter(d, 3)[..., 2].sum() == 4
+    e = oracle.disparity_blob_filter(d, 4)
+    assert e[..., 2].sum() == 0 and (e[m == 1] == 0).all() and (e[m == 0][:, 0] == 9).all()   # eroded pixels become result_type()
+    img = np.array([[0, 0, 0, 1, 8, 0], [0, 1, 0, 0, 0, 0], [0, 1, 0, 0, 1, 1], [1, 1, 0, 0, 0, 1], [1, 0, 1, 0, 0, 0], [0, 1, 0, 0, 0, 0]])
+    d = np.zeros((6, 6, 3), np.int32); d[..., 2] = img != 0
+    assert oracle.disparity_blob_filter(d, 2)[..., 2].sum() == 10          # the 2-blob goes
+    assert oracle.disparity_blob_filter(d, 3)[..., 2].sum() == 7           # ... and the 3-blob
+    assert oracle.disparity_blob_filter(d, 6)[..., 2].sum() == 7 and oracle.disparity_blob_filter(d, 7)[..., 2].sum() == 0
+
+
+def test_parabola_subpixel_mode_and_full_entry(oracle):
+    """vwo_calc_disparity_sgm == the older entry points where they overlap; SUBPIXEL_PARABOLA offsets stay inside the
+    half-pixel circle (ParabolaFit2d::find_peak, SGMAssist.h:99-134) and the integer part is untouched."""
+    left, right = _constant_offset_pair(3, 90, 70)
+    a = oracle.sgm_calc_disparity(left, right, (8, 8), 5)
+    bi, bf, bb = oracle.calc_disparity_sgm(left, right, (8, 8), 5, subpixel_mode=1)
+    assert np.array_equal(a, bi) and (bb == np.array([0, 0, 8, 8])).all()
+    off = bf[..., :2] - bi[..., :2]
+    assert np.hypot(off[..., 0], off[..., 1]).max() <= 0.5 + 1e-6 and np.abs(off).max() > 0.01
+    ci, cf = oracle.sgm_calc_disparity_subpixel(left, right, (8, 8), 5, 5)
+    di, df_, _ = oracle.calc_disparity_sgm(left, right, (8, 8), 5, subpixel_mode=5)
+    assert np.array_equal(ci, di) and np.array_equal(cf, df_)
+    ti, _, _ = oracle.calc_disparity_sgm(left, right, (8, 8), 5, cost_type=4)            # ternary census recovers the offset too
+    assert ((ti[..., 0] == 6) & (ti[..., 1] == 5)).mean() > 0.99
+    with pytest.raises(ValueError):
+        oracle.calc_disparity_sgm(left, right, (8, 8), 5, cost_type=0)                    # NoImplErr (SGM.cc:1888-1892)
+
+
+@pytest.mark.parametrize("algorithm", [1, 2, 3])
+def test_view_sgm_branch_recovers_a_constant_offset(oracle, algorithm):
+    """PyramidCorrelationView with algorithm SGM / MGM / FINAL_MGM (CorrelationView.cc:392-595): the statistical bar of
+    Stereo/tests/TestPyramidCorrelationView.cxx (>= 0.9 correct, >= 0.99 valid) on a constant shift, with the R->L check,
+    the filters and the sub-pixel stage on."""
+    rng = np.random.default_rng(5)
+    W, H, off = 200, 160, (3, -2)
+    base = np.floor(rng.random((H + 40, W + 40)) * 256)
+    base = np.floor((base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) / 4).astype(np.float32)
+    left = np.ascontiguousarray(base[20:20 + H, 20:20 + W]); right = np.ascontiguousarray(base[20 - off[1]:20 - off[1] + H, 20 - off[0]:20 - off[0] + W])
+    p = oracle.make_params((-8, -8, 9, 9), (5, 5), cost=3, consistency_threshold=2.0, min_consistency_level=0, filter_half_kernel=3,
+                           max_pyramid_levels=2, algorithm=algorithm, sgm_subpixel_mode=5)
+    d = oracle.pyramid_correlate(p, left, right, bbox=(20, 20, 180, 140))
+    ok = (np.abs(d[..., 0] - off[0]) < 0.5) & (np.abs(d[..., 1] - off[1]) < 0.5) & (d[..., 2] == 1)
+    # the R->L pass loses the rows whose partner lies above the left tile: populate_disp_bound_image takes the column extent
+    # of the right mask from the row of the LEFT pixel (SGM.cc:343-359), which is empty there -- reference behaviour
+    assert ok.mean() > 0.88 and (ok | (d[..., 2] == 0)).all(), (ok.mean(), (d[..., 2] == 1).mean())
+    assert (d[20:, :, 2] == 1).mean() > 0.99
+    assert (d[..., 0] != np.rint(d[..., 0])).mean() > 0.3          # sub-pixel offsets were applied

@@ -69,7 +69,10 @@ class CorrParams(C.Structure):
                 ("consistency_threshold", C.c_float), ("min_consistency_level", C.c_int32),
                 ("filter_half_kernel", C.c_int32), ("max_pyramid_levels", C.c_int32), ("collar_size", C.c_int32),
                 ("corr_timeout", C.c_int32), ("seconds_per_op", C.c_double),
-                ("algorithm", C.c_int32), ("blob_filter_area", C.c_int32)]
+                ("algorithm", C.c_int32), ("blob_filter_area", C.c_int32),
+                ("sgm_subpixel_mode", C.c_int32), ("sgm_search_buffer_x", C.c_int32), ("sgm_search_buffer_y", C.c_int32),
+                ("region_ul_x", C.c_int32), ("region_ul_y", C.c_int32), ("write_debug_images", C.c_int32),
+                ("sgm_threads", C.c_int32), ("memory_limit_mb", C.c_double)]
 
 
 class SgmParams(C.Structure):
@@ -113,6 +116,8 @@ def lib():
         L.vwb200_corr_create.argtypes = [C.POINTER(CorrParams), C.POINTER(P)]
         L.vwb200_corr_set_inputs.argtypes = [P, P, I, I, Z, P, I, I, Z, P, Z, P, Z, I]
         L.vwb200_corr_rasterize.argtypes = [P, I, I, I, I, P, Z, I, P]
+        L.vwb200_corr_prerasterize.argtypes = [P, I, I, I, I, P, Z, I, P]
+        L.vwb200_corr_set_lr_disp_diff.argtypes = [P, P, I, I, Z, I]
         L.vwb200_corr_num_levels.argtypes = [P, I, I]
         L.vwb200_corr_cols.argtypes = [P]
         L.vwb200_corr_rows.argtypes = [P]
@@ -428,27 +433,45 @@ class PyramidCorrelationView:
     def __init__(self, left, right, left_mask, right_mask, prefilter_mode, prefilter_width,
                  search_region, kernel_size, cost_type, corr_timeout, seconds_per_op,
                  consistency_threshold, min_consistency_level, filter_half_kernel, max_pyramid_levels,
-                 algorithm=VW_CORRELATION_BM, collar_size=0, sgm_subpixel_mode=None, sgm_search_buffer=(2, 2),
+                 algorithm=VW_CORRELATION_BM, collar_size=0, sgm_subpixel_mode=SUBPIXEL_LC_BLEND, sgm_search_buffer=(2, 2),
                  memory_limit_mb=6000, blob_filter_area=0, lr_disp_diff=None, region_ul=(0, 0),
-                 write_debug_images=False):
+                 write_debug_images=False, sgm_threads=4):
+        """Argument order = the reference constructor (Stereo/CorrelationView.h:48-69); sgm_threads stands for
+        vw_settings().default_num_threads(), which SGM's memory estimate reads (SGM.cc:715-716).
+        lr_disp_diff: float32 (rows, cols, 2) PixelMask<float> array whose pixel (0, 0) is image pixel region_ul; updated in place."""
         if isinstance(search_region, BBox2i):
             s = (search_region.x0, search_region.y0, search_region.x1, search_region.y1)
         else:
             s = tuple(int(v) for v in search_region)
-        if lr_disp_diff is not None:
-            raise NoImplErr("lr_disp_diff output is not implemented by the vwb200 engine")
         self._p = CorrParams(s[0], s[1], s[2], s[3], int(kernel_size[0]), int(kernel_size[1]), int(cost_type),
                              int(prefilter_mode), float(prefilter_width), float(consistency_threshold),
                              int(min_consistency_level), int(filter_half_kernel), int(max_pyramid_levels),
                              int(collar_size), int(corr_timeout), float(seconds_per_op), int(algorithm),
-                             int(blob_filter_area))
+                             int(blob_filter_area), int(sgm_subpixel_mode), int(sgm_search_buffer[0]), int(sgm_search_buffer[1]),
+                             int(region_ul[0]), int(region_ul[1]), int(bool(write_debug_images)), int(sgm_threads), float(memory_limit_mb))
         self._h = C.c_void_p()
         _check(lib().vwb200_corr_create(C.byref(self._p), C.byref(self._h)))
+        self._diff = None
+        if lr_disp_diff is not None:
+            if _is_torch(lr_disp_diff):
+                d = lr_disp_diff
+                assert d.dtype.is_floating_point and d.element_size() == 4 and d.dim() == 3 and d.shape[2] == 2 and d.stride(2) == 1 and d.stride(1) == 2
+                _check(lib().vwb200_corr_set_lr_disp_diff(self._h, d.data_ptr(), d.shape[1], d.shape[0], d.stride(0) // 2, 1))
+            else:
+                d = lr_disp_diff
+                if not (isinstance(d, np.ndarray) and d.dtype == np.float32 and d.ndim == 3 and d.shape[2] == 2 and d.strides[2] == 4 and d.strides[1] == 8):
+                    raise ArgumentErr("lr_disp_diff must be a float32 (rows, cols, 2) array")
+                _check(lib().vwb200_corr_set_lr_disp_diff(self._h, d.ctypes.data, d.shape[1], d.shape[0], d.strides[0] // 8, 0))
+            self._diff = d
         self._keep = None
         self._device = _is_torch(left)
         if self._device:
+            import torch
             l, r = left.contiguous().float(), right.contiguous().float()
-            lm, rm = left_mask.contiguous(), right_mask.contiguous()
+            if tuple(left_mask.shape) != tuple(l.shape) or tuple(right_mask.shape) != tuple(r.shape):
+                raise ArgumentErr("masks must have the size of their images")
+            lm = (left_mask != 0).to(torch.uint8).contiguous() if left_mask.dtype != torch.uint8 else left_mask.contiguous()
+            rm = (right_mask != 0).to(torch.uint8).contiguous() if right_mask.dtype != torch.uint8 else right_mask.contiguous()
             self._keep = (l, r, lm, rm)
             _check(lib().vwb200_corr_set_inputs(self._h, l.data_ptr(), l.shape[1], l.shape[0], l.stride(0),
                                                 r.data_ptr(), r.shape[1], r.shape[0], r.stride(0),
@@ -490,6 +513,9 @@ class PyramidCorrelationView:
     def rasterize(self, dest=None, bbox=None):
         """rasterize(dest, bbox) (CorrelationView.h:123-133).  dest: float32 (h, w, 3) numpy array (or torch
         CUDA tensor) already sized to bbox, or None to allocate.  Pixels are {dx, dy, valid}."""
+        return self._run(lib().vwb200_corr_rasterize, dest, bbox)
+
+    def _run(self, fn, dest, bbox):
         b = _bbox(bbox) if bbox is not None else (0, 0, self.cols(), self.rows())
         w, h = b[2] - b[0], b[3] - b[1]
         if dest is not None and _is_torch(dest) or (dest is None and self._device):
@@ -497,21 +523,18 @@ class PyramidCorrelationView:
             if dest is None:
                 dest = torch.empty((h, w, 3), dtype=torch.float32, device=self._keep[0].device)
             assert dest.shape == (h, w, 3) and dest.dtype == torch.float32 and dest.stride(2) == 1 and dest.stride(1) == 3
-            _check(lib().vwb200_corr_rasterize(self._h, b[0], b[1], b[2], b[3], dest.data_ptr(), dest.stride(0) // 3, 1, _stream_ptr()))
+            _check(fn(self._h, b[0], b[1], b[2], b[3], dest.data_ptr(), dest.stride(0) // 3, 1, _stream_ptr()))
             return dest
         if dest is None:
             dest = np.empty((h, w, 3), np.float32)
         assert dest.shape == (h, w, 3) and dest.dtype == np.float32 and dest.strides[2] == 4 and dest.strides[1] == 12
-        _check(lib().vwb200_corr_rasterize(self._h, b[0], b[1], b[2], b[3], dest.ctypes.data, dest.strides[0] // 12, 0, None))
+        _check(fn(self._h, b[0], b[1], b[2], b[3], dest.ctypes.data, dest.strides[0] // 12, 0, None))
         return dest
 
     def prerasterize(self, bbox):
-        """prerasterize(bbox): an owning buffer of bbox size (CorrelationView.cc:880-884); unlike rasterize()
-        no collar is added."""
-        saved = self._p.collar_size
-        if saved:
-            raise NoImplErr("prerasterize without collar on a collared view: call rasterize()")
-        return self.rasterize(None, bbox)
+        """prerasterize(bbox): an owning buffer of bbox size (CorrelationView.cc:880-884); processes exactly bbox --
+        unlike rasterize() no collar is added (CorrelationView.h:123-133)."""
+        return self._run(lib().vwb200_corr_prerasterize, None, bbox)
 
 
 def _bbox(b):
@@ -522,9 +545,12 @@ def _bbox(b):
 
 def pyramid_correlate(left, right, left_mask, right_mask, prefilter_mode, prefilter_width, search_region, kernel_size,
                       cost_type, corr_timeout, seconds_per_op, consistency_threshold, min_consistency_level,
-                      filter_half_kernel, max_pyramid_levels, algorithm=VW_CORRELATION_BM, collar_size=0, **kw):
-    """vw::stereo::pyramid_correlate (Stereo/CorrelationView.h:195-230)."""
+                      filter_half_kernel, max_pyramid_levels, algorithm=VW_CORRELATION_BM, collar_size=0,
+                      sgm_subpixel_mode=SUBPIXEL_LC_BLEND, sgm_search_buffer=(2, 2), memory_limit_mb=6000, blob_filter_area=0,
+                      lr_disp_diff=None, region_ul=(0, 0), write_debug_images=False, **kw):
+    """vw::stereo::pyramid_correlate (Stereo/CorrelationView.h:195-230), same positional order."""
     return PyramidCorrelationView(left, right, left_mask, right_mask, prefilter_mode, prefilter_width, search_region,
                                   kernel_size, cost_type, corr_timeout, seconds_per_op, consistency_threshold,
                                   min_consistency_level, filter_half_kernel, max_pyramid_levels, algorithm,
-                                  collar_size, **kw)
+                                  collar_size, sgm_subpixel_mode, sgm_search_buffer, memory_limit_mb, blob_filter_area,
+                                  lr_disp_diff, region_ul, write_debug_images, **kw)

@@ -140,7 +140,13 @@ int prefilter_final_launch(ImgF img, const float* g, int mode, float* out, cudaS
 
 // ---- K3 / K4 -------------------------------------------------------------------------------------
 int consistency_launch(vwb200_dispi* l2r, int lw, int lh, ptrdiff_t lpitch, const vwb200_dispi* r2l, int rw, int rh,
-                       ptrdiff_t rpitch, float thr, cudaStream_t st);
+                       ptrdiff_t rpitch, float thr, cudaStream_t st, int qax = 0, int qay = 0, float* diff = nullptr, ptrdiff_t dpitch = 0,
+                       int dox = 0, int doy = 0);
+int diff_invalidate_launch(const vwb200_dispi* disp, int w, int h, float* diff, ptrdiff_t dpitch, int dox, int doy, cudaStream_t st);
+int sgm_finalize_launch(const float* sub, const vwb200_dispi* disp, int w, int ax, int ay, float* out, ptrdiff_t opitch_px, int ox, int oy,
+                        int ow, int oh, cudaStream_t st);
+// disparity_blob_filter; work: 2 * w * h ints
+int blob_filter_launch(vwb200_dispi* d, int w, int h, int area, int* work, cudaStream_t st);
 // pass 1 of the outlier filter evaluated over [x0,x0+ow) x [y0,y0+oh) of the constant-edge-extended input
 int rm_outliers_launch(const vwb200_dispi* in, int w, int h, int hx, int hy, double pt, double rt,
                        int x0, int y0, int ow, int oh, vwb200_dispi* out, cudaStream_t st);

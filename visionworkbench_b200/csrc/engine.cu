@@ -54,7 +54,8 @@ int ensure_device() {
 }
 
 int zone_post_launch(const Tile* d_tiles, int ntiles, const Zone* d_zones, const Zone* d_rlzones, const int2* d_post_add,
-                     vwb200_dispi* disp, const vwb200_dispi* rl, float thr, int tile_w, int tile_h, cudaStream_t st);
+                     vwb200_dispi* disp, const vwb200_dispi* rl, float thr, int tile_w, int tile_h, cudaStream_t st, float* diff = nullptr,
+                     ptrdiff_t dpitch = 0, int dox = 0, int doy = 0);
 
 // ---------------------------------------------------------------------------------------------------
 // small RAII helpers: stream-ordered device buffers, an owned-or-borrowed stream
@@ -368,6 +369,7 @@ static int filtered_region(ImgF img, int mode, float width, Box reg, float** out
 
 using namespace vwb200;
 
+struct LevelImgsT;
 struct vwb200_corr {
   vwb200_corr_params p;
   int max_level_by_search = 0;
@@ -390,18 +392,26 @@ struct vwb200_corr {
     if (levels < 1) levels = 0;
     return levels;
   }
-  int prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_invalid, Arena& ar, cudaStream_t st) const;
+  // optional lr_disp_diff output (CorrelationView.h:67-68): PixelMask<float> pairs, caller-owned
+  float* diff = nullptr; int diff_cols = 0, diff_rows = 0; ptrdiff_t diff_pitch = 0; int diff_on_device = 0;
+  struct DiffTile { float* d = nullptr; ptrdiff_t pitch = 0; int ox = 0, oy = 0; };   // device view of the processed box's window
+  int prerasterize(Box bbox, vwb200_dispi** d_disp_out, float** d_sub_out, int* all_invalid, const DiffTile& df, Arena& ar, cudaStream_t st) const;
+  int prerasterize_sgm(Box bbox, const std::vector<struct LevelImgsT>& py, int levels, vwb200_dispi** d_disp_out, float** d_sub_out,
+                       const DiffTile& df, Arena& ar, cudaStream_t st) const;
 };
 
 namespace {
 inline Box bexpand(Box b, int ex, int ey) { if (b.x0 >= b.x1 || b.y0 >= b.y1) return b; return Box{b.x0 - ex, b.y0 - ey, b.x1 + ex, b.y1 + ey}; }
 inline bool bempty(Box b) { return b.x0 >= b.x1 || b.y0 >= b.y1; }
-struct LevelImgs { float* l; float* r; uint8_t* lm; uint8_t* rm; int lw, lh, rw, rh, lmw, lmh, rmw, rmh; };
 }
+struct LevelImgsT { float* l; float* r; uint8_t* lm; uint8_t* rm; int lw, lh, rw, rh, lmw, lmh, rmw, rmh; };
+typedef LevelImgsT LevelImgs;
 
 // The per-tile pipeline.  Result: integer disparity (bw x bh, dense) in device memory, WITHOUT the
 // final "+ search_region.min()" (finalize_kernel adds it while casting to float).
-int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_invalid, Arena& ar, cudaStream_t st) const {
+int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, float** d_sub_out, int* all_invalid, const DiffTile& df, Arena& ar,
+                              cudaStream_t st) const {
+  *d_sub_out = nullptr;
   const int bw = bbox.x1 - bbox.x0, bh = bbox.y1 - bbox.y0;
   const int kx = p.kernel_x, ky = p.kernel_y, hkx = kx / 2, hky = ky / 2;
   const int ssx = p.search_x1 - p.search_x0, ssy = p.search_y1 - p.search_y0;
@@ -473,10 +483,12 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
     VWB_TRY(subsample_mask_launch(ImgB{a.rm, a.rmw, a.rmh, a.rmw}, b.rm, b.rmw, st));
   }
 
+  const int prefilter_mode = p.algorithm != VWB200_CORRELATION_BM ? VWB200_PREFILTER_NONE : p.prefilter_mode;   // CorrelationView.h:96-97
   for (int i = 0; i <= levels; ++i) {   // :233-236 prefilter every level
-    VWB_TRY(prefilter_inplace(py[i].l, py[i].lw, py[i].lh, p.prefilter_mode, p.prefilter_width, ar, st));
-    VWB_TRY(prefilter_inplace(py[i].r, py[i].rw, py[i].rh, p.prefilter_mode, p.prefilter_width, ar, st));
+    VWB_TRY(prefilter_inplace(py[i].l, py[i].lw, py[i].lh, prefilter_mode, p.prefilter_width, ar, st));
+    VWB_TRY(prefilter_inplace(py[i].r, py[i].rw, py[i].rh, prefilter_mode, p.prefilter_width, ar, st));
   }
+  if (p.algorithm != VWB200_CORRELATION_BM) return prerasterize_sgm(bbox, py, levels, d_disp_out, d_sub_out, df, ar, st);
 
   // ---- level loop (CorrelationView.cc:363-830) ----
   std::vector<HostZone> zones;
@@ -555,7 +567,8 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
       int2* d_post;
       VWB_TRY(ar.alloc(&d_post, post.size()));
       VWB_CUDA(cudaMemcpyAsync(d_post, post.data(), post.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-      VWB_TRY(zone_post_launch(d_tl, ntl, d_zl, d_zr, d_post, disp, rl, p.consistency_threshold, tile_w, tile_h, st));
+      VWB_TRY(zone_post_launch(d_tl, ntl, d_zl, d_zr, d_post, disp, rl, p.consistency_threshold, tile_w, tile_h, st,
+                               (level == 0 && check) ? df.d : nullptr, df.pitch, df.ox, df.oy));
     }
     if (p.filter_half_kernel > 0) {   // :713-744
       const int fh = p.filter_half_kernel;
@@ -569,6 +582,11 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
         VWB_TRY(rm_outliers_launch(disp, dw, dh, fh, fh, 3.0, 0.5, 0, 0, dw, dh, t2, st));
       }
       VWB_TRY(disparity_mask_launch(t2, dw, dh, ImgB{lv.lm, lv.lmw, lv.lmh, lv.lmw}, ImgB{lv.rm, lv.rmw, lv.rmh, lv.rmw}, disp, st));
+    }
+    if (p.blob_filter_area / scaling >= 1) {   // :746-749, disparity_blob_filter (:242-271)
+      int* work;
+      VWB_TRY(ar.alloc(&work, (size_t)2 * dw * dh));
+      VWB_TRY(blob_filter_launch(disp, dw, dh, p.blob_filter_area / scaling, work, st));
     }
     if (level != 0) {   // :754-799 refine the search zones on the host (zones are O(10^3), data dependent)
       hdisp.resize((size_t)dw * dh);
@@ -592,7 +610,120 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, int* all_inva
   }
   const LevelImgs& l0 = py[0];
   if (l0.lmw != bw || l0.lmh != bh) { set_error("PyramidCorrelation: Solved disparity doesn't match requested bbox size."); return VWB200_EMATH; }
+  if (df.d) VWB_TRY(diff_invalidate_launch(disp, bw, bh, df.d, df.pitch, df.ox, df.oy, st));   // :848-857
   *d_disp_out = disp;
+  return VWB200_OK;
+}
+
+// The SGM / MGM / FINAL_MGM branch of the level loop (CorrelationView.cc:392-595, 700-750, 859-871): one calc_disparity_sgm
+// per level over the whole padded tile, seeded by the previous level's filtered disparity; an R->L pass + consistency check
+// at the levels >= min_consistency_level; the sub-pixel view is made at level 0 BEFORE the check and the filters.
+int vwb200_corr::prerasterize_sgm(Box bbox, const std::vector<LevelImgs>& py, int levels, vwb200_dispi** d_disp_out, float** d_sub_out,
+                                  const DiffTile& df, Arena& ar, cudaStream_t st) const {
+  const int bw = bbox.x1 - bbox.x0, bh = bbox.y1 - bbox.y0;
+  const int kx = p.kernel_x, ky = p.kernel_y, hkx = kx / 2, hky = ky / 2;
+  const int ssx = p.search_x1 - p.search_x0, ssy = p.search_y1 - p.search_y0;
+  const int up = 1 << levels;
+  if (kx != ky) { set_error("SGM needs a square kernel (SemiGlobalMatcher takes kernel_size[0], SGM.cc:213-215)"); return VWB200_EARG; }
+  vwb200_dispi *disp = nullptr, *disp_rl = nullptr, *prev = nullptr, *prev_rl = nullptr;
+  int dw = 0, dh = 0, pw = 0, ph = 0, rlw = 0, rlh = 0, prlw = 0, prlh = 0;
+  float* sub = nullptr;
+  for (int level = levels; level >= 0; --level) {
+    const LevelImgs& lv = py[level];
+    const int use_mgm = p.algorithm == VWB200_CORRELATION_MGM || (p.algorithm == VWB200_CORRELATION_FINAL_MGM && level == 0);   // :366-367
+    const int scaling = 1 << level;
+    prev = disp; pw = dw; ph = dh; prev_rl = disp_rl; prlw = rlw; prlh = rlh;                    // :373-376
+    disp = nullptr; disp_rl = nullptr;
+    dw = lv.lmw; dh = lv.lmh;
+    const int rox = up * hkx / scaling, roy = up * hky / scaling;
+    const int dsx = ssx / scaling, dsy = ssy / scaling;                                          // :395-396
+    const Box lr{rox - hkx, roy - hky, dw + rox + hkx, dh + roy + hky};                          // :404-405
+    const Box rr{lr.x0, lr.y0, lr.x1 + dsx, lr.y1 + dsy};                                       // :406-407
+    const int lcw = lr.x1 - lr.x0, lch = lr.y1 - lr.y0, rcw = rr.x1 - rr.x0, rch = rr.y1 - rr.y0;
+    float *lc, *rc;
+    VWB_TRY(ar.alloc(&lc, (size_t)lcw * lch));
+    VWB_TRY(ar.alloc(&rc, (size_t)rcw * rch));
+    VWB_TRY(crop_extend_f32_launch(ImgF{lv.l, lv.lw, lv.lh, lv.lw}, lr.x0, lr.y0, lcw, lch, lc, lcw, st));
+    VWB_TRY(crop_extend_f32_launch(ImgF{lv.r, lv.rw, lv.rh, lv.rw}, rr.x0, rr.y0, rcw, rch, rc, rcw, st));
+    SgmArgs a;
+    a.left = ImgF{lc, lcw, lch, lcw}; a.right = ImgF{rc, rcw, rch, rcw};
+    a.sx = dsx; a.sy = dsy; a.k = kx;
+    a.ternary = p.cost_type == VWB200_TERNARY_CENSUS_TRANSFORM; a.ternary_threshold = 5;
+    a.use_mgm = use_mgm; a.subpixel_mode = p.sgm_subpixel_mode;
+    a.buf_x = p.sgm_search_buffer_x; a.buf_y = p.sgm_search_buffer_y;
+    a.memory_limit_mb = p.memory_limit_mb > 0 ? p.memory_limit_mb : 6000.0;
+    a.assumed_threads = p.sgm_threads > 0 ? p.sgm_threads : 4;
+    a.lmask = ImgB{lv.lm, lv.lmw, lv.lmh, lv.lmw}; a.rmask = ImgB{lv.rm, lv.rmw, lv.rmh, lv.rmw};
+    if (level < levels) { a.prev = prev; a.pw = pw; a.ph = ph; a.ppitch = pw; }
+    int ow = 0, oh = 0;
+    sgm_output_size(lcw, lch, rcw, rch, dsx, dsy, kx, &ow, &oh);
+    if (ow != dw || oh != dh) { set_error("PyramidCorrelation(SGM): level %d disparity is %dx%d, expected %dx%d", level, ow, oh, dw, dh); return VWB200_EMATH; }
+    VWB_TRY(ar.alloc(&disp, (size_t)dw * dh));
+    a.out = disp; a.opitch = dw;
+    if (level == 0) { VWB_TRY(ar.alloc(&sub, (size_t)dw * dh * 3)); a.out_sub = sub; a.sub_pitch = (ptrdiff_t)dw * 3; }
+    VWB_TRY(sgm_run(a, ar, st));
+    bool check_rl = false;
+    uint8_t *rrm = nullptr, *lrm = nullptr; int lrmw = 0, lrmh = 0;
+    if (p.consistency_threshold >= 0.0f && level >= p.min_consistency_level) {                  // :438-590
+      check_rl = true;
+      const Box llr{lr.x0 - dsx, lr.y0 - dsy, lr.x1 + dsx, lr.y1 + dsy};                         // :453-455
+      const int l2w = llr.x1 - llr.x0, l2h = llr.y1 - llr.y0;
+      float* l2;
+      VWB_TRY(ar.alloc(&l2, (size_t)l2w * l2h));
+      VWB_TRY(crop_extend_f32_launch(ImgF{lv.l, lv.lw, lv.lh, lv.lw}, llr.x0, llr.y0, l2w, l2h, l2, l2w, st));
+      rlw = rcw - 2 * hkx; rlh = rch - 2 * hky;                                                  // masks of the reversed problem (:496-508)
+      lrmw = l2w - 2 * hkx; lrmh = l2h - 2 * hky;
+      VWB_TRY(ar.alloc(&rrm, (size_t)rlw * rlh));
+      VWB_TRY(ar.alloc(&lrm, (size_t)lrmw * lrmh));
+      VWB_TRY(crop_extend_u8_launch(ImgB{lv.rm, lv.rmw, lv.rmh, lv.rmw}, 0, 0, rlw, rlh, 1, rrm, rlw, st));
+      VWB_TRY(crop_extend_u8_launch(ImgB{lv.lm, lv.lmw, lv.lmh, lv.lmw}, -dsx, -dsy, lrmw, lrmh, 1, lrm, lrmw, st));
+      SgmArgs b = a;
+      b.left = ImgF{rc, rcw, rch, rcw}; b.right = ImgF{l2, l2w, l2h, l2w};
+      b.lmask = ImgB{rrm, rlw, rlh, rlw}; b.rmask = ImgB{lrm, lrmw, lrmh, lrmw};
+      b.prev = nullptr; b.pw = b.ph = 0; b.ppitch = 0;
+      if (level < levels) { b.prev = prev_rl; b.pw = prlw; b.ph = prlh; b.ppitch = prlw; }
+      int ow2 = 0, oh2 = 0;
+      sgm_output_size(rcw, rch, l2w, l2h, dsx, dsy, kx, &ow2, &oh2);
+      if (ow2 != rlw || oh2 != rlh) { set_error("PyramidCorrelation(SGM): R->L size mismatch"); return VWB200_EMATH; }
+      VWB_TRY(ar.alloc(&disp_rl, (size_t)rlw * rlh));
+      b.out = disp_rl; b.opitch = rlw; b.out_sub = nullptr; b.subpixel_mode = 0;
+      VWB_TRY(sgm_run(b, ar, st));
+      // the R->L disparity enters the check shifted by -size and goes on un-shifted (:548-549, 586)
+      VWB_TRY(consistency_launch(disp, dw, dh, dw, disp_rl, rlw, rlh, rlw, p.consistency_threshold, st, -dsx, -dsy,
+                                 level == 0 ? df.d : nullptr, df.pitch, df.ox, df.oy));
+    }
+    if (p.filter_half_kernel > 0) {                                                             // :713-744
+      const int fh = p.filter_half_kernel;
+      vwb200_dispi *t1, *t2;
+      VWB_TRY(ar.alloc(&t2, (size_t)dw * dh));
+      if (level != 0) {
+        VWB_TRY(ar.alloc(&t1, (size_t)(dw + 2) * (dh + 2)));
+        VWB_TRY(rm_outliers_launch(disp, dw, dh, fh, fh, 3.0, 0.5, -1, -1, dw + 2, dh + 2, t1, st));
+        VWB_TRY(cleanup_pass2_launch(t1, dw, dh, t2, st));
+      } else {
+        VWB_TRY(rm_outliers_launch(disp, dw, dh, fh, fh, 3.0, 0.5, 0, 0, dw, dh, t2, st));
+      }
+      VWB_TRY(disparity_mask_launch(t2, dw, dh, ImgB{lv.lm, lv.lmw, lv.lmh, lv.lmw}, ImgB{lv.rm, lv.rmw, lv.rmh, lv.rmw}, disp, st));
+      if (level != 0 && check_rl) {
+        vwb200_dispi *u1, *u2;
+        VWB_TRY(ar.alloc(&u1, (size_t)(rlw + 2) * (rlh + 2)));
+        VWB_TRY(ar.alloc(&u2, (size_t)rlw * rlh));
+        VWB_TRY(rm_outliers_launch(disp_rl, rlw, rlh, fh, fh, 3.0, 0.5, -1, -1, rlw + 2, rlh + 2, u1, st));
+        VWB_TRY(cleanup_pass2_launch(u1, rlw, rlh, u2, st));
+        VWB_TRY(disparity_mask_launch(u2, rlw, rlh, ImgB{rrm, rlw, rlh, rlw}, ImgB{lrm, lrmw, lrmh, lrmw}, disp_rl, st));
+      }
+    }
+    const int area = p.blob_filter_area / scaling;                                               // :747-749
+    if (area >= 1) {
+      int* work;
+      VWB_TRY(ar.alloc(&work, (size_t)2 * std::max(dw * dh, check_rl ? rlw * rlh : 0)));
+      VWB_TRY(blob_filter_launch(disp, dw, dh, area, work, st));
+      if (check_rl && level != 0) VWB_TRY(blob_filter_launch(disp_rl, rlw, rlh, area, work, st));
+    }
+  }
+  if (dw != bw || dh != bh) { set_error("PyramidCorrelation: Solved disparity doesn't match requested bbox size."); return VWB200_EMATH; }
+  if (df.d) VWB_TRY(diff_invalidate_launch(disp, bw, bh, df.d, df.pitch, df.ox, df.oy, st));
+  *d_disp_out = disp; *d_sub_out = sub;
   return VWB200_OK;
 }
 
@@ -998,9 +1129,8 @@ int vwb200_corr_create(const vwb200_corr_params* p, vwb200_corr** out) {
   if (!(w * h == w * h)) { set_error("PyramidCorrelationView: Invalid search region"); return VWB200_EARG; }   // CorrelationView.h:88-94
   if (p->search_x1 <= p->search_x0 || p->search_y1 <= p->search_y0) { set_error("PyramidCorrelationView: empty search region"); return VWB200_EARG; }
   if (p->kernel_x % 2 != 1 || p->kernel_y % 2 != 1 || p->kernel_x < 1 || p->kernel_y < 1) { set_error("PyramidCorrelationView: kernel size must be odd"); return VWB200_EARG; }
-  if (p->algorithm != 0) { set_error("only VW_CORRELATION_BM is implemented by the vwb200 engine"); return VWB200_ENOIMPL; }
-  if (p->blob_filter_area > 0) { set_error("blob_filter_area > 0 is not implemented"); return VWB200_ENOIMPL; }
-  if (p->cost_type < 0 || p->cost_type > 2) { set_error("cost type %d is only valid for SGM", p->cost_type); return VWB200_EARG; }
+  if (p->algorithm < VWB200_CORRELATION_BM || p->algorithm > VWB200_CORRELATION_FINAL_MGM) { set_error("unknown correlation algorithm %d", p->algorithm); return VWB200_EARG; }
+  if (p->cost_type < 0 || p->cost_type > VWB200_TERNARY_CENSUS_TRANSFORM) { set_error("unknown cost type %d", p->cost_type); return VWB200_EARG; }
   vwb200_corr* h_ = new vwb200_corr();
   h_->p = *p;
   // CorrelationView.h:96-105 (float maths)
@@ -1042,11 +1172,22 @@ int vwb200_corr_cols(const vwb200_corr* h) { return h ? h->lcols : 0; }
 int vwb200_corr_rows(const vwb200_corr* h) { return h ? h->lrows : 0; }
 int vwb200_corr_num_levels(const vwb200_corr* h, int bw, int bh) { return h ? h->num_levels(bw, bh) : VWB200_EARG; }
 
-int vwb200_corr_rasterize(vwb200_corr* h, int x0, int y0, int x1, int y1, float* dest, ptrdiff_t dest_pitch, int dest_on_device, void* stream) {
+static int corr_rasterize_impl(vwb200_corr* h, int x0, int y0, int x1, int y1, float* dest, ptrdiff_t dest_pitch, int dest_on_device, void* stream,
+                               bool with_collar) {
   if (!h || !dest) { set_error("corr_rasterize: null pointer"); return VWB200_EARG; }
   if (!h->L) { set_error("corr_rasterize: inputs not set"); return VWB200_ELOGIC; }
   if (x1 <= x0 || y1 <= y0) { set_error("corr_rasterize: empty bbox"); return VWB200_EARG; }
+  const bool sgm = h->p.algorithm != VWB200_CORRELATION_BM;
+  if (sgm && h->p.cost_type != VWB200_CENSUS_TRANSFORM && h->p.cost_type != VWB200_TERNARY_CENSUS_TRANSFORM) {
+    // NoImplErr of SGM.cc:1888-1892, re-thrown as ArgumentErr by calc_disparity_sgm (:221-226)
+    set_error("Failed to compute the correlation. Detailed error message: With SGM/MGM, only the census transform cost mode gives good results.");
+    return VWB200_EARG;
+  }
+  if (!sgm && h->p.cost_type > VWB200_CROSS_CORRELATION) { set_error("cost type %d is only valid for SGM", h->p.cost_type); return VWB200_EARG; }
   VWB_TRY(ensure_device());
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev != h->device ? prev_dev : -1};
   VWB_CUDA(cudaSetDevice(h->device));
   StreamGuard sg; VWB_TRY(sg.init(stream, (h->owned ? dest_on_device : 1)));
   cudaStream_t st = sg.st;
@@ -1054,21 +1195,52 @@ int vwb200_corr_rasterize(vwb200_corr* h, int x0, int y0, int x1, int y1, float*
     Arena ar(st);
     const int bw = x1 - x0, bh = y1 - y0;
     Box proc{x0, y0, x1, y1};
-    if (h->p.collar_size > 0) proc = bexpand(proc, h->p.collar_size, h->p.collar_size);   // CorrelationView.h:128-131
-    const int pw = proc.x1 - proc.x0;
-    vwb200_dispi* disp = nullptr; int all_invalid = 0;
-    VWB_TRY(h->prerasterize(proc, &disp, &all_invalid, ar, st));
+    if (with_collar && h->p.collar_size > 0) proc = bexpand(proc, h->p.collar_size, h->p.collar_size);   // CorrelationView.h:128-131
+    const int pw = proc.x1 - proc.x0, ph = proc.y1 - proc.y0;
+    vwb200_corr::DiffTile df;
+    float* host_diff_window = nullptr;
+    if (h->diff) {                                                                                        // CorrelationView.cc:276-283
+      const int ulx = h->p.region_ul_x, uly = h->p.region_ul_y;
+      if (!(proc.x0 >= ulx && proc.y0 >= uly && proc.x1 <= ulx + h->diff_cols && proc.y1 <= uly + h->diff_rows)) {
+        set_error("The L-R to R-L difference image domain does not contain the current tile.");
+        return VWB200_EARG;
+      }
+      if (h->diff_on_device) { df.d = h->diff; df.pitch = h->diff_pitch; df.ox = proc.x0 - ulx; df.oy = proc.y0 - uly; }
+      else {                        // stage the tile's window (pixels the tile does not write keep their content)
+        host_diff_window = h->diff + ((ptrdiff_t)(proc.y0 - uly) * h->diff_pitch + (proc.x0 - ulx)) * 2;
+        VWB_TRY(ar.alloc(&df.d, (size_t)pw * ph * 2));
+        df.pitch = pw; df.ox = 0; df.oy = 0;
+        VWB_CUDA(cudaMemcpy2DAsync(df.d, (size_t)pw * 8, host_diff_window, (size_t)h->diff_pitch * 8, (size_t)pw * 8, ph, cudaMemcpyHostToDevice, st));
+      }
+    }
+    vwb200_dispi* disp = nullptr; float* sub = nullptr; int all_invalid = 0;
+    VWB_TRY(h->prerasterize(proc, &disp, &sub, &all_invalid, df, ar, st));
     float* dout = dest; ptrdiff_t dop = dest_pitch;
     if (!dest_on_device) { VWB_TRY(ar.alloc(&dout, (size_t)bw * bh * 3)); dop = bw; }
     if (all_invalid) {
       VWB_CUDA(cudaMemset2DAsync(dout, (size_t)dop * 12, 0, (size_t)bw * 12, bh, st));
+    } else if (sgm) {
+      VWB_TRY(sgm_finalize_launch(sub, disp, pw, h->p.search_x0, h->p.search_y0, dout, dop, x0 - proc.x0, y0 - proc.y0, bw, bh, st));
     } else {
-      VWB_TRY(finalize_launch(disp, pw, proc.y1 - proc.y0, h->p.search_x0, h->p.search_y0, dout, dop, x0 - proc.x0, y0 - proc.y0, bw, bh, st));
+      VWB_TRY(finalize_launch(disp, pw, ph, h->p.search_x0, h->p.search_y0, dout, dop, x0 - proc.x0, y0 - proc.y0, bw, bh, st));
     }
     if (!dest_on_device)
       VWB_CUDA(cudaMemcpy2DAsync(dest, (size_t)dest_pitch * 12, dout, (size_t)bw * 12, (size_t)bw * 12, bh, cudaMemcpyDeviceToHost, st));
+    if (host_diff_window && !all_invalid)
+      VWB_CUDA(cudaMemcpy2DAsync(host_diff_window, (size_t)h->diff_pitch * 8, df.d, (size_t)pw * 8, (size_t)pw * 8, ph, cudaMemcpyDeviceToHost, st));
+    VWB_CUDA(cudaStreamSynchronize(st));
   }
-  VWB_CUDA(cudaStreamSynchronize(st));
+  return VWB200_OK;
+}
+int vwb200_corr_rasterize(vwb200_corr* h, int x0, int y0, int x1, int y1, float* dest, ptrdiff_t dest_pitch, int dest_on_device, void* stream) {
+  return corr_rasterize_impl(h, x0, y0, x1, y1, dest, dest_pitch, dest_on_device, stream, true);
+}
+int vwb200_corr_prerasterize(vwb200_corr* h, int x0, int y0, int x1, int y1, float* dest, ptrdiff_t dest_pitch, int dest_on_device, void* stream) {
+  return corr_rasterize_impl(h, x0, y0, x1, y1, dest, dest_pitch, dest_on_device, stream, false);
+}
+int vwb200_corr_set_lr_disp_diff(vwb200_corr* h, float* diff, int cols, int rows, ptrdiff_t pitch, int on_device) {
+  if (!h || (diff && (cols <= 0 || rows <= 0 || pitch < cols))) { set_error("corr_set_lr_disp_diff: bad arguments"); return VWB200_EARG; }
+  h->diff = diff; h->diff_cols = cols; h->diff_rows = rows; h->diff_pitch = pitch; h->diff_on_device = on_device;
   return VWB200_OK;
 }
 

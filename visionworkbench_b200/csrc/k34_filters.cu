@@ -11,28 +11,33 @@ namespace vwb200 {
 __device__ __forceinline__ int clampi3(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ---- K3 -------------------------------------------------------------------------------------------
+// (qax, qay) is added to the R->L disparity before the comparison (the SGM branch keeps it un-shifted, :548-549, 586);
+// diff (optional): the lr_disp_diff image, PixelMask<float> = {value, valid} pairs; pixel (c + dox, r + doy) receives the
+// discrepancy of a pixel that passes (Correlate.cc:1476-1484)
 __device__ __forceinline__ void consistency_pixel(vwb200_dispi* p, int c, int r, const vwb200_dispi* r2l, int rw, int rh,
-                                                  ptrdiff_t rpitch, float thr) {
+                                                  ptrdiff_t rpitch, float thr, int qax = 0, int qay = 0, float2* diff = nullptr,
+                                                  ptrdiff_t dpitch = 0, int dox = 0, int doy = 0) {
   const vwb200_dispi v = *p;
   const int x = c + v.dx, y = r + v.dy;
   if (x < 0 || x >= rw || y < 0 || y >= rh) { p->valid = 0; return; }
   const vwb200_dispi q = r2l[(ptrdiff_t)y * rpitch + x];
   if (!v.valid || !q.valid) { p->valid = 0; return; }
-  const double a = fabs((double)(v.dx + q.dx)), b = fabs((double)(v.dy + q.dy));
-  const float diff = (float)(a > b ? a : b);
-  if (!(thr >= diff)) p->valid = 0;
+  const double a = fabs((double)(v.dx + q.dx + qax)), b = fabs((double)(v.dy + q.dy + qay));
+  const float d = (float)(a > b ? a : b);
+  if (!(thr >= d)) p->valid = 0;
+  else if (diff) diff[(ptrdiff_t)(r + doy) * dpitch + (c + dox)] = make_float2(d, 1.0f);
 }
 __global__ void consistency_kernel(vwb200_dispi* l2r, int lw, int lh, ptrdiff_t lpitch, const vwb200_dispi* r2l, int rw,
-                                   int rh, ptrdiff_t rpitch, float thr) {
+                                   int rh, ptrdiff_t rpitch, float thr, int qax, int qay, float2* diff, ptrdiff_t dpitch, int dox, int doy) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
   if (c >= lw || r >= lh) return;
-  consistency_pixel(l2r + (ptrdiff_t)r * lpitch + c, c, r, r2l, rw, rh, rpitch, thr);
+  consistency_pixel(l2r + (ptrdiff_t)r * lpitch + c, c, r, r2l, rw, rh, rpitch, thr, qax, qay, diff, dpitch, dox, doy);
 }
 int consistency_launch(vwb200_dispi* l2r, int lw, int lh, ptrdiff_t lpitch, const vwb200_dispi* r2l, int rw, int rh,
-                       ptrdiff_t rpitch, float thr, cudaStream_t st) {
+                       ptrdiff_t rpitch, float thr, cudaStream_t st, int qax, int qay, float* diff, ptrdiff_t dpitch, int dox, int doy) {
   if (lw <= 0 || lh <= 0) return VWB200_OK;
   dim3 b(32, 8), g((lw + 31) / 32, (lh + 7) / 8);
-  consistency_kernel<<<g, b, 0, st>>>(l2r, lw, lh, lpitch, r2l, rw, rh, rpitch, thr);
+  consistency_kernel<<<g, b, 0, st>>>(l2r, lw, lh, lpitch, r2l, rw, rh, rpitch, thr, qax, qay, reinterpret_cast<float2*>(diff), dpitch, dox, doy);
   VWB_LAUNCH_CHECK();
   return VWB200_OK;
 }
@@ -41,7 +46,8 @@ int consistency_launch(vwb200_dispi* l2r, int lw, int lh, ptrdiff_t lpitch, cons
 // image, then "+= zone.disparity_range().min()" (CorrelationView.cc:691-698).  One launch per level.
 __global__ void zone_post_kernel(const Tile* __restrict__ tiles, const Zone* __restrict__ zones, const Zone* __restrict__ rlzones,
                                  const int2* __restrict__ post_add, vwb200_dispi* __restrict__ disp,
-                                 const vwb200_dispi* __restrict__ rl, float thr, int tile_w, int tile_h) {
+                                 const vwb200_dispi* __restrict__ rl, float thr, int tile_w, int tile_h, float2* diff, ptrdiff_t dpitch,
+                                 int dox, int doy) {
   const Tile t = tiles[blockIdx.x];
   const Zone z = zones[t.zone];
   const int tw = min(tile_w, z.w - t.tx), th = min(tile_h, z.h - t.ty);
@@ -51,16 +57,20 @@ __global__ void zone_post_kernel(const Tile* __restrict__ tiles, const Zone* __r
     vwb200_dispi* p = disp + z.obase + (ptrdiff_t)y * z.opitch + x;
     if (rl) {
       const Zone q = rlzones[t.zone];
-      consistency_pixel(p, x, y, rl + q.obase, q.w, q.h, q.opitch, thr);
+      // lr_disp_diff: ul_corner_offset = zone.image_region().min() + bbox.min() - region_ul (CorrelationView.cc:669-676)
+      const int zx0 = (int)(z.obase % z.opitch), zy0 = (int)(z.obase / z.opitch);
+      consistency_pixel(p, x, y, rl + q.obase, q.w, q.h, q.opitch, thr, 0, 0, diff, dpitch, dox + zx0, doy + zy0);
     }
     p->dx += add.x;
     p->dy += add.y;
   }
 }
 int zone_post_launch(const Tile* d_tiles, int ntiles, const Zone* d_zones, const Zone* d_rlzones, const int2* d_post_add,
-                     vwb200_dispi* disp, const vwb200_dispi* rl, float thr, int tile_w, int tile_h, cudaStream_t st) {
+                     vwb200_dispi* disp, const vwb200_dispi* rl, float thr, int tile_w, int tile_h, cudaStream_t st, float* diff,
+                     ptrdiff_t dpitch, int dox, int doy) {
   if (ntiles <= 0) return VWB200_OK;
-  zone_post_kernel<<<ntiles, 128, 0, st>>>(d_tiles, d_zones, d_rlzones, d_post_add, disp, rl, thr, tile_w, tile_h);
+  zone_post_kernel<<<ntiles, 128, 0, st>>>(d_tiles, d_zones, d_rlzones, d_post_add, disp, rl, thr, tile_w, tile_h,
+                                           reinterpret_cast<float2*>(diff), dpitch, dox, doy);
   VWB_LAUNCH_CHECK();
   return VWB200_OK;
 }
@@ -191,6 +201,99 @@ int finalize_launch(const vwb200_dispi* in, int w, int h, int ax, int ay, float*
   return VWB200_OK;
 }
 
+
+// ---- lr_disp_diff: invalidate where the final disparity is invalid (CorrelationView.cc:848-857) -----------------------
+__global__ void diff_invalidate_kernel(const vwb200_dispi* __restrict__ disp, int w, int h, float2* __restrict__ diff, ptrdiff_t dpitch,
+                                       int dox, int doy) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= w || r >= h) return;
+  if (!disp[(size_t)r * w + c].valid) diff[(ptrdiff_t)(r + doy) * dpitch + (c + dox)].y = 0.0f;
+}
+int diff_invalidate_launch(const vwb200_dispi* disp, int w, int h, float* diff, ptrdiff_t dpitch, int dox, int doy, cudaStream_t st) {
+  if (w <= 0 || h <= 0) return VWB200_OK;
+  diff_invalidate_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, st>>>(disp, w, h, reinterpret_cast<float2*>(diff), dpitch, dox, doy);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
+// ---- SGM branch: result = subpixel_disparity + search_region.min(), valid where both the sub-pixel view and the filtered
+// integer disparity are (CorrelationView.cc:859-871; PixelMask sums keep the child values of invalid pixels) ------------------
+__global__ void sgm_finalize_kernel(const float* __restrict__ sub, const vwb200_dispi* __restrict__ disp, int w, float ax, float ay,
+                                    float* __restrict__ out, ptrdiff_t opitch_px, int ox, int oy, int ow, int oh) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= ow || y >= oh) return;
+  const size_t src = (size_t)(oy + y) * w + (ox + x);
+  float* o = out + ((ptrdiff_t)y * opitch_px + x) * 3;
+  o[0] = __fadd_rn(sub[3 * src], ax);
+  o[1] = __fadd_rn(sub[3 * src + 1], ay);
+  o[2] = (sub[3 * src + 2] != 0.0f && disp[src].valid) ? 1.0f : 0.0f;
+}
+int sgm_finalize_launch(const float* sub, const vwb200_dispi* disp, int w, int ax, int ay, float* out, ptrdiff_t opitch_px, int ox, int oy,
+                        int ow, int oh, cudaStream_t st) {
+  if (ow <= 0 || oh <= 0) return VWB200_OK;
+  sgm_finalize_kernel<<<dim3((ow + 127) / 128, oh), 128, 0, st>>>(sub, disp, w, (float)ax, (float)ay, out, opitch_px, ox, oy, ow, oh);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
+// ---- disparity_blob_filter (CorrelationView.cc:242-271; BlobIndexThreaded, Image/BlobIndex.h:385-454; ErodeView.h:196-218):
+// 8-connected components of the valid pixels by union-find on pixel indices (the smaller index is the root, so the forest is
+// the same whatever the thread order); components of at most `area` pixels become result_type() = {0, 0, invalid}.
+__device__ __forceinline__ int uf_root(const int* parent, int i) { int p; while ((p = parent[i]) != i) i = p; return i; }
+__device__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_root(parent, a); b = uf_root(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }          // a > b: hang a under b
+    const int old = atomicMin(parent + a, b);
+    if (old == a) return;
+    a = old;                                               // somebody else moved a meanwhile: merge its new parent with b
+  }
+}
+__global__ void blob_init_kernel(const vwb200_dispi* __restrict__ d, int n, int* __restrict__ parent, int* __restrict__ size) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  parent[i] = d[i].valid ? i : -1;
+  size[i] = 0;
+}
+__global__ void blob_union_kernel(const vwb200_dispi* __restrict__ d, int w, int h, int* __restrict__ parent) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int i = y * w + x;
+  if (!d[i].valid) return;
+  if (x > 0 && d[i - 1].valid) uf_union(parent, i, i - 1);
+  if (y > 0) {
+    if (d[i - w].valid) uf_union(parent, i, i - w);
+    if (x > 0 && d[i - w - 1].valid) uf_union(parent, i, i - w - 1);
+    if (x < w - 1 && d[i - w + 1].valid) uf_union(parent, i, i - w + 1);
+  }
+}
+__global__ void blob_count_kernel(int n, int* __restrict__ parent, int* __restrict__ size) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || parent[i] < 0) return;
+  const int r = uf_root(parent, i);
+  parent[i] = r;                                           // compress (roots keep pointing at themselves)
+  atomicAdd(size + r, 1);
+}
+__global__ void blob_erode_kernel(vwb200_dispi* __restrict__ d, int n, const int* __restrict__ parent, const int* __restrict__ size, int area) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || parent[i] < 0) return;
+  if (size[uf_root(parent, i)] <= area) { vwb200_dispi z; z.dx = 0; z.dy = 0; z.valid = 0; d[i] = z; }
+}
+int blob_filter_launch(vwb200_dispi* d, int w, int h, int area, int* work /* 2 * w * h ints */, cudaStream_t st) {
+  if (area < 1 || w <= 0 || h <= 0) return VWB200_OK;      // CorrelationView.cc:249-250
+  const int n = w * h;
+  int* parent = work; int* size = work + n;
+  blob_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(d, n, parent, size);
+  VWB_LAUNCH_CHECK();
+  blob_union_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, st>>>(d, w, h, parent);
+  VWB_LAUNCH_CHECK();
+  blob_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, parent, size);
+  VWB_LAUNCH_CHECK();
+  blob_erode_kernel<<<(n + 255) / 256, 256, 0, st>>>(d, n, parent, size, area);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
 
 // ====================================================================================================
 // a11: ParabolaSubpixelView (Stereo/ParabolaSubpixelView.cc:31-330)

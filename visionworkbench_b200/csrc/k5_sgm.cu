@@ -607,7 +607,8 @@ int sgm_bounds_run(const SgmArgs& a, int ow, int oh, int* d_bounds, Arena& ar, c
   return VWB200_OK;
 }
 
-int sgm_run(const SgmArgs& a, Arena& ar, cudaStream_t st) {
+int sgm_run(const SgmArgs& a, Arena& /*callers_arena*/, cudaStream_t st) {
+  Arena ar(st);                 // everything allocated here is released (stream-ordered) when the call returns
   const int k = a.k;
   if (k != 3 && k != 5 && k != 7 && k != 9) {
     set_error("Census transforms are only available in size 3, 5, 7, and 9.");       // SGM.cc:1885-1888
