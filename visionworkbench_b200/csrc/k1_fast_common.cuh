@@ -43,10 +43,24 @@ static inline FastGeom make_geom(int W, int H, int sx, int sy, int kx, int ky) {
   g.rrows = g.NB * F_TH + ky - 1 + sy;
   g.rw = ((F_COLS + sx + 7) / 8) * 8 + 8;
   g.lox = g.loy = g.rox = g.roy = 0; g.addx = g.addy = 0; g.scale = F_B; g.dynamic_units = 1; g.sd = 1;
-  // enough work items to fill 148 persistent CTAs several times over: split the dy range when the raster is small
+  // The work items (strip x band x dy-chunk) are dealt round-robin to 148 persistent CTAs, so the last partial wave idles
+  // part of the chip: 1120 items = 7.57 waves run as 8 (efficiency 0.946 -- the 8-GPU share of the 8192^2 raster).  Split
+  // the dy range into J chunks (merged by k1_fast_merge) so that items * J fills its last wave: pick the J with the best
+  // wave efficiency, charging each extra chunk the measured ~0.4 % for its partial planes and the merge pass.  Small
+  // rasters additionally want >= ~6 waves for balance.
   g.J = 1;
   const int items = g.NS * g.NB;
-  if (items < 3 * 148) { g.J = (6 * 148 + items - 1) / items; if (g.J > 8) g.J = 8; if (g.J > (sy + 7) / 8) g.J = (sy + 7) / 8; if (g.J < 1) g.J = 1; }
+  const int jmax = sy / 8 < 1 ? 1 : (sy / 8 > 8 ? 8 : sy / 8);
+  if (items < 64 * 148) {
+    double best = -1.0;
+    for (int J = 1; J <= jmax; ++J) {
+      const double w = (double)items * J / 148.0;
+      const long long full = (long long)((items * (long long)J + 147) / 148);
+      double eff = w / (double)full * (1.0 - 0.004 * (J - 1));
+      if (w < 6.0) eff *= 0.5 + w / 12.0;          // few waves: uneven items (edge strips / bands) are not averaged out
+      if (eff > best + 1e-9) { best = eff; g.J = J; }
+    }
+  }
   g.dy_per = (sy + g.J - 1) / g.J;
   g.J = (sy + g.dy_per - 1) / g.dy_per;
   return g;
