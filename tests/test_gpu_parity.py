@@ -542,5 +542,6 @@ def test_sgm_subpixel_modes(vwb, oracle, mode):
     assert np.abs(gf - rf).max() <= 1e-5, float(np.abs(gf - rf).max())
     if mode:
         assert (gf[..., 0] != np.floor(gf[..., 0])).mean() > 0.5          # offsets were applied
-    with pytest.raises(vwb.NoImplErr):
-        vwb.calc_disparity_sgm_subpixel(left, right, (8, 8), 5, 1)
+    gi1, gf1 = vwb.calc_disparity_sgm_subpixel(left, right, (8, 8), 5, 1)          # SUBPIXEL_PARABOLA (2-D fit)
+    ri1, rf1, _ = oracle.calc_disparity_sgm(left, right, (8, 8), 5, subpixel_mode=1, memory_limit_mb=1e9)
+    assert np.array_equal(gi1, ri1) and np.abs(gf1 - rf1).max() <= 1e-5
