@@ -494,7 +494,7 @@ def cfg5_sharded(v, world, rank, dist, torch, size=16384, s=256, k=15):
     bad = None
     if rank == 0:      # parity of sampled tiles on rank 0 (rows assembled from its own band + the received halo)
         L, R = dl.cpu().numpy(), dr.cpu().numpy()
-        tiles = [(0, 0), (size - 128, H - 128), (236 * 11 - 64, H - 128), (5000, 32 * 7 - 64)]
+        tiles = [(0, 0), (size - 128, H - 128), (min(236 * 11 - 64, size - 128), H - 128), (min(5000, size - 128), 32 * 7 - 64)]
         bad = oracle_tile_check(0, L, R, out.cpu().numpy(), (s, s), (k, k), tiles, 128)
     evals = size * size * s * s
     kmean = float(np.mean(kms))
@@ -516,9 +516,11 @@ def run_ours(a):
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL's INFO lines (communicator size, rings, NVLS) go to stderr; stdout stays the one JSON line
+        # NCCL's INFO lines (communicator size, rings, NVLS) are collected in a per-rank file and replayed on stderr at the
+        # end; stdout stays the one JSON line
         os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        nccl_log = os.path.join(tempfile.gettempdir(), f"vwb200_nccl_{os.getpid()}.log")
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert v.device_count() > 0
     cost = COSTS[a.cost]
@@ -669,6 +671,12 @@ def run_ours(a):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+        try:
+            sys.stderr.write(open(nccl_log).read())
+            sys.stderr.flush()
+            os.unlink(nccl_log)
+        except Exception:
+            pass
 
 
 if __name__ == "__main__":
