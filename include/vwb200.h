@@ -240,6 +240,35 @@ int  vwb200_corr_prerasterize(vwb200_corr* h, int x0, int y0, int x1, int y1,
 int  vwb200_corr_num_levels(const vwb200_corr* h, int bw, int bh);
 void vwb200_corr_destroy(vwb200_corr* h);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU sharding (the reference has no distributed code): the unit of the path is the output
+ * tile (tools/correlate.cc:266, Image/ImageIO.h:289-311), tiles are independent, so a raster shards into contiguous
+ * output-row bands, one rank per GPU, with no reduction.  When the INPUT rasters are row-sharded the same way, rank r
+ * needs from rank r + 1 the rows its last kernel windows and search rows reach into (ky - 1 rows of the left raster,
+ * ky - 1 + sy - 1 of the right one): vwb200_shard_exchange_halos moves them with ncclSend / ncclRecv in one NCCL group.
+ * NCCL is bound at run time (libnccl.so.2); without it vwb200_shard_create(world > 1) returns VWB200_ENOIMPL.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t rank, world;
+  int32_t y0, y1;                 /* output rows [y0, y1) of this rank */
+  int32_t left_rows, right_rows;  /* rows of the left / right raster this rank's launch reads */
+  int32_t own_left, own_right;    /* rows resident on this rank before the exchange */
+  int32_t recv_left, recv_right;  /* halo rows received from rank + 1 */
+  int32_t send_left, send_right;  /* rows sent to rank - 1 (its halo) */
+} vwb200_band_plan;
+typedef struct vwb200_shard vwb200_shard;
+/* band arithmetic for out_rows output rows (left_total_rows / right_total_rows <= 0: out_rows + ky - 1 [+ sy - 1]) */
+int  vwb200_shard_plan(int rank, int world, int out_rows, int ky, int sy, int left_total_rows, int right_total_rows,
+                       vwb200_band_plan* plan);
+/* rank 0 calls this and hands the 128 bytes to every rank (MPI_Bcast, a file, torch.distributed, ...) */
+int  vwb200_shard_unique_id(void* id128);
+/* collective: every rank calls it with the same id on its own (current) device */
+int  vwb200_shard_create(const void* id128, int rank, int world, vwb200_shard** out);
+/* asynchronous on `stream` (NULL = the legacy default stream) */
+int  vwb200_shard_exchange_halos(vwb200_shard* s, const vwb200_band_plan* plan, float* left_band, int lcols, ptrdiff_t lpitch,
+                                 float* right_band, int rcols, ptrdiff_t rpitch, void* stream);
+void vwb200_shard_destroy(vwb200_shard* s);
+
 /* total number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 long long vwb200_kernel_launches(void);
 

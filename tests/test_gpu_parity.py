@@ -545,3 +545,29 @@ def test_sgm_subpixel_modes(vwb, oracle, mode):
     gi1, gf1 = vwb.calc_disparity_sgm_subpixel(left, right, (8, 8), 5, 1)          # SUBPIXEL_PARABOLA (2-D fit)
     ri1, rf1, _ = oracle.calc_disparity_sgm(left, right, (8, 8), 5, subpixel_mode=1, memory_limit_mb=1e9)
     assert np.array_equal(gi1, ri1) and np.abs(gf1 - rf1).max() <= 1e-5
+
+
+@pytest.mark.parametrize("cost", [0, 1, 2])
+def test_host_rasters_are_fed_in_bands(vwb, oracle, cost, monkeypatch):
+    """the tile feeder of vwb200_calc_disparity (host buffers): H2D / correlate / D2H overlapped over output-row bands with
+    three rotating band buffers; results identical to the one-shot path and to the oracle, whatever the band height"""
+    from visionworkbench_b200.synth import make_rasters
+    left, right = make_rasters(300, 333, (24, 17), (9, 7), seed=77 + cost)
+    ref = oracle.calc_disparity(cost, left, right, (24, 17), (9, 7))
+    for rows in ("32", "64", "100", "320"):          # 11, 6, 4 and 2 bands (the last one ragged)
+        monkeypatch.setenv("VWB200_BAND_ROWS", rows)
+        got = vwb.calc_disparity(cost, left, right, (24, 17), (9, 7))
+        _assert_disp_equal(got, ref, f"bands of {rows} rows, cost {cost}")
+    monkeypatch.delenv("VWB200_BAND_ROWS")
+    monkeypatch.setenv("VWB200_NO_PIPELINE", "1")
+    _assert_disp_equal(vwb.calc_disparity(cost, left, right, (24, 17), (9, 7)), ref, "one shot")
+    # a strided (pitched) host view goes through the same feeder
+    big_l = np.zeros((left.shape[0], left.shape[1] + 13), np.float32); big_l[:, :left.shape[1]] = left
+    monkeypatch.delenv("VWB200_NO_PIPELINE")
+    monkeypatch.setenv("VWB200_BAND_ROWS", "64")
+    import ctypes as C
+    out = np.empty((333, 300, 3), np.int32)
+    rc = vwb.lib().vwb200_calc_disparity(cost, big_l.ctypes.data, left.shape[1], left.shape[0], big_l.shape[1], right.ctypes.data, right.shape[1],
+                                         right.shape[0], right.shape[1], 24, 17, 9, 7, out.ctypes.data, 300, 0, None)
+    assert rc == 0
+    _assert_disp_equal(out, ref, "pitched input")

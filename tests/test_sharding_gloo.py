@@ -61,3 +61,30 @@ def test_halo_exchange_reassembles_the_rasters(world):
     by_rank = {r: n for r, _, n in res}
     assert by_rank[world - 1] == 0
     assert by_rank[0] == ((ky - 1) * (width + ky - 1) + (ky - 1 + sy - 1) * (width + ky - 1 + sy - 1)) * 4
+
+
+def test_c_abi_plan_and_single_rank_comm():
+    """vwb200_shard_plan (the arithmetic behind sharding.plan) against the closed form, and the world-size-1 communicator:
+    no NCCL, no device, exchange is a no-op (the N > 1 NCCL path is exercised by bench.py on GPUs)"""
+    import ctypes as C
+    for world in (1, 2, 3, 8):
+        for out_rows, ky, sy in ((8192, 21, 128), (16384, 15, 256), (1000, 7, 9)):
+            covered = []
+            for r in range(world):
+                p = sharding.plan(r, world, out_rows, ky, sy)
+                band = (out_rows + world - 1) // world
+                assert (p.y0, p.y1) == (min(out_rows, r * band), min(out_rows, (r + 1) * band))
+                h = p.y1 - p.y0
+                assert p.left_rows == h + ky - 1 and p.right_rows == h + ky - 1 + sy - 1
+                last = r == world - 1 or p.y1 >= out_rows
+                assert p.recv_left == (0 if last else ky - 1) and p.recv_right == (0 if last else ky - 1 + sy - 1)
+                assert p.send_left == (ky - 1 if r and h else 0) and p.send_right == (ky - 1 + sy - 1 if r and h else 0)
+                covered += list(range(p.y0, p.y1))
+            assert covered == list(range(out_rows))
+    comm = sharding.ShardComm(0, 1)
+    p = sharding.plan(0, 1, 64, 5, 7)
+    from visionworkbench_b200 import api
+    cp = sharding._cplan(p)
+    buf = (C.c_float * 16)()
+    assert api.lib().vwb200_shard_exchange_halos(comm._h, C.byref(cp), buf, 4, 4, buf, 4, 4, None) == 0
+    comm.close()

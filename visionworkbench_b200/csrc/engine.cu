@@ -754,6 +754,154 @@ int vwb200_device_count(void) {
 long long vwb200_kernel_launches(void) { return g_launches.load(); }
 int vwb200_last_k1_stats(vwb200_k1_stats* out) { if (!out) return VWB200_EARG; *out = t_k1_stats; return VWB200_OK; }
 
+// calc_disparity on device-resident rasters: statistics -> kernel choice -> launch(es).  Results are bit-identical
+// whichever kernel runs, so callers may split a raster into bands freely.
+static int calc_disparity_device(int cost_type, ImgF Li, ImgF Ri, int W, int H, int sx, int sy, int kx, int ky, vwb200_dispi* dout, ptrdiff_t dop,
+                                 Arena& ar, cudaStream_t st, const KEvents* kev, int* path_out) {
+  int path = 1;
+  float* d_stats; float hs[6];
+  VWB_TRY(ar.alloc(&d_stats, 6));
+  VWB_TRY(image_stats_launch(Li, d_stats, st));
+  VWB_TRY(image_stats_launch(Ri, d_stats + 3, st));
+  VWB_CUDA(cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  VWB_CUDA(cudaStreamSynchronize(st));
+  const float vmin = std::min(hs[0], hs[3]), vmax = std::max(hs[1], hs[4]);
+  const bool integer = hs[2] != 0.0f && hs[5] != 0.0f;
+  // exact-integer fast path when the imagery allows it
+  if (k1_fast_supported(cost_type, kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK) {
+    const size_t wb = k1_fast_workspace_bytes(W, H, sx, sy, kx, ky);
+    unsigned char* ws;
+    VWB_TRY(ar.alloc(&ws, wb));
+    VWB_TRY(k1_fast_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, vmin, vmax, dout, dop, ws, wb, st, kev));
+    path = 0;
+  } else if (k1_screen_supported(cost_type, kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK && !getenv("VWB200_K1_GENERIC")) {
+    unsigned char* ws;
+    VWB_TRY(ar.alloc(&ws, k1_screen_workspace_bytes(cost_type, W, H, sx, sy, kx, ky)));
+    VWB_TRY(k1_screen_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, vmin, vmax, dout, dop, ws, st, kev));
+    path = 0;
+  }
+  if (path == 1) {
+    std::vector<Zone> zones(1);
+    Zone& z = zones[0];
+    z.obase = 0; z.opitch = (int)dop; z.w = W; z.h = H; z.lx = 0; z.ly = 0; z.rx = 0; z.ry = 0; z.sx = sx; z.sy = sy; z.addx = 0; z.addy = 0;
+    VWB_TRY(run_k1_zones(cost_type, Li, Ri, zones, kx, ky, dout, ar, st, nullptr, nullptr, nullptr, kev));
+  }
+  *path_out = path;
+  return VWB200_OK;
+}
+
+namespace {
+struct EventGuard {              // RAII for the cudaEvents of one call (they used to leak on the error paths)
+  std::vector<cudaEvent_t> ev;
+  int make(cudaEvent_t* out, unsigned flags = cudaEventDefault) {
+    cudaEvent_t e;
+    VWB_CUDA(cudaEventCreateWithFlags(&e, flags));
+    ev.push_back(e); *out = e;
+    return VWB200_OK;
+  }
+  ~EventGuard() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+struct ExtraStream {
+  cudaStream_t s = nullptr;
+  int init() { VWB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return VWB200_OK; }
+  ~ExtraStream() { if (s) cudaStreamDestroy(s); }
+};
+}  // namespace
+
+// Host-resident rasters (the tile feeder; caller pattern Image/ImageIO.h:150-314): the output rows are cut
+// into bands; band b's input rows go up on a copy stream while band b-1 is correlated and band b-2's result comes down on
+// a third stream.  Three band-sized buffer sets rotate, so the rasters never have to be resident as a whole.
+static int calc_disparity_host_pipelined(int cost_type, const float* left, int lw, int lh, ptrdiff_t lpitch, const float* right, ptrdiff_t rpitch,
+                                         int sx, int sy, int kx, int ky, vwb200_dispi* out, ptrdiff_t opitch, cudaStream_t st, int* path_out,
+                                         float* kernel_ms_out) {
+  const int W = lw - kx + 1, H = lh - ky + 1, rw = lw + sx - 1;
+  // band schedule: a short first band (the kernels start after ~1 ms of upload), a short last band (only ~1 ms of
+  // download is left when the kernels end), and in between bands as tall as a quarter of the free HBM allows -- tall
+  // bands keep the persistent kernels' wave efficiency, the copies of a tall band hide behind its neighbours' kernels
+  std::vector<int> ys;          // band b = output rows [ys[b], ys[b + 1])
+  {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t row_bytes = (size_t)lw * 4 + (size_t)rw * 4 + (size_t)W * sizeof(vwb200_dispi);
+    long long cap = (long long)(free_b / 4 / (3 * row_bytes));
+    cap = std::max<long long>(256, cap / 32 * 32);
+    int edge = 512;
+    if (const char* e = getenv("VWB200_BAND_ROWS")) { edge = std::max(32, atoi(e)); cap = edge; }
+    ys.push_back(0);
+    if (H > 3 * edge) {
+      ys.push_back(edge);
+      int y = edge;
+      const int mid_end = H - edge;
+      while (y < mid_end) { y = (int)std::min<long long>(mid_end, y + cap); ys.push_back(y); }
+      ys.push_back(H);
+    } else {
+      for (int y = edge; y < H; y += edge) ys.push_back(y);
+      ys.push_back(H);
+    }
+  }
+  const int NB = (int)ys.size() - 1;
+  int BH = 0;
+  for (int b = 0; b < NB; ++b) BH = std::max(BH, ys[b + 1] - ys[b]);
+  constexpr int NBUF = 3;
+  ExtraStream s_in, s_out;
+  VWB_TRY(s_in.init()); VWB_TRY(s_out.init());
+  EventGuard evs;
+  std::vector<cudaEvent_t> in_done(NB), comp_done(NB), out_done(NB), k0(NB), k1(NB);
+  for (int b = 0; b < NB; ++b) {
+    VWB_TRY(evs.make(&in_done[b], cudaEventDisableTiming)); VWB_TRY(evs.make(&comp_done[b], cudaEventDisableTiming));
+    VWB_TRY(evs.make(&out_done[b], cudaEventDisableTiming)); VWB_TRY(evs.make(&k0[b])); VWB_TRY(evs.make(&k1[b]));
+  }
+  Arena ar(st);
+  const int lrows_max = BH + ky - 1, rrows_max = lrows_max + sy - 1;
+  float* bl[NBUF]; float* br[NBUF]; vwb200_dispi* bo[NBUF];
+  for (int i = 0; i < std::min(NBUF, NB); ++i) {
+    VWB_TRY(ar.alloc(&bl[i], (size_t)lrows_max * lw));
+    VWB_TRY(ar.alloc(&br[i], (size_t)rrows_max * rw));
+    VWB_TRY(ar.alloc(&bo[i], (size_t)BH * W));
+  }
+  cudaEvent_t alloc_done;
+  VWB_TRY(evs.make(&alloc_done, cudaEventDisableTiming));
+  VWB_CUDA(cudaEventRecord(alloc_done, st));
+  VWB_CUDA(cudaStreamWaitEvent(s_in.s, alloc_done, 0));
+  auto upload = [&](int b) -> int {
+    const int y0 = ys[b], h = ys[b + 1] - ys[b], buf = b % NBUF;
+    if (b >= NBUF) VWB_CUDA(cudaStreamWaitEvent(s_in.s, comp_done[b - NBUF], 0));       // the buffers are free again
+    VWB_CUDA(cudaMemcpy2DAsync(bl[buf], (size_t)lw * 4, left + (ptrdiff_t)y0 * lpitch, (size_t)lpitch * 4, (size_t)lw * 4, h + ky - 1,
+                               cudaMemcpyHostToDevice, s_in.s));
+    VWB_CUDA(cudaMemcpy2DAsync(br[buf], (size_t)rw * 4, right + (ptrdiff_t)y0 * rpitch, (size_t)rpitch * 4, (size_t)rw * 4, h + ky - 1 + sy - 1,
+                               cudaMemcpyHostToDevice, s_in.s));
+    VWB_CUDA(cudaEventRecord(in_done[b], s_in.s));
+    return VWB200_OK;
+  };
+  for (int b = 0; b < std::min(NBUF, NB); ++b) VWB_TRY(upload(b));
+  int path = 0;
+  for (int b = 0; b < NB; ++b) {
+    const int y0 = ys[b], h = ys[b + 1] - ys[b], buf = b % NBUF;
+    VWB_CUDA(cudaStreamWaitEvent(st, in_done[b], 0));
+    if (b >= NBUF) VWB_CUDA(cudaStreamWaitEvent(st, out_done[b - NBUF], 0));             // its output buffer has been read back
+    const ImgF Li{bl[buf], lw, h + ky - 1, lw}, Ri{br[buf], rw, h + ky - 1 + sy - 1, rw};
+    KEvents kev; kev.e0 = k0[b]; kev.e1 = k1[b];
+    int pth = 1;
+    {
+      Arena band(st);            // the band's workspace is returned to the pool as soon as its kernels are queued
+      VWB_TRY(calc_disparity_device(cost_type, Li, Ri, W, h, sx, sy, kx, ky, bo[buf], W, band, st, &kev, &pth));
+    }
+    path = std::max(path, pth);
+    VWB_CUDA(cudaEventRecord(comp_done[b], st));
+    VWB_CUDA(cudaStreamWaitEvent(s_out.s, comp_done[b], 0));
+    VWB_CUDA(cudaMemcpy2DAsync(out + (ptrdiff_t)y0 * opitch, (size_t)opitch * sizeof(vwb200_dispi), bo[buf], (size_t)W * sizeof(vwb200_dispi),
+                               (size_t)W * sizeof(vwb200_dispi), h, cudaMemcpyDeviceToHost, s_out.s));
+    VWB_CUDA(cudaEventRecord(out_done[b], s_out.s));
+    if (b + NBUF < NB) VWB_TRY(upload(b + NBUF));
+  }
+  VWB_CUDA(cudaStreamSynchronize(s_out.s));
+  VWB_CUDA(cudaStreamSynchronize(st));
+  float total = 0.0f;
+  for (int b = 0; b < NB; ++b) { float ms = 0.0f; if (cudaEventElapsedTime(&ms, k0[b], k1[b]) == cudaSuccess) total += ms; else cudaGetLastError(); }
+  *kernel_ms_out = total; *path_out = path;
+  return VWB200_OK;
+}
+
 int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrdiff_t lpitch,
                           const float* right, int rw, int rh, ptrdiff_t rpitch,
                           int sx, int sy, int kx, int ky, vwb200_dispi* out, ptrdiff_t opitch,
@@ -765,62 +913,39 @@ int vwb200_calc_disparity(int cost_type, const float* left, int lw, int lh, ptrd
   if (rw < lw + sx - 1 || rh < lh + sy - 1) { set_error("calc_disparity: right raster smaller than region + search volume - 1."); return VWB200_EARG; }
   if (cost_type < 0 || cost_type > 2) { set_error("calc_disparity: unsupported cost type %d", cost_type); return VWB200_EARG; }
   if (!left || !right || !out) { set_error("calc_disparity: null pointer"); return VWB200_EARG; }
+  if (lpitch < lw || rpitch < lw + sx - 1 || opitch < lw - kx + 1) { set_error("calc_disparity: a row pitch is smaller than its row"); return VWB200_EARG; }
   VWB_TRY(ensure_device());
   StreamGuard sg; VWB_TRY(sg.init(stream, on_device));
   cudaStream_t st = sg.st;
   const long long launches0 = g_launches.load();
-  KEvents kev;
-  VWB_CUDA(cudaEventCreate(&kev.e0));
-  VWB_CUDA(cudaEventCreate(&kev.e1));
-  {
-    Arena ar(st);
-    const int W = lw - kx + 1, H = lh - ky + 1;
-    const float *dl, *dr; ptrdiff_t dlp, drp;
-    VWB_TRY(stage_in(left, lw, lh, lpitch, on_device, ar, st, &dl, &dlp));
-    VWB_TRY(stage_in(right, lw + sx - 1, lh + sy - 1, rpitch, on_device, ar, st, &dr, &drp));
-    vwb200_dispi* dout = out; ptrdiff_t dop = opitch;
-    if (!on_device) { VWB_TRY(ar.alloc(&dout, (size_t)W * H)); dop = W; }
-    const ImgF Li{dl, lw, lh, dlp}, Ri{dr, lw + sx - 1, lh + sy - 1, drp};
-    int path = 1;
-    // exact-integer fast path when the imagery allows it
+  const int W = lw - kx + 1, H = lh - ky + 1;
+  int path = 1;
+  float kernel_ms = 0.0f;
+  if (!on_device && (H > 1024 || getenv("VWB200_BAND_ROWS")) && !getenv("VWB200_NO_PIPELINE")) {
+    VWB_TRY(calc_disparity_host_pipelined(cost_type, left, lw, lh, lpitch, right, rpitch, sx, sy, kx, ky, out, opitch, st, &path, &kernel_ms));
+  } else {
+    EventGuard evs;
+    KEvents kev;
+    VWB_TRY(evs.make(&kev.e0)); VWB_TRY(evs.make(&kev.e1));
     {
-      float* d_stats; float hs[6];
-      VWB_TRY(ar.alloc(&d_stats, 6));
-      VWB_TRY(image_stats_launch(Li, d_stats, st));
-      VWB_TRY(image_stats_launch(Ri, d_stats + 3, st));
-      VWB_CUDA(cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
-      VWB_CUDA(cudaStreamSynchronize(st));
-      const float vmin = std::min(hs[0], hs[3]), vmax = std::max(hs[1], hs[4]);
-      const bool integer = hs[2] != 0.0f && hs[5] != 0.0f;
-      if (k1_fast_supported(cost_type, kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK) {
-        const size_t wb = k1_fast_workspace_bytes(W, H, sx, sy, kx, ky);
-        unsigned char* ws;
-        VWB_TRY(ar.alloc(&ws, wb));
-        VWB_TRY(k1_fast_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, vmin, vmax, dout, dop, ws, wb, st, &kev));
-        path = 0;
-      } else if (k1_screen_supported(cost_type, kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK && !getenv("VWB200_K1_GENERIC")) {
-        unsigned char* ws;
-        VWB_TRY(ar.alloc(&ws, k1_screen_workspace_bytes(cost_type, W, H, sx, sy, kx, ky)));
-        VWB_TRY(k1_screen_launch(cost_type, Li, Ri, W, H, sx, sy, kx, ky, vmin, vmax, dout, dop, ws, st, &kev));
-        path = 0;
-      }
+      Arena ar(st);
+      const float *dl, *dr; ptrdiff_t dlp, drp;
+      VWB_TRY(stage_in(left, lw, lh, lpitch, on_device, ar, st, &dl, &dlp));
+      VWB_TRY(stage_in(right, lw + sx - 1, lh + sy - 1, rpitch, on_device, ar, st, &dr, &drp));
+      vwb200_dispi* dout = out; ptrdiff_t dop = opitch;
+      if (!on_device) { VWB_TRY(ar.alloc(&dout, (size_t)W * H)); dop = W; }
+      const ImgF Li{dl, lw, lh, dlp}, Ri{dr, lw + sx - 1, lh + sy - 1, drp};
+      VWB_TRY(calc_disparity_device(cost_type, Li, Ri, W, H, sx, sy, kx, ky, dout, dop, ar, st, &kev, &path));
+      if (!on_device)
+        VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch * sizeof(vwb200_dispi), dout, (size_t)W * sizeof(vwb200_dispi),
+                                   (size_t)W * sizeof(vwb200_dispi), H, cudaMemcpyDeviceToHost, st));
     }
-    if (path == 1) {
-      std::vector<Zone> zones(1);
-      Zone& z = zones[0];
-      z.obase = 0; z.opitch = (int)dop; z.w = W; z.h = H; z.lx = 0; z.ly = 0; z.rx = 0; z.ry = 0; z.sx = sx; z.sy = sy; z.addx = 0; z.addy = 0;
-      VWB_TRY(run_k1_zones(cost_type, Li, Ri, zones, kx, ky, dout, ar, st, nullptr, nullptr, nullptr, &kev));
-    }
-    if (!on_device)
-      VWB_CUDA(cudaMemcpy2DAsync(out, (size_t)opitch * sizeof(vwb200_dispi), dout, (size_t)W * sizeof(vwb200_dispi),
-                                 (size_t)W * sizeof(vwb200_dispi), H, cudaMemcpyDeviceToHost, st));
-    t_k1_stats.path = path;
+    VWB_CUDA(cudaStreamSynchronize(st));
+    if (cudaEventElapsedTime(&kernel_ms, kev.e0, kev.e1) != cudaSuccess) { kernel_ms = 0.0f; cudaGetLastError(); }
   }
-  VWB_CUDA(cudaStreamSynchronize(st));
+  t_k1_stats.path = path;
   t_k1_stats.launches = (int)(g_launches.load() - launches0);
-  t_k1_stats.kernel_ms = 0.0f;
-  cudaEventElapsedTime(&t_k1_stats.kernel_ms, kev.e0, kev.e1);
-  cudaEventDestroy(kev.e0); cudaEventDestroy(kev.e1);
+  t_k1_stats.kernel_ms = kernel_ms;
   return VWB200_OK;
 }
 

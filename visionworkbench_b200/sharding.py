@@ -5,9 +5,11 @@ output-row bands, one per rank, with no reduction.  When the INPUT rasters are r
 rank r must receive from rank r+1 the rows its last kernel windows (and search rows) reach into:
     left  raster: ky - 1          rows
     right raster: ky - 1 + sy - 1 rows
-`plan()` returns the arithmetic, `exchange_halos()` performs the send/recv with torch.distributed
-(NCCL on GPUs, gloo in the CPU tests).
+`plan()` returns the arithmetic (the C ABI's vwb200_shard_plan), `ShardComm` moves the halo rows on GPUs through the C
+ABI (vwb200_shard_exchange_halos: ncclSend / ncclRecv in one NCCL group over NVLink), and `exchange_halos()` is the same
+exchange over torch.distributed for host tensors (the gloo CPU tests of the band logic).
 """
+import ctypes as C
 from dataclasses import dataclass
 
 
@@ -27,26 +29,83 @@ class BandPlan:
     send_right: int
 
 
+class _CPlan(C.Structure):          # vwb200_band_plan (include/vwb200.h)
+    _fields_ = [(n, C.c_int32) for n in ("rank", "world", "y0", "y1", "left_rows", "right_rows", "own_left", "own_right",
+                                         "recv_left", "recv_right", "send_left", "send_right")]
+
+
+def _cplan(p):
+    return _CPlan(p.rank, p.world, p.y0, p.y1, p.left_rows, p.right_rows, p.own_left, p.own_right, p.recv_left, p.recv_right,
+                  p.send_left, p.send_right)
+
+
 def plan(rank, world, out_rows, ky, sy, left_total_rows=None, right_total_rows=None):
-    """Band plan for `out_rows` output rows.  The padded rasters have out_rows + ky - 1 (left) and
+    """Band plan for `out_rows` output rows (vwb200_shard_plan).  The padded rasters have out_rows + ky - 1 (left) and
     out_rows + ky - 1 + sy - 1 (right) rows unless given."""
-    if left_total_rows is None:
-        left_total_rows = out_rows + ky - 1
-    if right_total_rows is None:
-        right_total_rows = out_rows + ky - 1 + sy - 1
-    band = (out_rows + world - 1) // world
-    y0, y1 = min(out_rows, rank * band), min(out_rows, (rank + 1) * band)
-    h = y1 - y0
-    left_rows, right_rows = h + ky - 1, h + ky - 1 + sy - 1
-    last = rank == world - 1 or y1 >= out_rows
-    own_left = min(left_rows, (left_total_rows - y0) if last else h)
-    own_right = min(right_rows, (right_total_rows - y0) if last else h)
-    recv_left, recv_right = left_rows - own_left, right_rows - own_right
-    send_left = (ky - 1) if rank > 0 and h > 0 else 0
-    send_right = (ky - 1 + sy - 1) if rank > 0 and h > 0 else 0
-    if band < ky - 1 + sy - 1 and world > 1:
-        raise ValueError("band height smaller than the halo: a rank would need rows from beyond its neighbour")
-    return BandPlan(rank, world, y0, y1, left_rows, right_rows, own_left, own_right, recv_left, recv_right, send_left, send_right)
+    from .api import lib
+    c = _CPlan()
+    f = lib().vwb200_shard_plan
+    f.argtypes = [C.c_int] * 7 + [C.POINTER(_CPlan)]
+    rc = f(rank, world, out_rows, ky, sy, left_total_rows or 0, right_total_rows or 0, C.byref(c))
+    if rc:
+        raise ValueError(lib().vwb200_last_error().decode())
+    return BandPlan(*[getattr(c, n) for n, _ in _CPlan._fields_])
+
+
+class ShardComm:
+    """The NCCL communicator of the C ABI (vwb200_shard_create): rank 0 draws the unique id, `broadcast` hands the 128
+    bytes to every rank (here: torch.distributed), every rank joins on its current CUDA device."""
+
+    def __init__(self, rank, world, broadcast=None):
+        from .api import lib, _check
+        self._lib, self._check, self._h = lib(), _check, C.c_void_p()
+        self.rank, self.world = rank, world
+        ident = (C.c_ubyte * 128)()
+        if world > 1:
+            if rank == 0:
+                _check(self._lib.vwb200_shard_unique_id(ident))
+            data = bytes(ident)
+            data = broadcast(data) if broadcast else data
+            ident = (C.c_ubyte * 128).from_buffer_copy(data)
+        self._lib.vwb200_shard_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        _check(self._lib.vwb200_shard_create(ident, rank, world, C.byref(self._h)))
+        self._lib.vwb200_shard_exchange_halos.argtypes = [C.c_void_p, C.POINTER(_CPlan), C.c_void_p, C.c_int, C.c_ssize_t, C.c_void_p, C.c_int,
+                                                          C.c_ssize_t, C.c_void_p]
+        self._lib.vwb200_shard_destroy.argtypes = [C.c_void_p]
+        self._lib.vwb200_shard_destroy.restype = None
+
+    def exchange_halos(self, p, left_band, right_band, stream=None):
+        """left_band / right_band: float32 CUDA tensors with p.left_rows / p.right_rows rows whose first own_* rows are
+        valid; the halo rows arrive from rank + 1 (asynchronously, on the current torch stream)."""
+        import torch
+        assert left_band.dtype == torch.float32 and right_band.dtype == torch.float32 and left_band.is_cuda and right_band.is_cuda
+        assert left_band.stride(1) == 1 and right_band.stride(1) == 1
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        cp = _cplan(p)
+        self._check(self._lib.vwb200_shard_exchange_halos(self._h, C.byref(cp), left_band.data_ptr(), left_band.shape[1], left_band.stride(0),
+                                                          right_band.data_ptr(), right_band.shape[1], right_band.stride(0), C.c_void_p(st)))
+        return (p.recv_left * left_band.shape[1] + p.recv_right * right_band.shape[1]) * 4
+
+    def close(self):
+        if self._h:
+            self._lib.vwb200_shard_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def torch_broadcast(data):
+    """hand rank 0's bytes to every rank over the default torch.distributed group"""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(data), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, 0)
+    return bytes(t.cpu().tolist())
 
 
 def exchange_halos(p, left_band, right_band):
