@@ -513,12 +513,14 @@ def run_ours(a):
     if world != a.gpus and world > 1:
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version / INFO lines) is sent to stderr by
+    # pointing fd 1 at fd 2 for the run; the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL's INFO lines (communicator size, rings, NVLS) are collected in a per-rank file and replayed on stderr at the
-        # end; stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        nccl_log = os.path.join(tempfile.gettempdir(), f"vwb200_nccl_{os.getpid()}.log")
-        os.environ["NCCL_DEBUG_FILE"] = nccl_log
+        os.environ["NCCL_DEBUG"] = "INFO"              # communicator size, rings, NVLS: on stderr for the driver's rank check
+        os.environ.pop("NCCL_DEBUG_FILE", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert v.device_count() > 0
     cost = COSTS[a.cost]
@@ -670,16 +672,14 @@ def run_ours(a):
             line["configs"] = configs
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_measure(a, left, right)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     comm.close()
     if world > 1:
         dist.destroy_process_group()
-        try:
-            sys.stderr.write(open(nccl_log).read())
-            sys.stderr.flush()
-            os.unlink(nccl_log)
-        except Exception:
-            pass
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
 
 
 if __name__ == "__main__":

@@ -214,8 +214,12 @@ typedef struct {
 typedef struct vwb200_corr vwb200_corr;
 
 int  vwb200_corr_create(const vwb200_corr_params* p, vwb200_corr** out);
-/* Inputs are copied to (or, if on_device, referenced in) HBM once; they must outlive the handle
- * when on_device != 0.  Masks are uint8, nonzero = valid, same size as their image. */
+/* on_device == 0: host rasters, copied to HBM once.  on_device == 1: device rasters, referenced in place.
+ * on_device == VWB200_INPUTS_STREAMED: host rasters that STAY on the host -- every rasterize() uploads just its tile's
+ * region of interest (left box + kernel padding, right box + search window; CorrelationView.cc:89-97), so rasters larger
+ * than HBM work and nothing is resident between calls (the tile feeder; caller pattern Image/ImageIO.h:150-314).
+ * Referenced rasters must outlive the handle.  Masks are uint8, nonzero = valid, same size as their image. */
+#define VWB200_INPUTS_STREAMED 2
 int  vwb200_corr_set_inputs(vwb200_corr* h,
                             const float* left,  int lcols, int lrows, ptrdiff_t lpitch,
                             const float* right, int rcols, int rrows, ptrdiff_t rpitch,

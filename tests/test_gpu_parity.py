@@ -571,3 +571,22 @@ def test_host_rasters_are_fed_in_bands(vwb, oracle, cost, monkeypatch):
                                          right.shape[0], right.shape[1], 24, 17, 9, 7, out.ctypes.data, 300, 0, None)
     assert rc == 0
     _assert_disp_equal(out, ref, "pitched input")
+
+
+def test_view_streamed_inputs_tile_feeder(vwb, oracle):
+    """VWB200_INPUTS_STREAMED: the rasters stay on the host and every rasterize() uploads its tile's region of interest
+    (edge tiles clamp / zero-extend exactly like resident rasters)"""
+    search, kernel = (-12, -8, 12, 8), (7, 7)
+    left, right, lm, rm, _ = make_pair_for_tests(300, 260, search, seed=21)
+    args = (vwb.PREFILTER_NONE, 0.0, search, kernel, vwb.SQUARED_DIFFERENCE, 0, 0.0, 2.0, 0, 3, 3)
+    streamed = vwb.PyramidCorrelationView(left, right, lm, rm, *args, streamed=True)
+    p = oracle.make_params(search, kernel, cost=1, consistency_threshold=2.0, filter_half_kernel=3, max_pyramid_levels=3)
+    for bbox in [(0, 0, 128, 128), (172, 132, 300, 260), (100, 60, 220, 200), (0, 200, 90, 260), (0, 0, 300, 260)]:
+        got = streamed.rasterize(None, bbox)
+        ref = oracle.pyramid_correlate(p, left, right, lm, rm, bbox=bbox)
+        assert np.array_equal(got, ref), (bbox, int((got != ref).any(-1).sum()))
+
+
+def make_pair_for_tests(W, H, search, seed):
+    from visionworkbench_b200.synth import make_pair
+    return make_pair(W, H, search, seed=seed)

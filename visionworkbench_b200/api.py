@@ -435,7 +435,7 @@ class PyramidCorrelationView:
                  consistency_threshold, min_consistency_level, filter_half_kernel, max_pyramid_levels,
                  algorithm=VW_CORRELATION_BM, collar_size=0, sgm_subpixel_mode=SUBPIXEL_LC_BLEND, sgm_search_buffer=(2, 2),
                  memory_limit_mb=6000, blob_filter_area=0, lr_disp_diff=None, region_ul=(0, 0),
-                 write_debug_images=False, sgm_threads=4):
+                 write_debug_images=False, sgm_threads=4, streamed=False):
         """Argument order = the reference constructor (Stereo/CorrelationView.h:48-69); sgm_threads stands for
         vw_settings().default_num_threads(), which SGM's memory estimate reads (SGM.cc:715-716).
         lr_disp_diff: float32 (rows, cols, 2) PixelMask<float> array whose pixel (0, 0) is image pixel region_ul; updated in place."""
@@ -481,9 +481,11 @@ class PyramidCorrelationView:
             lm, rm = _np(left_mask, np.uint8), _np(right_mask, np.uint8)
             if lm.shape != l.shape or rm.shape != r.shape:
                 raise ArgumentErr("masks must have the size of their images")
+            if streamed:          # the rasters stay on the host; each rasterize() uploads its tile's region of interest
+                self._keep = (l, r, lm, rm)
             _check(lib().vwb200_corr_set_inputs(self._h, l.ctypes.data, l.shape[1], l.shape[0], l.shape[1],
                                                 r.ctypes.data, r.shape[1], r.shape[0], r.shape[1],
-                                                lm.ctypes.data, lm.shape[1], rm.ctypes.data, rm.shape[1], 0))
+                                                lm.ctypes.data, lm.shape[1], rm.ctypes.data, rm.shape[1], 2 if streamed else 0))
 
     def __del__(self):
         try:

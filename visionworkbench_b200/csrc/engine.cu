@@ -378,11 +378,12 @@ struct vwb200_corr {
   int lcols = 0, lrows = 0, rcols = 0, rrows = 0;
   ptrdiff_t lpitch = 0, rpitch = 0, lmpitch = 0, rmpitch = 0;
   bool owned = false;
+  bool streamed = false;       // L / R / Lm / Rm are HOST pointers; every rasterize call uploads its own region of interest
   int device = 0;
   ~vwb200_corr() { release(); }
   void release() {
     if (owned) { cudaFree((void*)L); cudaFree((void*)R); cudaFree((void*)Lm); cudaFree((void*)Rm); }
-    L = R = nullptr; Lm = Rm = nullptr; owned = false;
+    L = R = nullptr; Lm = Rm = nullptr; owned = false; streamed = false;
   }
   int num_levels(int bw, int bh) const {
     // CorrelationView.cc:301-310: log(int) is double, log(2.0f) is float
@@ -427,17 +428,42 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, float** d_sub
   b0.lw = lg.x1 - lg.x0; b0.lh = lg.y1 - lg.y0; b0.rw = rg.x1 - rg.x0; b0.rh = rg.y1 - rg.y0;
   VWB_TRY(ar.alloc(&b0.l, (size_t)b0.lw * b0.lh));
   VWB_TRY(ar.alloc(&b0.r, (size_t)b0.rw * b0.rh));
-  const ImgF Lin{L, lcols, lrows, lpitch}, Rin{R, rcols, rrows, rpitch};
-  const ImgB Lmin{Lm, lcols, lrows, lmpitch}, Rmin{Rm, rcols, rrows, rmpitch};
-  VWB_TRY(crop_extend_f32_launch(Lin, lg.x0, lg.y0, b0.lw, b0.lh, b0.l, b0.lw, st));
-  VWB_TRY(crop_extend_f32_launch(Rin, rg.x0, rg.y0, b0.rw, b0.rh, b0.r, b0.rw, st));
+  ImgF Lin{L, lcols, lrows, lpitch}, Rin{R, rcols, rrows, rpitch};
+  ImgB Lmin{Lm, lcols, lrows, lmpitch}, Rmin{Rm, rcols, rrows, rmpitch};
+  int lox = 0, loy = 0, rox_ = 0, roy_ = 0;          // origin of the device-resident part of the rasters
+  if (streamed) {
+    // the tile feeder (Image/ImageIO.h:150-314 is the caller pattern): the rasters stay on the host and only
+    // this tile's region of interest -- the padded left box and the right box grown by the search window, clipped to the
+    // image -- goes up.  Clamping to the ROI equals clamping to the image: the ROI reaches the image edge wherever the
+    // needed region crosses it, and coordinates inside the image but outside the ROI are never requested.
+    auto clip = [](Box b, int w, int h) {
+      Box r{std::min(std::max(b.x0, 0), w - 1), std::min(std::max(b.y0, 0), h - 1), std::max(std::min(b.x1, w), 1), std::max(std::min(b.y1, h), 1)};
+      if (r.x1 <= r.x0) r.x1 = r.x0 + 1;
+      if (r.y1 <= r.y0) r.y1 = r.y0 + 1;
+      return r;
+    };
+    const Box lr_ = clip(lg, lcols, lrows), rr_ = clip(rg, rcols, rrows);
+    const int lw_ = lr_.x1 - lr_.x0, lh_ = lr_.y1 - lr_.y0, rw_ = rr_.x1 - rr_.x0, rh_ = rr_.y1 - rr_.y0;
+    float *dl_, *dr_; uint8_t *dlm_, *drm_;
+    VWB_TRY(ar.alloc(&dl_, (size_t)lw_ * lh_)); VWB_TRY(ar.alloc(&dr_, (size_t)rw_ * rh_));
+    VWB_TRY(ar.alloc(&dlm_, (size_t)lw_ * lh_)); VWB_TRY(ar.alloc(&drm_, (size_t)rw_ * rh_));
+    VWB_CUDA(cudaMemcpy2DAsync(dl_, (size_t)lw_ * 4, L + (ptrdiff_t)lr_.y0 * lpitch + lr_.x0, (size_t)lpitch * 4, (size_t)lw_ * 4, lh_, cudaMemcpyHostToDevice, st));
+    VWB_CUDA(cudaMemcpy2DAsync(dr_, (size_t)rw_ * 4, R + (ptrdiff_t)rr_.y0 * rpitch + rr_.x0, (size_t)rpitch * 4, (size_t)rw_ * 4, rh_, cudaMemcpyHostToDevice, st));
+    VWB_CUDA(cudaMemcpy2DAsync(dlm_, (size_t)lw_, Lm + (ptrdiff_t)lr_.y0 * lmpitch + lr_.x0, (size_t)lmpitch, (size_t)lw_, lh_, cudaMemcpyHostToDevice, st));
+    VWB_CUDA(cudaMemcpy2DAsync(drm_, (size_t)rw_, Rm + (ptrdiff_t)rr_.y0 * rmpitch + rr_.x0, (size_t)rmpitch, (size_t)rw_, rh_, cudaMemcpyHostToDevice, st));
+    Lin = ImgF{dl_, lw_, lh_, lw_}; Rin = ImgF{dr_, rw_, rh_, rw_};
+    Lmin = ImgB{dlm_, lw_, lh_, lw_}; Rmin = ImgB{drm_, rw_, rh_, rw_};
+    lox = lr_.x0; loy = lr_.y0; rox_ = rr_.x0; roy_ = rr_.y0;
+  }
+  VWB_TRY(crop_extend_f32_launch(Lin, lg.x0 - lox, lg.y0 - loy, b0.lw, b0.lh, b0.l, b0.lw, st));
+  VWB_TRY(crop_extend_f32_launch(Rin, rg.x0 - rox_, rg.y0 - roy_, b0.rw, b0.rh, b0.r, b0.rw, st));
   {  // mean fill of masked pixels (:116-149); masks here are constant-edge-extended over the padded ROI
     uint8_t *lmb, *rmb; double* acc;
     VWB_TRY(ar.alloc(&lmb, (size_t)b0.lw * b0.lh));
     VWB_TRY(ar.alloc(&rmb, (size_t)b0.rw * b0.rh));
     VWB_TRY(ar.alloc(&acc, 2 * (2 + 2 * 256)));
-    VWB_TRY(crop_extend_u8_launch(Lmin, lg.x0, lg.y0, b0.lw, b0.lh, 0, lmb, b0.lw, st));
-    VWB_TRY(crop_extend_u8_launch(Rmin, rg.x0, rg.y0, b0.rw, b0.rh, 0, rmb, b0.rw, st));
+    VWB_TRY(crop_extend_u8_launch(Lmin, lg.x0 - lox, lg.y0 - loy, b0.lw, b0.lh, 0, lmb, b0.lw, st));
+    VWB_TRY(crop_extend_u8_launch(Rmin, rg.x0 - rox_, rg.y0 - roy_, b0.rw, b0.rh, 0, rmb, b0.rw, st));
     double* acc_r = acc + (2 + 2 * 256);
     VWB_TRY(masked_mean_launch(ImgF{b0.l, b0.lw, b0.lh, b0.lw}, ImgB{lmb, b0.lw, b0.lh, b0.lw}, acc, st));
     VWB_TRY(masked_mean_launch(ImgF{b0.r, b0.rw, b0.rh, b0.rw}, ImgB{rmb, b0.rw, b0.rh, b0.rw}, acc_r, st));
@@ -466,8 +492,8 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, float** d_sub
   b0.lmw = bw; b0.lmh = bh; b0.rmw = bw + ssx; b0.rmh = bh + ssy;
   VWB_TRY(ar.alloc(&b0.lm, (size_t)b0.lmw * b0.lmh));
   VWB_TRY(ar.alloc(&b0.rm, (size_t)b0.rmw * b0.rmh));
-  VWB_TRY(crop_extend_u8_launch(Lmin, bbox.x0, bbox.y0, b0.lmw, b0.lmh, 1, b0.lm, b0.lmw, st));
-  VWB_TRY(crop_extend_u8_launch(Rmin, bbox.x0 + p.search_x0, bbox.y0 + p.search_y0, b0.rmw, b0.rmh, 1, b0.rm, b0.rmw, st));
+  VWB_TRY(crop_extend_u8_launch(Lmin, bbox.x0 - lox, bbox.y0 - loy, b0.lmw, b0.lmh, 1, b0.lm, b0.lmw, st));
+  VWB_TRY(crop_extend_u8_launch(Rmin, bbox.x0 + p.search_x0 - rox_, bbox.y0 + p.search_y0 - roy_, b0.rmw, b0.rmh, 1, b0.rm, b0.rmw, st));
   for (int i = 1; i <= levels; ++i) {   // :209-216
     const LevelImgs& a = py[i - 1];
     LevelImgs& b = py[i];
@@ -1276,6 +1302,12 @@ int vwb200_corr_set_inputs(vwb200_corr* h, const float* left, int lcols, int lro
   h->release();
   VWB_CUDA(cudaGetDevice(&h->device));
   h->lcols = lcols; h->lrows = lrows; h->rcols = rcols; h->rrows = rrows;
+  if (on_device == VWB200_INPUTS_STREAMED) {          // host rasters, fed tile by tile
+    h->L = left; h->R = right; h->Lm = lmask; h->Rm = rmask;
+    h->lpitch = lpitch; h->rpitch = rpitch; h->lmpitch = lmpitch; h->rmpitch = rmpitch;
+    h->streamed = true;
+    return VWB200_OK;
+  }
   if (on_device) {
     h->L = left; h->R = right; h->Lm = lmask; h->Rm = rmask;
     h->lpitch = lpitch; h->rpitch = rpitch; h->lmpitch = lmpitch; h->rmpitch = rmpitch;
@@ -1314,7 +1346,7 @@ static int corr_rasterize_impl(vwb200_corr* h, int x0, int y0, int x1, int y1, f
   cudaGetDevice(&prev_dev);
   struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev != h->device ? prev_dev : -1};
   VWB_CUDA(cudaSetDevice(h->device));
-  StreamGuard sg; VWB_TRY(sg.init(stream, (h->owned ? dest_on_device : 1)));
+  StreamGuard sg; VWB_TRY(sg.init(stream, ((h->owned || h->streamed) ? dest_on_device : 1)));
   cudaStream_t st = sg.st;
   {
     Arena ar(st);
