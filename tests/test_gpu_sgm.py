@@ -239,3 +239,35 @@ def test_view_prerasterize_ignores_collar(vwb, oracle):
     bbox = (40, 30, 140, 120)
     assert np.array_equal(view.prerasterize(bbox), oracle.pyramid_correlate(p0, left, right, lm, rm, bbox=bbox))
     assert np.array_equal(view.rasterize(None, bbox), oracle.pyramid_correlate(p16, left, right, lm, rm, bbox=bbox))
+
+
+@pytest.mark.parametrize("maxw,maxh", [(6, 8), (8, 8), (5, 5), (1, 1), (8, 3)])
+def test_sgm_small_boxes_rows_in_lanes(vwb, oracle, maxw, maxh):
+    """the four-lines-per-warp kernel (no box wider or higher than 8): every pixel its own box size and position, empty
+    pixels, single-disparity pixels, boxes jumping by many disparities between neighbours -- and the same boxes through the
+    lane-per-disparity kernel (VWB200_SGM_LANES_PER_ENTRY) give the oracle's result too"""
+    import os
+    rng = np.random.default_rng(maxw * 10 + maxh)
+    search, kernel = (23, 17), 5
+    for W, H in [(150, 97), (61, 140)]:
+        left, right = _pair(W + maxw, W, H, search, (4, 2))
+        oh, ow = oracle.sgm_output_shape(left, right, search, kernel)
+        b = np.zeros((oh, ow, 4), np.int32)
+        b[..., 0] = rng.integers(0, search[0] + 1, (oh, ow)); b[..., 1] = rng.integers(0, search[1] + 1, (oh, ow))
+        # smooth-ish regions (boxes shared by 2 x 2 blocks, like a half-resolution prior) mixed with noisy ones
+        b[: oh // 2, :, 0] = np.repeat(np.repeat(b[: oh // 2: 2, ::2, 0], 2, 0), 2, 1)[: oh // 2, :ow]
+        b[: oh // 2, :, 1] = np.repeat(np.repeat(b[: oh // 2: 2, ::2, 1], 2, 0), 2, 1)[: oh // 2, :ow]
+        b[..., 2] = np.minimum(b[..., 0] + rng.integers(0, maxw, (oh, ow)), search[0])
+        b[..., 3] = np.minimum(b[..., 1] + rng.integers(0, maxh, (oh, ow)), search[1])
+        b[rng.random((oh, ow)) < 0.04] = (0, 0, -1, -1)
+        b[10:14, 20:40] = (0, 0, -1, -1)
+        ri, rf = oracle.sgm_calc_disparity_bounds(left, right, search, kernel, b, subpixel_mode=5)
+        for env in (None, "1"):
+            if env:
+                os.environ["VWB200_SGM_LANES_PER_ENTRY"] = env
+            try:
+                gi, gf = vwb.calc_disparity_sgm_ex(vwb.CENSUS_TRANSFORM, left, right, search, kernel, subpixel_mode=5, bounds=b)
+            finally:
+                os.environ.pop("VWB200_SGM_LANES_PER_ENTRY", None)
+            assert np.array_equal(gi, ri), f"{W}x{H} lanes-per-entry={env}: {int((gi != ri).any(-1).sum())} pixels differ"
+            assert np.abs(gf - rf).max() <= 1e-5

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) sgm_meta_kernel(const short4* __restrict_
   unsigned woff = 0;
   for (int i = 0; i < wid; ++i) woff += wsum[i];
   unsigned long long run = block_offs[blockIdx.x] + woff + (incl - s);
-  unsigned mx = 0;
+  unsigned mx = 0, mw = 0, mh = 0;
   for (int i = 0; i < 4; ++i) {
     if (base + i < npix) {
       const size_t pix = base + i;
@@ -280,11 +280,16 @@ __global__ void __launch_bounds__(256) sgm_meta_kernel(const short4* __restrict_
       m.val_n = (unsigned)left8[(size_t)(r + g.min_row) * g.lw + (c + g.min_col)] | (n[i] << 8);
       meta[pix] = m;
       mx = max(mx, n[i]);
+      if (n[i]) { mw = max(mw, (unsigned)(v[i].z - v[i].x + 1)); mh = max(mh, (unsigned)(v[i].w - v[i].y + 1)); }
     }
     run += n[i];
   }
-  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0 && mx) atomicMax(max_n, mx);
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mw = max(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+    mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, o));
+  }
+  if (lane == 0 && mx) { atomicMax(max_n, mx); atomicMax(max_n + 1, mw); atomicMax(max_n + 2, mh); }
 }
 
 // ---- Hamming costs (get_hamming_distance_costs, SGM.cc:39-73) ---------------------------------------------------------
@@ -385,7 +390,11 @@ __device__ __forceinline__ bool sgm_parabola_peak(const double* z, double* dx, d
   return true;
 }
 
-__global__ void __launch_bounds__(128) sgm_wta_kernel(sgm_accum_t* __restrict__ accum, sgm_accum_t* __restrict__ scratch,
+// accum = the first partial volume (it receives the totals of the pixels that need them re-read: ties, sub-pixel), a1..a3 =
+// the other partial volumes of the concurrent directions (NULL: accum already holds the total)
+__global__ void __launch_bounds__(128) sgm_wta_kernel(sgm_accum_t* __restrict__ accum, const sgm_accum_t* __restrict__ a1,
+                                                      const sgm_accum_t* __restrict__ a2, const sgm_accum_t* __restrict__ a3,
+                                                      sgm_accum_t* __restrict__ scratch,
                                                       const SgmMeta* __restrict__ meta, SgmGeom g, vwb200_dispi* __restrict__ out,
                                                       ptrdiff_t opitch, int want_sub, int mode, float* __restrict__ out_sub, ptrdiff_t sub_pitch) {
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -407,12 +416,20 @@ __global__ void __launch_bounds__(128) sgm_wta_kernel(sgm_accum_t* __restrict__ 
   const int width = b2 - b0 + 1, height = b3 - b1 + 1;
   int min_count = 0, min_index = 0;
   unsigned min_val = 65535;
+  const bool parts = a1 != nullptr;
+  const bool need_total = parts && want_sub && mode != 0;              // the sub-pixel stage re-reads neighbours of the winner
   for (int i = 0; i < num; ++i) {
-    const unsigned v = accum_vec[i];
+    unsigned v = accum_vec[i];
+    if (parts) {                                                        // uint16 wrapping sum, like the reference's in-place adds
+      v = (v + a1[mq.z + i] + a2[mq.z + i] + a3[mq.z + i]) & 0xffffu;
+      if (need_total) accum_vec[i] = (sgm_accum_t)v;
+    }
     if (v == min_val) ++min_count;
     if (v < min_val) { min_index = i; min_val = v; min_count = 1; }
   }
   if (min_count > 1) {                                                  // tie smoothing (:1196-1288), rare
+    if (parts && !need_total)
+      for (int i = 0; i < num; ++i) accum_vec[i] = (sgm_accum_t)((accum_vec[i] + a1[mq.z + i] + a2[mq.z + i] + a3[mq.z + i]) & 0xffffu);
     for (int i = 0; i < num; ++i) buffer[i] = accum_vec[i];
     sgm_accum_t* input_array = accum_vec;
     sgm_accum_t* output_array = buffer;
@@ -676,16 +693,29 @@ int sgm_run(const SgmArgs& a, Arena& /*callers_arena*/, cudaStream_t st) {
   }
   if (total == 0) return all_invalid();
   SgmMeta* meta; unsigned* d_maxn; sgm_cost_t* cost; sgm_accum_t *accum, *scratch;
+  sgm_accum_t* parts[4] = {nullptr, nullptr, nullptr, nullptr};
   VWB_TRY(ar.alloc(&meta, npix));
-  VWB_TRY(ar.alloc(&d_maxn, 1));
-  VWB_CUDA(cudaMemsetAsync(d_maxn, 0, sizeof(unsigned), st));
+  VWB_TRY(ar.alloc(&d_maxn, 4));          // max entries, max box width, max box height
+  VWB_CUDA(cudaMemsetAsync(d_maxn, 0, 4 * sizeof(unsigned), st));
   sgm_meta_kernel<<<ss.nblocks, 256, 0, st>>>(bs.b, npix, ss.block_sums, l8, g, meta, d_maxn);
   VWB_LAUNCH_CHECK();
-  unsigned max_n = 0;
-  VWB_CUDA(cudaMemcpyAsync(&max_n, d_maxn, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  VWB_TRY(ar.alloc(&cost, (size_t)total + 64));
-  VWB_TRY(ar.alloc(&accum, (size_t)total + 64));
+  unsigned maxes[4] = {0, 0, 0, 0};
+  VWB_CUDA(cudaMemcpyAsync(maxes, d_maxn, sizeof(maxes), cudaMemcpyDeviceToHost, st));
+  // 64 entries of padding in front of and behind the ragged volumes (the rows-in-lanes kernel fetches rows with aligned
+  // word loads that may start one entry early and end a few entries late)
+  VWB_TRY(ar.alloc(&cost, (size_t)total + 192));
+  VWB_TRY(ar.alloc(&accum, (size_t)total + 192));
   VWB_TRY(ar.alloc(&scratch, (size_t)total + 64));
+  VWB_CUDA(cudaMemsetAsync(cost, 0, 64, st));
+  VWB_CUDA(cudaMemsetAsync(accum, 0, 64 * sizeof(sgm_accum_t), st));
+  cost += 64; accum += 64;
+  parts[0] = accum;
+  const int naccum = (a.use_mgm || getenv("VWB200_SGM_SERIAL")) ? 1 : 4;       // partial volumes of the concurrent directions
+  for (int k = 1; k < naccum; ++k) {
+    VWB_TRY(ar.alloc(&parts[k], (size_t)total + 192));
+    VWB_CUDA(cudaMemsetAsync(parts[k], 0, 64 * sizeof(sgm_accum_t), st));
+    parts[k] += 64;
+  }
   sgm_cost_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(lc, rc, meta, g, cost);
   VWB_LAUNCH_CHECK();
   VWB_CUDA(cudaStreamSynchronize(st));                                  // max_n
@@ -693,10 +723,10 @@ int sgm_run(const SgmArgs& a, Arena& /*callers_arena*/, cudaStream_t st) {
     VWB_CUDA(cudaMemsetAsync(accum, 0, ((size_t)total + 64) * sizeof(sgm_accum_t), st));
     VWB_TRY(mgm_paths_launch(meta, cost, accum, l8, g, (size_t)total, ar, st));
   } else {
-    VWB_TRY(sgm_paths_launch(meta, cost, accum, g, max_n, ar, st));
+    VWB_TRY(sgm_paths_launch(meta, cost, parts, naccum, g, maxes[0], maxes[1], maxes[2], ar, st));
   }
-  sgm_wta_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, scratch, meta, g, a.out, a.opitch, a.out_sub != nullptr, a.subpixel_mode,
-                                                                 a.out_sub, a.sub_pitch);
+  sgm_wta_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, parts[1], parts[2], parts[3], scratch, meta, g, a.out, a.opitch,
+                                                                 a.out_sub != nullptr, a.subpixel_mode, a.out_sub, a.sub_pitch);
   VWB_LAUNCH_CHECK();
   return VWB200_OK;
 }

@@ -149,7 +149,6 @@ __global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sgm_lines_kernel(const
   const uint4 MZ = make_uint4(0xffff0000u, 0xffffu, 0u, 0u);         // box (0,0,-1,-1), n = 0
 
   // pixel of step t on this line: horizontal (line, t) or the wrapped column (line + sc * t) mod ow of row t
-  const int edge_c = sc > 0 ? 0 : ow - 1;
   int lc;                                                             // this lane's column cursor for the meta fetches
   if (horiz) lc = sc > 0 ? lane : ow - 1 - lane;
   else { lc = (line + sc * lane) % ow; if (lc < 0) lc += ow; }
@@ -274,27 +273,269 @@ __global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sgm_lines_kernel(const
   }
 }
 
-int sgm_paths_launch(const SgmMeta* meta, const sgm_cost_t* cost, sgm_accum_t* accum, const SgmGeom& g, unsigned max_n, Arena& ar,
-                     cudaStream_t st) {
-  // the eight directions of accum_sgm_multithread (:2462-2611), one launch each (a pixel lies on one line per direction)
-  static const int DIRS[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
-  sgm_accum_t* scratch = nullptr;
-  unsigned per_warp = 0;
-  if (max_n > 32) {
-    per_warp = 2 * ((max_n + 31u) & ~31u);
-    VWB_TRY(ar.alloc(&scratch, (size_t)per_warp * std::max(g.ow, g.oh)));
+// ---- rows-in-lanes variant: FOUR lines per warp ------------------------------------------------------------------------------
+// When no search box of the image is wider or higher than 8 (the regime of config 4 and of every pyramid level below the
+// top: boxes of (2 * buffer + 1)^2 around the doubled previous disparity), a lane owns one ROW of its line's box: eight lanes
+// = the rows of one line, four lines per warp, and the up-to-8 path costs of a row sit in NR registers as packed u16 pairs.
+// Path costs are kept in COMPLEMENT form c = 0x7fff - v, so that "outside the previous box" is simply 0 (shifts and
+// out-of-range shuffles fill with zeros) and every minimum becomes a packed maximum:
+//   vertical 3-max   : the previous pixel's rows Y-1, Y, Y+1 arrive by three shuffles per register (rows = lanes)
+//   horizontal 3-max : 16-bit funnel shifts inside the row + VIMNMX3.U16x2
+//   realignment      : the row is shifted by (box.min_x - previous box.min_x) elements when a box moved (64-bit shifts)
+//   min over the previous pixel = max of the complements: in-lane, then 3 xor-shuffles inside the 8-lane group
+//   recurrence       : __viaddmin_u16x2 / __vimin3_u16x2 on two disparities at a time (no 16-bit overflow: P2 <= 30000)
+// 0x7fff instead of BAD for a neighbour outside the box gives the same result as long as the centre is clamped to BAD
+// (min(.., centre, dJ) <= BAD < BAD + P1).  Per line-step this issues ~40 instructions instead of ~110.
+__device__ __forceinline__ void shift_row(unsigned (&r)[4], int s) {      // r[x] <- r[x + s] (halfword elements), zeros shifted in
+  unsigned long long lo = ((unsigned long long)r[1] << 32) | r[0], hi = ((unsigned long long)r[3] << 32) | r[2];
+  unsigned long long nlo, nhi;
+  if (s >= 0) {
+    const int k = 16 * s;
+    if (k == 0) { nlo = lo; nhi = hi; }
+    else if (k < 64) { nlo = (lo >> k) | (hi << (64 - k)); nhi = hi >> k; }
+    else if (k < 128) { nlo = hi >> (k - 64); nhi = 0; }
+    else { nlo = 0; nhi = 0; }
+  } else {
+    const int k = -16 * s;
+    if (k < 64) { nhi = (hi << k) | (lo >> (64 - k)); nlo = lo << k; }
+    else if (k < 128) { nhi = lo << (k - 64); nlo = 0; }
+    else { nlo = 0; nhi = 0; }
   }
-  for (int i = 0; i < 8; ++i) {
-    const int sc = DIRS[i][0], sr = DIRS[i][1];
-    const int lines = sr == 0 ? g.oh : g.ow;
+  r[0] = (unsigned)nlo; r[1] = (unsigned)(nlo >> 32); r[2] = (unsigned)nhi; r[3] = (unsigned)(nhi >> 32);
+}
+
+// Register layout of a row: element 0 is a margin (the column left of the box, always empty), elements 1..w are the box
+// columns, so the 3-wide horizontal maximum of the previous row also exists for the column just left and just right of
+// the previous box (w <= 6).  The ragged buffers carry 64 entries of padding in front for the margin's loads.
+template <int MODE, bool FIRST>
+__global__ void __launch_bounds__(64) sgm_rows_kernel(const SgmMeta* __restrict__ meta, const sgm_cost_t* __restrict__ cost,
+                                                      sgm_accum_t* __restrict__ accum, SgmGeom g, int sc, int sr) {
+  constexpr int WPC = 2, DR = 8, P = DR - 1;
+  constexpr unsigned K = 0x7fff7fffu;
+  __shared__ unsigned short s_p2mod[256];
+  __shared__ uint4 s_meta[WPC][4][64];
+  __shared__ uint4 s_data[WPC][DR][32][2];
+  for (unsigned d = threadIdx.x; d < 256; d += blockDim.x) {
+    const unsigned p2u = (unsigned)g.p2 & 0xffffu;
+    unsigned v = d ? p2u / d : p2u;
+    if (v < (unsigned)g.p1) v = (unsigned)g.p1;
+    s_p2mod[d] = (unsigned short)v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gl = lane >> 3, ry = lane & 7;
+  constexpr bool horiz = MODE == 0, wraps = MODE == 2;
+  const int ow = g.ow, oh = g.oh;
+  const int NL = horiz ? oh : ow, NS = horiz ? ow : oh;
+  const int line0 = (blockIdx.x * WPC + wid) * 4;
+  if (line0 >= NL) return;
+  const int line = line0 + gl;
+  const unsigned BAD = (unsigned)((255 + g.p2) & 0xffff), BB = BAD * 0x10001u, P1P1 = (unsigned)g.p1 * 0x10001u;
+  const uint4 MZ = make_uint4(0xffff0000u, 0xffffu, 0u, 0u);
+  const unsigned* cost32 = reinterpret_cast<const unsigned*>(cost);
+  const unsigned* accum32 = reinterpret_cast<const unsigned*>(accum);
+  // meta fetch: lane i brings the record of step 32 * epoch + i of each of the warp's four lines
+  int lc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (horiz) lc[q] = sc > 0 ? lane : ow - 1 - lane;
+    else { lc[q] = (line0 + q + sc * lane) % ow; if (lc[q] < 0) lc[q] += ow; }
+  }
+  auto fetch_meta = [&](int epoch) {
+    const int t = 32 * epoch + lane;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 m = MZ;
+      if (t < NS && line0 + q < NL) {
+        const int r = horiz ? line0 + q : (sr > 0 ? t : oh - 1 - t);
+        m = __ldg(reinterpret_cast<const uint4*>(meta) + ((size_t)r * ow + lc[q]));
+      }
+      s_meta[wid][q][(t & 63)] = m;
+      lc[q] += 32 * sc;
+      if (!horiz) { while (lc[q] >= ow) lc[q] -= ow; while (lc[q] < 0) lc[q] += ow; }
+    }
+  };
+  fetch_meta(0);
+  fetch_meta(1);
+  __syncwarp();
+  // this lane's row of the pixel of step t, RAW: the three aligned words that hold its cost bytes and the four that hold its
+  // accumulated costs (element e = column e - 1).  Nothing here depends on the loaded values -- they rest in registers for
+  // two steps, then in the ring, and are only shifted into place (funnel shifts by the row's misalignment) when the step
+  // is computed; whatever lies outside the row is masked there.
+  auto load_data = [&](int t, uint4& cq, uint4& aq) {
+    const uint4 q = s_meta[wid][gl][t & 63];
+    const int b0 = (short)(q.x & 0xffff), b1 = (short)(q.x >> 16), b2 = (short)(q.y & 0xffff), b3 = (short)(q.y >> 16);
+    const int w = (q.w >> 8) ? b2 - b0 + 1 : 0, h = b3 - b1 + 1;
+    cq = make_uint4(0u, 0u, 0u, 0u); aq = cq;
+    if (ry < h && w > 0) {
+      const long long A = (long long)q.z + (long long)(ry * w) - 1;   // entry of element 0 (the margin; -1 for the very first row:
+      const unsigned* cw = cost32 + (A >> 2);                         // the front padding makes it valid)
+      cq.x = __ldg(cw); cq.y = __ldg(cw + 1); cq.z = __ldg(cw + 2);
+      if (!FIRST) {
+        const unsigned* aw = accum32 + (A >> 1);
+        aq.x = aw[0]; aq.y = aw[1]; aq.z = aw[2]; aq.w = aw[3];
+      }
+    }
+  };
+  uint4 d1c, d1a, d0c, d0a;
+  for (int t = 0; t < P - 2; ++t) {
+    uint4 c, a;
+    load_data(t, c, a);
+    s_data[wid][t & (DR - 1)][lane][0] = c;
+    s_data[wid][t & (DR - 1)][lane][1] = a;
+  }
+  load_data(P - 2, d1c, d1a);
+  load_data(P - 1, d0c, d0a);
+
+  unsigned pc[4] = {0u, 0u, 0u, 0u};     // previous pixel's path costs of this lane's row, complement form, 0 = no entry
+  int pb0 = 0, pb1 = 0, ph = 0, last_val = 0;
+  int to_edge = wraps ? (sc > 0 ? ow - line : line + 1) : 0x7fffffff;
+
+#pragma unroll 1
+  for (int t = 0; t < NS; ++t) {
+    if ((t & 31) == 0 && t) { fetch_meta((t >> 5) + 1); __syncwarp(); }
+    // data ring: the loads issued two steps ago go in, the loads for step t + P go out
+    s_data[wid][(t + P - 2) & (DR - 1)][lane][0] = d1c;
+    s_data[wid][(t + P - 2) & (DR - 1)][lane][1] = d1a;
+    d1c = d0c; d1a = d0a;
+    load_data(t + P, d0c, d0a);
+    const uint4 mq = s_meta[wid][gl][t & 63];
+    const uint4 dcq = s_data[wid][t & (DR - 1)][lane][0], daq = s_data[wid][t & (DR - 1)][lane][1];
+    const int b0 = (short)(mq.x & 0xffff), b1 = (short)(mq.x >> 16), b2 = (short)(mq.y & 0xffff), b3 = (short)(mq.y >> 16);
+    const int n = (int)(mq.w >> 8), val = (int)(mq.w & 255u);
+    const int w = n ? b2 - b0 + 1 : 0, h = n ? b3 - b1 + 1 : 0;
+    unsigned cst[4], acc[4];
+    {   // shift the raw words into place: element e <- entry A + e
+      const long long A = (long long)mq.z + (long long)(ry * w) - 1;
+      const unsigned sh = (unsigned)(A & 3) * 8u, s2 = (unsigned)(A & 1) * 16u;
+      const unsigned B0 = __funnelshift_r(dcq.x, dcq.y, sh), B1 = __funnelshift_r(dcq.y, dcq.z, sh);
+      cst[0] = __byte_perm(B0, 0u, 0x4140); cst[1] = __byte_perm(B0, 0u, 0x4342); cst[2] = __byte_perm(B1, 0u, 0x4140); cst[3] = __byte_perm(B1, 0u, 0x4342);
+      acc[0] = __funnelshift_r(daq.x, daq.y, s2); acc[1] = __funnelshift_r(daq.y, daq.z, s2);
+      acc[2] = __funnelshift_r(daq.z, daq.w, s2); acc[3] = __funnelshift_r(daq.w, 0u, s2);
+    }
+    if (wraps && to_edge == 0) { pc[0] = pc[1] = pc[2] = pc[3] = 0u; ph = 0; to_edge = ow; }      // the line restarts at the image edge
+    const unsigned p2_mod = s_p2mod[abs(val - last_val)];
+    // min over the previous pixel (all rows of the group)
+    unsigned mx = __vimax3_u16x2(pc[0], pc[1], pc[2]);
+    mx = __vimax3_u16x2(mx, pc[3], pc[3]);
+    mx = max(mx & 0xffffu, mx >> 16);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    const unsigned mp = min(0x7fffu - mx, BAD);
+    const unsigned dJ = mp + p2_mod;
+    // rows Y - 1, Y, Y + 1 of the previous pixel (Y = this lane's row of the current box)
+    const int sy = b1 - pb1, sx = b0 - pb0;
+    unsigned v3[4], cr[4];
+    {
+      const int r0 = ry + sy - 1, r1 = ry + sy, r2 = ry + sy + 1;
+      const int base = lane & 24;
+      const bool k0 = (unsigned)r0 < (unsigned)ph, k1 = (unsigned)r1 < (unsigned)ph, k2 = (unsigned)r2 < (unsigned)ph;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        unsigned u0 = __shfl_sync(0xffffffffu, pc[j], base | (r0 & 7));
+        unsigned u1 = __shfl_sync(0xffffffffu, pc[j], base | (r1 & 7));
+        unsigned u2 = __shfl_sync(0xffffffffu, pc[j], base | (r2 & 7));
+        if (!k0) u0 = 0u;
+        if (!k1) u1 = 0u;
+        if (!k2) u2 = 0u;
+        v3[j] = __vimax3_u16x2(u0, u1, u2);
+        cr[j] = u1;
+      }
+    }
+    // horizontal 3-max inside the row (previous box's columns, with the margins)
+    unsigned h9[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned below = j > 0 ? v3[j - 1] : 0u, above = j < 3 ? v3[j + 1] : 0u;
+      const unsigned vl = __funnelshift_l(below, v3[j], 16), vr = __funnelshift_r(v3[j], above, 16);
+      h9[j] = __vimax3_u16x2(vl, v3[j], vr);
+    }
+    if (__any_sync(0xffffffffu, sx != 0)) {      // a box moved sideways: bring the row into the current box's columns
+      shift_row(h9, sx);
+      shift_row(cr, sx);
+    }
+    // recurrence on pairs of disparities
+    const unsigned dJdJ = dJ * 0x10001u, mpmp = mp * 0x10001u;
+    const bool rowok = ry < h;
+    sgm_accum_t* arow = accum + (size_t)mq.z + (size_t)(ry * w) - 1;          // entry of element 0
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool e0 = rowok && 2 * j >= 1 && 2 * j <= w, e1 = rowok && 2 * j + 1 <= w;
+      const unsigned em = (e0 ? 0xffffu : 0u) | (e1 ? 0xffff0000u : 0u);
+      const unsigned nb = K - h9[j];
+      const unsigned centre = __vimin3_u16x2(K - cr[j], BB, BB);
+      unsigned tt = __viaddmin_u16x2(nb, P1P1, centre);
+      tt = __vimin3_u16x2(tt, dJdJ, dJdJ);
+      const unsigned cur = tt + (cst[j] & em) - mpmp;
+      const unsigned na = __vadd2(acc[j], cur);             // update_accum_buffer: uint16 wrap per entry
+      if (e0) arow[2 * j] = (sgm_accum_t)(na & 0xffffu);
+      if (e1) arow[2 * j + 1] = (sgm_accum_t)(na >> 16);
+      pc[j] = (K - cur) & em;
+    }
+    pb0 = b0; pb1 = b1; ph = h; last_val = val;
+    if (wraps) --to_edge;
+  }
+}
+
+// One direction: the rows-in-lanes kernel when no box is wider than 6 or higher than 8, else the lane-per-disparity kernel.
+static int sgm_direction_launch(bool rows, const SgmMeta* meta, const sgm_cost_t* cost, sgm_accum_t* accum, const SgmGeom& g, int sc, int sr,
+                                bool first, sgm_accum_t* scratch, unsigned per_warp, cudaStream_t st) {
+  const int lines = sr == 0 ? g.oh : g.ow;
+  if (rows) {
+    const dim3 grid((lines + 7) / 8), blk(64);
+    if (sr == 0) { if (first) sgm_rows_kernel<0, true><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr); else sgm_rows_kernel<0, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr); }
+    else if (sc == 0) { if (first) sgm_rows_kernel<1, true><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr); else sgm_rows_kernel<1, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr); }
+    else { if (first) sgm_rows_kernel<2, true><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr); else sgm_rows_kernel<2, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr); }
+  } else {
     constexpr int WPB = 4;                                             // warps (= neighbouring lines) per CTA
     const dim3 grid((lines + WPB - 1) / WPB), blk(WPB * 32);
-    if (i == 0) sgm_lines_kernel<WPB, 0, true><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp);
-    else if (sr == 0) sgm_lines_kernel<WPB, 0, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp);
-    else if (sc == 0) sgm_lines_kernel<WPB, 1, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp);
-    else sgm_lines_kernel<WPB, 2, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp);
-    VWB_LAUNCH_CHECK();
+    if (sr == 0) { if (first) sgm_lines_kernel<WPB, 0, true><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp); else sgm_lines_kernel<WPB, 0, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp); }
+    else if (sc == 0) { if (first) sgm_lines_kernel<WPB, 1, true><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp); else sgm_lines_kernel<WPB, 1, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp); }
+    else { if (first) sgm_lines_kernel<WPB, 2, true><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp); else sgm_lines_kernel<WPB, 2, false><<<grid, blk, 0, st>>>(meta, cost, accum, g, sc, sr, scratch, per_warp); }
   }
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
+// The eight directions of accum_sgm_multithread (:2462-2611).  A direction is a set of sequential chains -- 4096 lines keep
+// a B200 far from full -- and the reference only ever ADDS the per-direction results (uint16, wrapping), so the directions
+// are independent: they run FOUR AT A TIME on four streams, each pair of directions into its own partial volume
+// (accum[k] receives directions k and k + 4; the first one stores without reading), and the winner-takes-all kernel sums
+// the four partial volumes on the fly.
+int sgm_paths_launch(const SgmMeta* meta, const sgm_cost_t* cost, sgm_accum_t* const* accum, int naccum, const SgmGeom& g, unsigned max_n,
+                     unsigned max_w, unsigned max_h, Arena& ar, cudaStream_t st) {
+  static const int DIRS[8][2] = {{1, 0}, {0, 1}, {1, 1}, {-1, 1}, {-1, 0}, {0, -1}, {1, -1}, {-1, -1}};
+  const bool rows = max_w <= 6 && max_h <= 8 && !getenv("VWB200_SGM_LANES_PER_ENTRY");
+  const int nlines = std::max(g.ow, g.oh);
+  sgm_accum_t* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned per_warp = 0;
+  if (!rows && max_n > 32) {
+    per_warp = 2 * ((max_n + 31u) & ~31u);
+    for (int k = 0; k < naccum; ++k) VWB_TRY(ar.alloc(&scratch[k], (size_t)per_warp * nlines));
+  }
+  if (naccum == 1) {
+    for (int i = 0; i < 8; ++i) VWB_TRY(sgm_direction_launch(rows, meta, cost, accum[0], g, DIRS[i][0], DIRS[i][1], i == 0, scratch[0], per_warp, st));
+    return VWB200_OK;
+  }
+  struct Side { cudaStream_t s = nullptr; cudaEvent_t e = nullptr; ~Side() { if (e) cudaEventDestroy(e); if (s) cudaStreamDestroy(s); } } side[3];
+  cudaEvent_t fork;
+  VWB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  struct EvGuard { cudaEvent_t e; ~EvGuard() { cudaEventDestroy(e); } } fg{fork};
+  VWB_CUDA(cudaEventRecord(fork, st));
+  for (int k = 0; k < 4; ++k) {
+    cudaStream_t sk = st;
+    if (k > 0) {
+      VWB_CUDA(cudaStreamCreateWithFlags(&side[k - 1].s, cudaStreamNonBlocking));
+      VWB_CUDA(cudaEventCreateWithFlags(&side[k - 1].e, cudaEventDisableTiming));
+      sk = side[k - 1].s;
+      VWB_CUDA(cudaStreamWaitEvent(sk, fork, 0));
+    }
+    VWB_TRY(sgm_direction_launch(rows, meta, cost, accum[k], g, DIRS[k][0], DIRS[k][1], true, scratch[k], per_warp, sk));
+    VWB_TRY(sgm_direction_launch(rows, meta, cost, accum[k], g, DIRS[k + 4][0], DIRS[k + 4][1], false, scratch[k], per_warp, sk));
+    if (k > 0) VWB_CUDA(cudaEventRecord(side[k - 1].e, sk));
+  }
+  for (int k = 0; k < 3; ++k) VWB_CUDA(cudaStreamWaitEvent(st, side[k].e, 0));
   return VWB200_OK;
 }
 
