@@ -273,6 +273,10 @@ int  vwb200_shard_exchange_halos(vwb200_shard* s, const vwb200_band_plan* plan, 
                                  float* right_band, int rcols, ptrdiff_t rpitch, void* stream);
 void vwb200_shard_destroy(vwb200_shard* s);
 
+/* Scratch memory is stream-ordered and stays cached in the device's default memory pool between calls (returning it at
+ * every synchronisation costs ~100 ms per 8K x 8K call).  vwb200_trim() hands the cached memory back to the driver. */
+int vwb200_trim(void);
+
 /* total number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 long long vwb200_kernel_launches(void);
 

@@ -778,6 +778,18 @@ int vwb200_device_count(void) {
   return n;
 }
 long long vwb200_kernel_launches(void) { return g_launches.load(); }
+// the engine keeps its stream-ordered scratch cached in the device's default memory pool between calls (ensure_device raises
+// the release threshold); a host application that wants the memory back -- e.g. before a torch allocation burst -- calls this
+int vwb200_trim(void) {
+  VWB_TRY(ensure_device());
+  int dev = 0;
+  VWB_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  VWB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  VWB_CUDA(cudaDeviceSynchronize());
+  VWB_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return VWB200_OK;
+}
 int vwb200_last_k1_stats(vwb200_k1_stats* out) { if (!out) return VWB200_EARG; *out = t_k1_stats; return VWB200_OK; }
 
 // calc_disparity on device-resident rasters: statistics -> kernel choice -> launch(es).  Results are bit-identical

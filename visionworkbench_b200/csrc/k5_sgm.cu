@@ -390,6 +390,19 @@ __device__ __forceinline__ bool sgm_parabola_peak(const double* z, double* dx, d
   return true;
 }
 
+// total of the four partial volumes of the concurrent directions (uint16 wrapping adds, like the reference's in-place
+// accumulation), 8 entries per thread, into the first volume: HBM bound, 4 x 2 B read + 2 B written per entry
+__global__ void __launch_bounds__(256) sgm_sum4_kernel(uint4* __restrict__ a0, const uint4* __restrict__ a1, const uint4* __restrict__ a2,
+                                                       const uint4* __restrict__ a3, size_t nvec) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 v = a0[i];
+    const uint4 x = a1[i], y = a2[i], z = a3[i];
+    v.x = __vadd2(__vadd2(v.x, x.x), __vadd2(y.x, z.x)); v.y = __vadd2(__vadd2(v.y, x.y), __vadd2(y.y, z.y));
+    v.z = __vadd2(__vadd2(v.z, x.z), __vadd2(y.z, z.z)); v.w = __vadd2(__vadd2(v.w, x.w), __vadd2(y.w, z.w));
+    a0[i] = v;
+  }
+}
+
 // accum = the first partial volume (it receives the totals of the pixels that need them re-read: ties, sub-pixel), a1..a3 =
 // the other partial volumes of the concurrent directions (NULL: accum already holds the total)
 __global__ void __launch_bounds__(128) sgm_wta_kernel(sgm_accum_t* __restrict__ accum, const sgm_accum_t* __restrict__ a1,
@@ -725,7 +738,13 @@ int sgm_run(const SgmArgs& a, Arena& /*callers_arena*/, cudaStream_t st) {
   } else {
     VWB_TRY(sgm_paths_launch(meta, cost, parts, naccum, g, maxes[0], maxes[1], maxes[2], ar, st));
   }
-  sgm_wta_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, parts[1], parts[2], parts[3], scratch, meta, g, a.out, a.opitch,
+  if (naccum == 4) {
+    const size_t nvec = ((size_t)total + 7) / 8;              // the volumes are 16-byte aligned and padded
+    sgm_sum4_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<uint4*>(accum), reinterpret_cast<const uint4*>(parts[1]),
+                                             reinterpret_cast<const uint4*>(parts[2]), reinterpret_cast<const uint4*>(parts[3]), nvec);
+    VWB_LAUNCH_CHECK();
+  }
+  sgm_wta_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, nullptr, nullptr, nullptr, scratch, meta, g, a.out, a.opitch,
                                                                  a.out_sub != nullptr, a.subpixel_mode, a.out_sub, a.sub_pitch);
   VWB_LAUNCH_CHECK();
   return VWB200_OK;
