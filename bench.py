@@ -334,7 +334,7 @@ def cfg_calc(v, name, cost_name, size, s, k, seed, left=None, right=None, tiles=
             "parity_sample": {"tiles": tiles, "tile": 128, "mismatches": bad}}
 
 
-def cfg3_view(v, size=8192, tile=1024, threads=8):
+def cfg3_view(v, size=8192, tile=1024, threads=16):
     """config 3: PyramidCorrelationView, 5 levels, SquaredCost 15x15, 128x128 window, L/R check 2, filter radius 5, 1024^2
     tiles rasterised from `threads` host threads (the reference's block_write_image pattern), device-resident inputs"""
     import torch

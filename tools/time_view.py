@@ -17,19 +17,20 @@ print(f"generated in {time.time()-t0:.1f}s")
 dl, dr, dlm, drm = [torch.from_numpy(a).cuda() for a in (left, right, lm, rm)]
 view = v.pyramid_correlate(dl, dr, dlm, drm, 0, 0.0, search, (k, k), cost, 0, 0.0, 2.0, 0, 5, LV)
 out = torch.empty((S, S, 3), dtype=torch.float32, device="cuda")
-for it in range(2):
+streams = [torch.cuda.Stream() for _ in range(NT)]      # one stream per host thread, as bench.py's config 3 does
+for it in range(3):
     n0 = v.kernel_launches()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     tiles = [(x, y) for y in range(0, S, T) for x in range(0, S, T)]
-    def one(t):
-        x, y = t
-        out[y:y+T, x:x+T] = view.rasterize(None, (x, y, min(S, x+T), min(S, y+T)))
+    def work(i):
+        with torch.cuda.stream(streams[i]):
+            for x, y in tiles[i::NT]:
+                view.rasterize(out[y:y+T, x:x+T], (x, y, min(S, x+T), min(S, y+T)))
     if NT > 1:
         with ThreadPoolExecutor(NT) as ex:
-            list(ex.map(one, tiles))
+            list(ex.map(work, range(NT)))
     else:
-        for t in tiles:
-            one(t)
+        work(0)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(f"view {S}x{S} tiles {T} levels {LV} cost {cost} k{k} search {s} threads {NT}: {dt*1e3:.1f} ms  {S*S/dt/1e6:.2f} Mpix/s  launches {v.kernel_launches()-n0}  valid {float((out[...,2]>0).float().mean()):.3f}")
 if check:

@@ -86,7 +86,8 @@ struct NccMaps { const double* inv_l; int l_ox, l_oy, l_w, l_h; const double* in
 struct KEvents { cudaEvent_t e0 = nullptr, e1 = nullptr; };
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
                       int kx, int ky, NccMaps ncc, vwb200_dispi* out, double* scratch_cost, int* scratch_idx, bool clamp_reads,
-                      int stage_r_floats, cudaStream_t st, const KEvents* ev = nullptr);   // stage_r_floats: 0 = read through L1
+                      int stage_r_floats, cudaStream_t st, const KEvents* ev = nullptr,    // stage_r_floats: 0 = read through L1
+                      const int* zone_gate = nullptr);                                     // != nullptr: only tiles of zones with gate[zone] != 0
 bool k1_generic_can_stage(int kx, int ky, int sx, int sy, int nchunks);
 long long k1_generic_stage_floats(int kx, int ky, int sx, int sy, int nchunks);
 static constexpr int K1G_DCHUNK = 256;
@@ -95,6 +96,21 @@ int k1_generic_merge_launch(int cost, const Zone* d_zones, const int* d_split, i
                             const int* scratch_idx, vwb200_dispi* out, cudaStream_t st);
 int k1_generic_tile_w(int kx);
 int k1_generic_tile_h(int ky);
+// ---- K1 zone-int (k1_zone_int.cu): the zone kernel in exact int32 for integer-valued imagery (level 0 of 8-bit rasters) ----
+// range = vmax - vmin of both rasters; *ib_out = log2 of the disparities one warp covers (larger zones are split in chunks)
+bool k1_zone_int_supported(int cost, int kx, int ky, long long range, int* ib_out);
+int k1_zone_int_tile_w(int k);
+int k1_zone_int_tile_h();
+long long k1_zone_int_stage_u16(int k, int sx, int sy, int nchunks, int ib);
+long long k1_zone_int_stage_max();
+// zone_flag[zone] is set when a tile of the zone met a non-integer pixel (mean-filled masked pixels): the caller re-runs those
+// zones through the fp64 zone kernel
+int k1_zone_int_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles, int k, float vmin, float vmax,
+                       int warp_u16, vwb200_dispi* out, double* scratch_cost, int* scratch_idx, int* zone_flag, cudaStream_t st,
+                       const KEvents* ev = nullptr);
+// integer-valued rasters of a zone batch: enables the zone-int kernel in run_k1_zones.  checked: some pixels were replaced by
+// a (non-integer) mean, zones that touch them fall back to the fp64 kernel
+struct ZoneIntMode { bool on; float vmin, vmax; bool checked; };
 // 1/boxsum(v*v) over window origins [ox0,ox0+ow) x [oy0,oy0+oh) with clamped (constant edge) reads.
 int box_sq_inv_launch(ImgF img, int kx, int ky, int ox0, int oy0, int ow, int oh, double* out, cudaStream_t st);
 // boxsum(v) (centred == 0) or boxsum((v - c)^2) (centred == 1) as int32 over the same window-origin domain (integer imagery)
@@ -132,6 +148,7 @@ int crop_extend_u8_launch(ImgB src, int x0, int y0, int w, int h, int zero_outsi
 // masked mean over every 2nd pixel (CorrelationView.cc:133-136): d_acc = {double sum, double count}
 int masked_mean_launch(ImgF img, ImgB mask, double* d_acc2, cudaStream_t st);
 int mean_fill_launch(float* img, int w, int h, ptrdiff_t pitch, ImgB mask, const double* d_acc2, cudaStream_t st);
+int mask_any_zero_launch(ImgB mask, int* d_flag, cudaStream_t st);      // *d_flag = 1 if the mask holds a zero (caller zeroes it)
 int pyramid_down_launch(ImgF in, float* out, ptrdiff_t opitch, cudaStream_t st);
 int subsample_mask_launch(ImgB in, uint8_t* out, ptrdiff_t opitch, cudaStream_t st);
 // gaussian (separable, constant edge) into out via work; then Laplacian (mode 1) or img - g (mode 2)

@@ -6,6 +6,7 @@
 // owns a stream and stream-ordered allocations (VW calls prerasterize concurrently from its tile
 // thread pool, Image/ImageIO.h:228-235).
 #include "common.cuh"
+#include <chrono>
 #include "k5_sgm.cuh"
 #include <cstdarg>
 #include <cstdio>
@@ -90,8 +91,13 @@ static void make_tiles(const std::vector<Zone>& zones, int tile_w, int tile_h, s
 static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones, int kx, int ky,
                         vwb200_dispi* d_out, Arena& ar, cudaStream_t st, const Zone** d_zones_out = nullptr,
                         const Tile** d_tiles_out = nullptr, int* ntiles_out = nullptr, const KEvents* ev = nullptr,
-                        const std::vector<char>* skip = nullptr) {
+                        const std::vector<char>* skip = nullptr, const ZoneIntMode* zim = nullptr) {
   if (zones.empty()) { if (ntiles_out) *ntiles_out = 0; return VWB200_OK; }
+  // integer-valued imagery (level 0 of 8-bit rasters): the int32 warp-per-tile kernel takes every zone whose search patch fits
+  int ib = 0;
+  const bool int_mode = zim && zim->on && !getenv("VWB200_NO_ZONE_INT") &&
+                        k1_zone_int_supported(cost, kx, ky, (long long)zim->vmax - (long long)zim->vmin, &ib);
+  std::vector<char> zint(zones.size(), 0);
   // split the disparity range of zones with many disparities over several CTAs (load balance: a zone whose
   // range was reset to the full search window would otherwise be one CTA's serial loop)
   std::vector<int> split;
@@ -100,7 +106,13 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
   for (size_t zi = 0; zi < zones.size(); ++zi) {
     Zone& z = zones[zi];
     const int nd = z.sx * z.sy;
-    z.nchunks = (skip && (*skip)[zi]) ? 1 : (nd + K1G_DCHUNK - 1) / K1G_DCHUNK;     // zones the fast kernel took are not ours
+    const bool skipped = skip && (*skip)[zi];
+    z.nchunks = skipped ? 1 : (nd + K1G_DCHUNK - 1) / K1G_DCHUNK;     // zones the fast kernel took are not ours
+    if (int_mode && !skipped) {
+      const int nci = (nd + (1 << ib) - 1) >> ib;
+      if (k1_zone_int_stage_u16(kx, z.sx, z.sy, nci, ib) <= k1_zone_int_stage_max() &&
+          (nci == 1 || (long long)z.w * z.h * nci < (1ll << 29))) { zint[zi] = 1; z.nchunks = nci; }
+    }
     z.sbase = 0;
     if (z.nchunks > 1 && (long long)z.w * z.h * z.nchunks < (1ll << 29)) {
       z.sbase = scratch_elems; scratch_elems += (long long)z.nchunks * z.w * z.h; split.push_back((int)zi);
@@ -108,9 +120,37 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
     if (z.lx < 0 || z.ly < 0 || z.lx + z.w + kx - 1 > left.w || z.ly + z.h + ky - 1 > left.h ||
         z.rx < 0 || z.ry < 0 || z.rx + z.w + kx - 1 + z.sx - 1 > right.w || z.ry + z.h + ky - 1 + z.sy - 1 > right.h) clamp_reads = true;
   }
-  std::vector<Tile> tiles, tiles_post;
+  std::vector<Tile> tiles, tiles_post, tiles_int;
   make_tiles(zones, k1_generic_tile_w(kx), k1_generic_tile_h(ky), tiles, true);
-  if (skip) tiles.erase(std::remove_if(tiles.begin(), tiles.end(), [&](const Tile& t) { return (*skip)[t.zone] != 0; }), tiles.end());
+  tiles.erase(std::remove_if(tiles.begin(), tiles.end(), [&](const Tile& t) { return (skip && (*skip)[t.zone] != 0) || zint[t.zone]; }), tiles.end());
+  // zone-int tiles: balanced split of each zone (the kernel derives the tile size from the zone with the same formula),
+  // in up to three launches by the size of the staged right patch, heaviest tiles first inside a launch
+  static constexpr long long ZI_CLS[2] = {3072, 12288};
+  int ni_cls[3] = {0, 0, 0};
+  long long ri_max[3] = {0, 0, 0};
+  if (int_mode) {
+    const int TW = k1_zone_int_tile_w(kx), TH = k1_zone_int_tile_h();
+    for (size_t zi = 0; zi < zones.size(); ++zi) {
+      if (!zint[zi]) continue;
+      const Zone& z = zones[zi];
+      const int ntx = (z.w + TW - 1) / TW, twb = (z.w + ntx - 1) / ntx, nty = (z.h + TH - 1) / TH, thb = (z.h + nty - 1) / nty;
+      for (int c = 0; c < z.nchunks; ++c)
+        for (int ty = 0; ty < z.h; ty += thb)
+          for (int tx = 0; tx < z.w; tx += twb) tiles_int.push_back(Tile{(int)zi, tx, ty, c});
+    }
+    auto need = [&](const Tile& t) { const Zone& z = zones[t.zone]; return k1_zone_int_stage_u16(kx, z.sx, z.sy, z.nchunks, ib); };
+    auto icls = [&](const Tile& t) { const long long n = need(t); return n <= ZI_CLS[0] ? 0 : (n <= ZI_CLS[1] ? 1 : 2); };
+    auto work = [&](const Tile& t) {
+      const Zone& z = zones[t.zone];
+      const int nd = z.sx * z.sy;
+      return z.nchunks > 1 ? std::min(1 << ib, nd - (t.chunk << ib)) : nd;
+    };
+    std::stable_sort(tiles_int.begin(), tiles_int.end(), [&](const Tile& a, const Tile& b) {
+      const int ca = icls(a), cb = icls(b);
+      return ca != cb ? ca < cb : work(a) > work(b);
+    });
+    for (const Tile& t : tiles_int) { const int c = icls(t); ++ni_cls[c]; ri_max[c] = std::max(ri_max[c], need(t)); }
+  }
   // three launches: tiles with a small right search patch (staged; little shared memory -> 2-3 CTAs per SM), tiles with
   // a large one (staged, 1 CTA per SM), and tiles whose patch does not fit (reads through L1)
   static constexpr long long SMALL_R = 6144;
@@ -135,9 +175,51 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
     VWB_CUDA(cudaMemcpyAsync(d_split, split.data(), split.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   }
   VWB_TRY(ar.alloc(&d_zones, zones.size()));
-  VWB_TRY(ar.alloc(&d_tiles, tiles.size()));
+  VWB_TRY(ar.alloc(&d_tiles, tiles.size() + 1));
   VWB_CUDA(cudaMemcpyAsync(d_zones, zones.data(), zones.size() * sizeof(Zone), cudaMemcpyHostToDevice, st));
-  VWB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+  if (!tiles.empty()) VWB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+  bool ev_used = false;
+  std::vector<Tile> tiles_gated;
+  const NccMaps no_ncc = {};
+  if (!tiles_int.empty()) {
+    Tile* d_ti; int* d_flag;
+    VWB_TRY(ar.alloc(&d_ti, tiles_int.size()));
+    VWB_TRY(ar.alloc(&d_flag, zones.size()));
+    VWB_CUDA(cudaMemcpyAsync(d_ti, tiles_int.data(), tiles_int.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    VWB_CUDA(cudaMemsetAsync(d_flag, 0, zones.size() * sizeof(int), st));
+    int off = 0;
+    for (int c = 0; c < 3; ++c) {
+      if (!ni_cls[c]) continue;
+      VWB_TRY(k1_zone_int_launch(cost, left, right, d_zones, d_ti + off, ni_cls[c], kx, zim->vmin, zim->vmax, (int)ri_max[c], d_out, d_sc, d_si,
+                                 d_flag, st, ev_used ? nullptr : ev));
+      ev_used = true;
+      off += ni_cls[c];
+    }
+    if (zim->checked) {
+      // zones that met a mean-filled (non-integer) pixel: the fp64 kernel over the tiles of every integer zone, gated by the flag
+      make_tiles(zones, k1_generic_tile_w(kx), k1_generic_tile_h(ky), tiles_gated, true);
+      tiles_gated.erase(std::remove_if(tiles_gated.begin(), tiles_gated.end(), [&](const Tile& t) { return !zint[t.zone]; }), tiles_gated.end());
+      std::stable_sort(tiles_gated.begin(), tiles_gated.end(), [&](const Tile& a, const Tile& b) { return cls(a) < cls(b); });
+      int ng[3] = {0, 0, 0};
+      long long rg[3] = {0, 0, 0};
+      for (const Tile& t : tiles_gated) {
+        const int c = cls(t);
+        const Zone& z = zones[t.zone];
+        ++ng[c];
+        rg[c] = std::max(rg[c], k1_generic_stage_floats(kx, ky, z.sx, z.sy, z.nchunks));
+      }
+      Tile* d_tg;
+      VWB_TRY(ar.alloc(&d_tg, tiles_gated.size()));
+      VWB_CUDA(cudaMemcpyAsync(d_tg, tiles_gated.data(), tiles_gated.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+      int goff = 0;
+      for (int c = 0; c < 3; ++c) {
+        if (!ng[c]) continue;
+        VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tg + goff, ng[c], kx, ky, no_ncc, d_out, d_sc, d_si, clamp_reads,
+                                  c == 2 ? 0 : (int)rg[c], st, nullptr, d_flag));
+        goff += ng[c];
+      }
+    }
+  }
   NccMaps ncc = {};
   if (cost == VWB200_CROSS_CORRELATION) {
     int lx0 = INT_MAX, ly0 = INT_MAX, lx1 = INT_MIN, ly1 = INT_MIN, rx0 = INT_MAX, ry0 = INT_MAX, rx1 = INT_MIN, ry1 = INT_MIN;
@@ -155,7 +237,6 @@ static int run_k1_zones(int cost, ImgF left, ImgF right, std::vector<Zone> zones
   }
   {
     int off = 0;
-    bool ev_used = false;
     for (int c = 0; c < 3; ++c) {
       if (!n_cls[c]) continue;
       VWB_TRY(k1_generic_launch(cost, left, right, d_zones, d_tiles + off, n_cls[c], kx, ky, ncc, d_out, d_sc, d_si, clamp_reads,
@@ -457,8 +538,16 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, float** d_sub
   }
   VWB_TRY(crop_extend_f32_launch(Lin, lg.x0 - lox, lg.y0 - loy, b0.lw, b0.lh, b0.l, b0.lw, st));
   VWB_TRY(crop_extend_f32_launch(Rin, rg.x0 - rox_, rg.y0 - roy_, b0.rw, b0.rh, b0.r, b0.rw, st));
+  // level-0 imagery statistics, taken BEFORE the mean fill (the mean of pixels lies inside their range, so vmin / vmax
+  // still bound the filled image): integer-valued rasters with a small range -> the exact-integer kernels take level 0.
+  // any_filled: some pixel of the padded tile is masked and becomes the (non-integer) mean -- the integer zone kernel then
+  // checks what it reads and hands the zones that touch such pixels to the fp64 kernel; the whole-zone fast kernels are off.
+  float hstats[6] = {0, 0, 0, 0, 0, 0};
+  int any_filled = 0;
+  const bool want_stats = p.cost_type == VWB200_ABSOLUTE_DIFFERENCE || p.cost_type == VWB200_SQUARED_DIFFERENCE;
   {  // mean fill of masked pixels (:116-149); masks here are constant-edge-extended over the padded ROI
     uint8_t *lmb, *rmb; double* acc;
+    float* d_stats = nullptr; int* d_filled = nullptr;
     VWB_TRY(ar.alloc(&lmb, (size_t)b0.lw * b0.lh));
     VWB_TRY(ar.alloc(&rmb, (size_t)b0.rw * b0.rh));
     VWB_TRY(ar.alloc(&acc, 2 * (2 + 2 * 256)));
@@ -470,24 +559,25 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, float** d_sub
     double hacc[4];
     VWB_CUDA(cudaMemcpyAsync(hacc, acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     VWB_CUDA(cudaMemcpyAsync(hacc + 2, acc_r, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (want_stats) {
+      VWB_TRY(ar.alloc(&d_stats, 6));
+      VWB_TRY(ar.alloc(&d_filled, 1));
+      VWB_TRY(image_stats_launch(ImgF{b0.l, b0.lw, b0.lh, b0.lw}, d_stats, st));
+      VWB_TRY(image_stats_launch(ImgF{b0.r, b0.rw, b0.rh, b0.rw}, d_stats + 3, st));
+      VWB_CUDA(cudaMemsetAsync(d_filled, 0, sizeof(int), st));
+      VWB_TRY(mask_any_zero_launch(ImgB{lmb, b0.lw, b0.lh, b0.lw}, d_filled, st));
+      VWB_TRY(mask_any_zero_launch(ImgB{rmb, b0.rw, b0.rh, b0.rw}, d_filled, st));
+      VWB_CUDA(cudaMemcpyAsync(hstats, d_stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
+      VWB_CUDA(cudaMemcpyAsync(&any_filled, d_filled, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     VWB_CUDA(cudaStreamSynchronize(st));
     if (hacc[1] == 0.0 || hacc[3] == 0.0) { *all_invalid = 1; *d_disp_out = nullptr; return VWB200_OK; }   // :137-142, :320-331
     VWB_TRY(mean_fill_launch(b0.l, b0.lw, b0.lh, b0.lw, ImgB{lmb, b0.lw, b0.lh, b0.lw}, acc, st));
     VWB_TRY(mean_fill_launch(b0.r, b0.rw, b0.rh, b0.rw, ImgB{rmb, b0.rw, b0.rh, b0.rw}, acc_r, st));
   }
-  // level-0 imagery statistics (after the mean fill): integer valued with a small range -> the exact-integer fast
-  // kernel can take the large zones of level 0
-  float hstats[6] = {0, 0, 0, 0, 0, 0};
-  if (p.cost_type == VWB200_ABSOLUTE_DIFFERENCE || p.cost_type == VWB200_SQUARED_DIFFERENCE) {
-    float* d_stats;
-    VWB_TRY(ar.alloc(&d_stats, 6));
-    VWB_TRY(image_stats_launch(ImgF{b0.l, b0.lw, b0.lh, b0.lw}, d_stats, st));
-    VWB_TRY(image_stats_launch(ImgF{b0.r, b0.rw, b0.rh, b0.rw}, d_stats + 3, st));
-    VWB_CUDA(cudaMemcpyAsync(hstats, d_stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
-    VWB_CUDA(cudaStreamSynchronize(st));
-  }
   const float tile_vmin = std::min(hstats[0], hstats[3]), tile_vmax = std::max(hstats[1], hstats[4]);
-  const bool tile_integer = hstats[2] != 0.0f && hstats[5] != 0.0f && p.prefilter_mode == VWB200_PREFILTER_NONE;
+  const bool raster_integer = want_stats && hstats[2] != 0.0f && hstats[5] != 0.0f && p.prefilter_mode == VWB200_PREFILTER_NONE;
+  const bool tile_integer = raster_integer && !any_filled;          // every pixel of the level-0 images is an integer
   // final masks: zero edge extension, no kernel padding (:192-197)
   b0.lmw = bw; b0.lmh = bh; b0.rmw = bw + ssx; b0.rmh = bh + ssy;
   VWB_TRY(ar.alloc(&b0.lm, (size_t)b0.lmw * b0.lmh));
@@ -517,6 +607,11 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, float** d_sub
   if (p.algorithm != VWB200_CORRELATION_BM) return prerasterize_sgm(bbox, py, levels, d_disp_out, d_sub_out, df, ar, st);
 
   // ---- level loop (CorrelationView.cc:363-830) ----
+  const bool prof = getenv("VWB200_PROFILE") != nullptr;      // host-side wall-clock split of this call, one line on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+  const auto t_loop = now();
+  double ms_zones = 0, ms_d2h = 0, ms_subdiv = 0;
   std::vector<HostZone> zones;
   zones.push_back(HostZone{Box{0, 0, py[levels].lmw, py[levels].lmh}, Box{0, 0, ssx / up + 1, ssy / up + 1}});   // :338-342
   vwb200_dispi* disp = nullptr;
@@ -586,9 +681,12 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, float** d_sub
       for (size_t i = 0; i < zr.size(); ++i) VWB_TRY(try_fast(zr[i], Rl, Ll, rl, fast_r[i]));
     }
     const Zone* d_zl = nullptr; const Tile* d_tl = nullptr; int ntl = 0;
-    VWB_TRY(run_k1_zones(p.cost_type, Ll, Rl, zl, kx, ky, disp, ar, st, &d_zl, &d_tl, &ntl, nullptr, &fast_l));
+    const ZoneIntMode zim{level == 0 && raster_integer, tile_vmin, tile_vmax, any_filled != 0};
+    const auto t_z = now();
+    VWB_TRY(run_k1_zones(p.cost_type, Ll, Rl, zl, kx, ky, disp, ar, st, &d_zl, &d_tl, &ntl, nullptr, &fast_l, &zim));
     const Zone* d_zr = nullptr;
-    if (check && !zr.empty()) VWB_TRY(run_k1_zones(p.cost_type, Rl, Ll, zr, kx, ky, rl, ar, st, &d_zr, nullptr, nullptr, nullptr, &fast_r));
+    if (check && !zr.empty()) VWB_TRY(run_k1_zones(p.cost_type, Rl, Ll, zr, kx, ky, rl, ar, st, &d_zr, nullptr, nullptr, nullptr, &fast_r, &zim));
+    ms_zones += ms_since(t_z);
     if (!zl.empty()) {
       int2* d_post;
       VWB_TRY(ar.alloc(&d_post, post.size()));
@@ -615,11 +713,15 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, float** d_sub
       VWB_TRY(blob_filter_launch(disp, dw, dh, p.blob_filter_area / scaling, work, st));
     }
     if (level != 0) {   // :754-799 refine the search zones on the host (zones are O(10^3), data dependent)
+      const auto t_d = now();
       hdisp.resize((size_t)dw * dh);
       VWB_CUDA(cudaMemcpyAsync(hdisp.data(), disp, hdisp.size() * sizeof(vwb200_dispi), cudaMemcpyDeviceToHost, st));
       VWB_CUDA(cudaStreamSynchronize(st));
+      ms_d2h += ms_since(t_d);
+      const auto t_s = now();
       zones.clear();
       subdivide_regions_host(hdisp.data(), dw, dh, kx, ky, zones);
+      ms_subdiv += ms_since(t_s);
       const LevelImgs& nl = py[level - 1];
       const Box scale_search{0, 0, nl.rw - nl.lw, nl.rh - nl.lh};
       for (HostZone& z : zones) {
@@ -637,6 +739,12 @@ int vwb200_corr::prerasterize(Box bbox, vwb200_dispi** d_disp_out, float** d_sub
   const LevelImgs& l0 = py[0];
   if (l0.lmw != bw || l0.lmh != bh) { set_error("PyramidCorrelation: Solved disparity doesn't match requested bbox size."); return VWB200_EMATH; }
   if (df.d) VWB_TRY(diff_invalidate_launch(disp, bw, bh, df.d, df.pitch, df.ox, df.oy, st));   // :848-857
+  if (prof) {
+    const double enq = ms_since(t_loop);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[vwb200] tile %d,%d: level loop %.2f ms host (zone tables+launch+sync %.2f, D2H+wait %.2f, subdivide %.2f), %.2f ms until the stream drained\n",
+            bbox.x0, bbox.y0, enq, ms_zones, ms_d2h, ms_subdiv, ms_since(t_loop));
+  }
   *d_disp_out = disp;
   return VWB200_OK;
 }
@@ -806,7 +914,9 @@ static int calc_disparity_device(int cost_type, ImgF Li, ImgF Ri, int W, int H, 
   const float vmin = std::min(hs[0], hs[3]), vmax = std::max(hs[1], hs[4]);
   const bool integer = hs[2] != 0.0f && hs[5] != 0.0f;
   // exact-integer fast path when the imagery allows it
-  if (k1_fast_supported(cost_type, kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK) {
+  const bool force_zone_int = getenv("VWB200_K1_ZONE_INT") && integer;      // test hook: the level loop's integer zone kernel
+  if (force_zone_int) {
+  } else if (k1_fast_supported(cost_type, kx, ky, sx, sy, vmin, vmax, integer) == VWB200_OK) {
     const size_t wb = k1_fast_workspace_bytes(W, H, sx, sy, kx, ky);
     unsigned char* ws;
     VWB_TRY(ar.alloc(&ws, wb));
@@ -822,7 +932,8 @@ static int calc_disparity_device(int cost_type, ImgF Li, ImgF Ri, int W, int H, 
     std::vector<Zone> zones(1);
     Zone& z = zones[0];
     z.obase = 0; z.opitch = (int)dop; z.w = W; z.h = H; z.lx = 0; z.ly = 0; z.rx = 0; z.ry = 0; z.sx = sx; z.sy = sy; z.addx = 0; z.addy = 0;
-    VWB_TRY(run_k1_zones(cost_type, Li, Ri, zones, kx, ky, dout, ar, st, nullptr, nullptr, nullptr, kev));
+    const ZoneIntMode zim{force_zone_int, vmin, vmax, false};
+    VWB_TRY(run_k1_zones(cost_type, Li, Ri, zones, kx, ky, dout, ar, st, nullptr, nullptr, nullptr, kev, nullptr, &zim));
   }
   *path_out = path;
   return VWB200_OK;

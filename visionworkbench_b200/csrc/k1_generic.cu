@@ -73,9 +73,10 @@ template <int COST, bool CLAMP, bool STAGE>
 __global__ void __launch_bounds__(K1G_THREADS)
 k1_generic_kernel(ImgF L, ImgF R, const Zone* __restrict__ zones, const Tile* __restrict__ tiles,
                   int kx, int ky, NccMaps ncc, vwb200_dispi* __restrict__ out, double* __restrict__ scratch_cost,
-                  int* __restrict__ scratch_idx) {
+                  int* __restrict__ scratch_idx, const int* __restrict__ zone_gate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Tile t = tiles[blockIdx.x];
+  if (zone_gate && !zone_gate[t.zone]) return;                  // fallback pass behind the integer zone kernel: flagged zones only
   const Zone z = zones[t.zone];
   const int tw = min(ZT_W, z.w - t.tx), th = min(ZT_H, z.h - t.ty);
   const int pw = tw + kx - 1, ph = th + ky - 1;
@@ -263,12 +264,12 @@ bool k1_generic_can_stage(int kx, int ky, int sx, int sy, int nchunks) { return 
 
 int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, const Tile* d_tiles, int ntiles,
                       int kx, int ky, NccMaps ncc, vwb200_dispi* out, double* scratch_cost, int* scratch_idx, bool clamp_reads,
-                      int stage_r_floats, cudaStream_t st, const KEvents* ev) {
+                      int stage_r_floats, cudaStream_t st, const KEvents* ev, const int* zone_gate) {
   if (ntiles <= 0) return VWB200_OK;
   if (kx > 129 || ky > 129) { set_error("kernel size %dx%d exceeds the supported 129", kx, ky); return VWB200_ENOIMPL; }
   const bool stage = stage_r_floats > 0;
   const size_t smem = k1g_smem_bytes(kx, ky, stage_r_floats);
-  void (*kern)(ImgF, ImgF, const Zone*, const Tile*, int, int, NccMaps, vwb200_dispi*, double*, int*);
+  void (*kern)(ImgF, ImgF, const Zone*, const Tile*, int, int, NccMaps, vwb200_dispi*, double*, int*, const int*);
 #define KSEL(C) (stage ? k1_generic_kernel<C, true, true> : (clamp_reads ? k1_generic_kernel<C, true, false> : k1_generic_kernel<C, false, false>))
   switch (cost) {
     case VWB200_SQUARED_DIFFERENCE: kern = KSEL(VWB200_SQUARED_DIFFERENCE); break;
@@ -280,7 +281,7 @@ int k1_generic_launch(int cost, ImgF left, ImgF right, const Zone* d_zones, cons
   if (smem > 227 * 1024) { set_error("zone kernel needs %zu bytes of shared memory", smem); return VWB200_ENOIMPL; }
   VWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (ev && ev->e0) cudaEventRecord(ev->e0, st);
-  kern<<<ntiles, K1G_THREADS, smem, st>>>(left, right, d_zones, d_tiles, kx, ky, ncc, out, scratch_cost, scratch_idx);
+  kern<<<ntiles, K1G_THREADS, smem, st>>>(left, right, d_zones, d_tiles, kx, ky, ncc, out, scratch_cost, scratch_idx, zone_gate);
   VWB_LAUNCH_CHECK();
   if (ev && ev->e1) cudaEventRecord(ev->e1, st);
   return VWB200_OK;

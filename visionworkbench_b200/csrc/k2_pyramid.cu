@@ -100,6 +100,21 @@ int mean_fill_launch(float* img, int w, int h, ptrdiff_t pitch, ImgB mask, const
   return VWB200_OK;
 }
 
+// *flag = 1 if the mask holds a zero (some pixel of the tile will be mean-filled: the imagery is then not integer-valued
+// everywhere even when the rasters are).  The caller zeroes the flag.
+__global__ void mask_any_zero_kernel(ImgB mask, int* __restrict__ flag) {
+  const long long n = (long long)mask.w * mask.h;
+  bool z = false;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+    z |= mask.p[(ptrdiff_t)(k / mask.w) * mask.pitch + (k % mask.w)] == 0;
+  if (__any_sync(0xffffffffu, z) && (threadIdx.x & 31) == 0) *flag = 1;
+}
+int mask_any_zero_launch(ImgB mask, int* d_flag, cudaStream_t st) {
+  mask_any_zero_kernel<<<148, 256, 0, st>>>(mask, d_flag);
+  VWB_LAUNCH_CHECK();
+  return VWB200_OK;
+}
+
 // ---- fused 5-tap separable smoothing + 2x subsample ---------------------------------------------------
 // CTA computes a PD_TW x PD_TH tile of OUTPUT pixels.  Stage A: row-convolved values at the even
 // columns for the (2*PD_TH+3) source rows the tile needs go to shared memory (each computed once per
