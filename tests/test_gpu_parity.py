@@ -224,6 +224,29 @@ def test_device_tensor_path(vwb, oracle):
     _assert_disp_equal(got.cpu().numpy(), oracle.calc_disparity(0, left, right, (12, 10), (9, 9)))
 
 
+@pytest.mark.parametrize("side_stream", [False, True])
+def test_device_inputs_are_ordered_after_their_producer(vwb, oracle, side_stream):
+    """device-resident inputs are produced on the caller's stream -- torch's default stream is the NULL
+    (legacy) stream -- and the engine must run after the producer.  A long matmul is queued in front of the copy that gives
+    the rasters their content; an engine that ran on a private stream would read the zeros underneath."""
+    import torch
+    from visionworkbench_b200.synth import make_rasters
+    left, right = make_rasters(160, 120, (16, 12), (9, 9), seed=23)
+    ref = oracle.calc_disparity(0, left, right, (16, 12), (9, 9))
+    hl, hr = torch.from_numpy(left).pin_memory(), torch.from_numpy(right).pin_memory()
+    big = torch.randn(8192, 8192, device="cuda")
+    stream = torch.cuda.Stream() if side_stream else torch.cuda.current_stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        dl, dr = torch.zeros(left.shape, device="cuda"), torch.zeros(right.shape, device="cuda")
+        for _ in range(4):
+            big = big @ big * 1e-4                      # tens of milliseconds of queued work
+        dl.copy_(hl, non_blocking=True)
+        dr.copy_(hr, non_blocking=True)
+        got = vwb.calc_disparity(0, dl, dr, (16, 12), (9, 9))
+    _assert_disp_equal(got.cpu().numpy(), ref)
+
+
 @pytest.mark.parametrize("shape", [((300, 70), (16, 8), (21, 21)), ((500, 40), (32, 4), (7, 7)), ((237, 33), (64, 3), (15, 15)),
                                    ((64, 64), (8, 8), (3, 5)), ((260, 100), (128, 2), (21, 21)), ((473, 65), (24, 11), (31, 9))])
 def test_calc_disparity_exact_int_fast_path(vwb, oracle, shape):
