@@ -678,8 +678,7 @@ def run_ours(a):
     if world > 1:
         dist.destroy_process_group()
     sys.stdout.flush()
-    os.dup2(real_stdout, 1)
-    os.close(real_stdout)
+    os.close(real_stdout)        # fd 1 keeps pointing at stderr: NCCL still prints INFO lines while the process exits
 
 
 if __name__ == "__main__":
