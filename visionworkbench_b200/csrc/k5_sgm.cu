@@ -295,8 +295,9 @@ __global__ void __launch_bounds__(256) sgm_meta_kernel(const short4* __restrict_
 // ---- Hamming costs (get_hamming_distance_costs, SGM.cc:39-73) ---------------------------------------------------------
 // one warp per 32 consecutive pixels: lane i fetches record i (coalesced), then the warp walks the 32 pixels with
 // lanes = the pixel's disparities (coalesced byte stores into the ragged volume); 4 pixels in flight per iteration
+// only_big != 0: the warps whose 32 pixels all have <= 32 entries were done by sgm_cost_lanes_kernel
 __global__ void __launch_bounds__(256) sgm_cost_kernel(const unsigned long long* __restrict__ lc, const unsigned long long* __restrict__ rc,
-                                                       const SgmMeta* __restrict__ meta, SgmGeom g, sgm_cost_t* __restrict__ cost) {
+                                                       const SgmMeta* __restrict__ meta, SgmGeom g, sgm_cost_t* __restrict__ cost, int only_big) {
   const int lane = threadIdx.x & 31;
   const size_t npix = (size_t)g.ow * g.oh;
   const size_t p0 = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
@@ -305,8 +306,9 @@ __global__ void __launch_bounds__(256) sgm_cost_kernel(const unsigned long long*
   uint4 mq = make_uint4(0xffff0000u, 0xffffu, 0u, 0u);
   unsigned long long l = 0;
   int br = 0, bc = 0;
+  if (mine < npix) mq = __ldg(reinterpret_cast<const uint4*>(meta) + mine);
+  if (only_big && !__any_sync(0xffffffffu, (mq.w >> 8) > 32u)) return;
   if (mine < npix) {
-    mq = __ldg(reinterpret_cast<const uint4*>(meta) + mine);
     const int c = (int)(mine % g.ow), r = (int)(mine / g.ow);
     br = r + g.min_row - g.hk; bc = c + g.min_col - g.hk;
     l = lc[(size_t)br * g.clw + bc];
@@ -336,6 +338,49 @@ __global__ void __launch_bounds__(256) sgm_cost_kernel(const unsigned long long*
 #pragma unroll
     for (int u = 0; u < 4; ++u) if (ok[u]) cost[dst[u]] = (sgm_cost_t)__popcll(v[u]);
   }
+}
+
+// The common case (every pixel of the warp has <= 32 entries, e.g. the 5x5 boxes of a pyramid level): lane = pixel.  A lane
+// walks its own box (the loads of neighbouring lanes fall on neighbouring census words), the costs are staged in shared
+// memory at the offsets they have in the ragged volume -- the 32 pixels of a warp own ONE contiguous byte range of it --
+// and the range goes out with aligned 4-byte stores.  ~2.7x fewer instructions than the walk above.
+__global__ void __launch_bounds__(256) sgm_cost_lanes_kernel(const unsigned long long* __restrict__ lc, const unsigned long long* __restrict__ rc,
+                                                             const SgmMeta* __restrict__ meta, SgmGeom g, sgm_cost_t* __restrict__ cost) {
+  __shared__ __align__(16) unsigned char stage[8][1040];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t npix = (size_t)g.ow * g.oh;
+  const size_t p0 = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  if (p0 >= npix) return;
+  const size_t mine = p0 + lane;
+  uint4 mq = make_uint4(0xffff0000u, 0xffffu, 0u, 0u);
+  if (mine < npix) mq = __ldg(reinterpret_cast<const uint4*>(meta) + mine);
+  const unsigned n = mine < npix ? (mq.w >> 8) : 0u;
+  if (__any_sync(0xffffffffu, n > 32u)) return;                          // sgm_cost_kernel(only_big) takes this warp
+  const unsigned st0 = __shfl_sync(0xffffffffu, mq.z, 0);                 // pixel p0 always exists
+  unsigned end = n ? mq.z + n : st0;
+  for (int o = 16; o > 0; o >>= 1) end = max(end, __shfl_xor_sync(0xffffffffu, end, o));
+  const unsigned a = st0 & 3u, total = end - st0;                         // <= 1024 bytes
+  unsigned char* s = stage[warp];
+  if (n) {
+    const int c = (int)(mine % g.ow), r = (int)(mine / g.ow);
+    const int br = r + g.min_row - g.hk, bc = c + g.min_col - g.hk;
+    const unsigned long long l = lc[(size_t)br * g.clw + bc];
+    const int b0 = (short)(mq.x & 0xffff), b1 = (short)(mq.x >> 16), b2 = (short)(mq.y & 0xffff);
+    const int w = max(b2 - b0 + 1, 1);
+    const unsigned long long* rrow = rc + (size_t)(br + b1) * g.crw + (bc + b0);
+    unsigned char* d = s + a + (mq.z - st0);
+    int x = 0;
+    for (unsigned e = 0; e < n; ++e) {
+      d[e] = (unsigned char)__popcll(l ^ rrow[x]);
+      if (++x == w) { x = 0; rrow += g.crw; }
+    }
+  }
+  __syncwarp();
+  unsigned char* gbase = reinterpret_cast<unsigned char*>(cost) + (st0 - a);      // 4-byte aligned (the volume is, and st0 - a is)
+  const unsigned nb = a + total, w_lo = a ? 1u : 0u, w_hi = nb >> 2;
+  for (unsigned i = w_lo + lane; i < w_hi; i += 32) reinterpret_cast<unsigned*>(gbase)[i] = reinterpret_cast<const unsigned*>(s)[i];
+  if (a) for (unsigned b = a + lane; b < min(4u, nb); b += 32) gbase[b] = s[b];                   // head of a partial first word
+  for (unsigned b = max(w_hi << 2, w_lo << 2) + lane; b < nb; b += 32) gbase[b] = s[b];          // tail
 }
 
 // ---- create_disparity_view / select_best_disparity (SGM.cc:1159-1346) + create_disparity_view_subpixel (:1402-1614) ----
@@ -729,7 +774,13 @@ int sgm_run(const SgmArgs& a, Arena& /*callers_arena*/, cudaStream_t st) {
     VWB_CUDA(cudaMemsetAsync(parts[k], 0, 64 * sizeof(sgm_accum_t), st));
     parts[k] += 64;
   }
-  sgm_cost_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(lc, rc, meta, g, cost);
+  static_assert(sizeof(sgm_cost_t) == 1, "the staged copy moves bytes");
+  const int lanes_path = getenv("VWB200_SGM_COST_OLD") ? 0 : 1;
+  if (lanes_path) {
+    sgm_cost_lanes_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(lc, rc, meta, g, cost);
+    VWB_LAUNCH_CHECK();
+  }
+  sgm_cost_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(lc, rc, meta, g, cost, lanes_path);
   VWB_LAUNCH_CHECK();
   VWB_CUDA(cudaStreamSynchronize(st));                                  // max_n
   if (a.use_mgm) {
