@@ -450,17 +450,40 @@ __global__ void __launch_bounds__(256) sgm_sum4_kernel(uint4* __restrict__ a0, c
 
 // accum = the first partial volume (it receives the totals of the pixels that need them re-read: ties, sub-pixel), a1..a3 =
 // the other partial volumes of the concurrent directions (NULL: accum already holds the total)
+// staged != 0 (with a1..a3): a warp's 32 consecutive pixels own one contiguous range of the ragged volumes; when every one of
+// them has <= 32 entries the warp adds the four partial volumes with coalesced word loads into shared memory and the
+// winner / sub-pixel stages read the totals from there (nothing is written back unless a pixel needs the tie smoothing).
 __global__ void __launch_bounds__(128) sgm_wta_kernel(sgm_accum_t* __restrict__ accum, const sgm_accum_t* __restrict__ a1,
                                                       const sgm_accum_t* __restrict__ a2, const sgm_accum_t* __restrict__ a3,
                                                       sgm_accum_t* __restrict__ scratch,
                                                       const SgmMeta* __restrict__ meta, SgmGeom g, vwb200_dispi* __restrict__ out,
-                                                      ptrdiff_t opitch, int want_sub, int mode, float* __restrict__ out_sub, ptrdiff_t sub_pitch) {
+                                                      ptrdiff_t opitch, int want_sub, int mode, float* __restrict__ out_sub, ptrdiff_t sub_pitch,
+                                                      int staged) {
+  __shared__ __align__(16) sgm_accum_t tot[4][1024 + 8];
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= (size_t)g.ow * g.oh) return;
+  const size_t npix = (size_t)g.ow * g.oh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4 mq = make_uint4(0xffff0000u, 0xffffu, 0u, 0u);
+  if (pix < npix) mq = __ldg(reinterpret_cast<const uint4*>(meta) + pix);
+  const int num = pix < npix ? (int)(mq.w >> 8) : 0;
+  const sgm_accum_t* tot_vec = nullptr;                                 // != NULL: this pixel's totals in shared memory
+  if (staged && a1 && !__any_sync(0xffffffffu, num > 32)) {
+    const unsigned st0 = __shfl_sync(0xffffffffu, mq.z, 0);              // the warp's first pixel exists (pix - lane < npix)
+    unsigned end = num ? mq.z + (unsigned)num : st0;
+    for (int o = 16; o > 0; o >>= 1) end = max(end, __shfl_xor_sync(0xffffffffu, end, o));
+    const unsigned a = st0 & 1u, nw = (a + (end - st0) + 1) >> 1;       // words from the even entry st0 - a; <= 513
+    const unsigned* w0 = reinterpret_cast<const unsigned*>(accum + (st0 - a));
+    const unsigned* w1 = reinterpret_cast<const unsigned*>(a1 + (st0 - a));
+    const unsigned* w2 = reinterpret_cast<const unsigned*>(a2 + (st0 - a));
+    const unsigned* w3 = reinterpret_cast<const unsigned*>(a3 + (st0 - a));
+    unsigned* t = reinterpret_cast<unsigned*>(tot[warp]);
+    for (unsigned i = lane; i < nw; i += 32) t[i] = __vadd2(__vadd2(w0[i], w1[i]), __vadd2(w2[i], w3[i]));   // uint16 wrapping sums
+    __syncwarp();
+    tot_vec = tot[warp] + a + (mq.z - st0);
+  }
+  if (pix >= npix) return;
   const int oi = (int)(pix % g.ow), oj = (int)(pix / g.ow);
-  const uint4 mq = __ldg(reinterpret_cast<const uint4*>(meta) + pix);
   const int b0 = (short)(mq.x & 0xffff), b1 = (short)(mq.x >> 16), b2 = (short)(mq.y & 0xffff), b3 = (short)(mq.y >> 16);
-  const int num = (int)(mq.w >> 8);
   vwb200_dispi o;
   float* f = want_sub ? out_sub + (ptrdiff_t)oj * sub_pitch + 3 * oi : nullptr;
   if (num == 0) {                                                       // never valid (:1317-1321)
@@ -474,10 +497,10 @@ __global__ void __launch_bounds__(128) sgm_wta_kernel(sgm_accum_t* __restrict__ 
   const int width = b2 - b0 + 1, height = b3 - b1 + 1;
   int min_count = 0, min_index = 0;
   unsigned min_val = 65535;
-  const bool parts = a1 != nullptr;
+  const bool parts = a1 != nullptr && !tot_vec;
   const bool need_total = parts && want_sub && mode != 0;              // the sub-pixel stage re-reads neighbours of the winner
   for (int i = 0; i < num; ++i) {
-    unsigned v = accum_vec[i];
+    unsigned v = tot_vec ? tot_vec[i] : accum_vec[i];
     if (parts) {                                                        // uint16 wrapping sum, like the reference's in-place adds
       v = (v + a1[mq.z + i] + a2[mq.z + i] + a3[mq.z + i]) & 0xffffu;
       if (need_total) accum_vec[i] = (sgm_accum_t)v;
@@ -485,7 +508,9 @@ __global__ void __launch_bounds__(128) sgm_wta_kernel(sgm_accum_t* __restrict__ 
     if (v == min_val) ++min_count;
     if (v < min_val) { min_index = i; min_val = v; min_count = 1; }
   }
+  bool in_global = !tot_vec;                                            // where the totals of this pixel are
   if (min_count > 1) {                                                  // tie smoothing (:1196-1288), rare
+    if (tot_vec) { for (int i = 0; i < num; ++i) accum_vec[i] = tot_vec[i]; in_global = true; }
     if (parts && !need_total)
       for (int i = 0; i < num; ++i) accum_vec[i] = (sgm_accum_t)((accum_vec[i] + a1[mq.z + i] + a2[mq.z + i] + a3[mq.z + i]) & 0xffffu);
     for (int i = 0; i < num; ++i) buffer[i] = accum_vec[i];
@@ -533,7 +558,7 @@ __global__ void __launch_bounds__(128) sgm_wta_kernel(sgm_accum_t* __restrict__ 
   if (dx == b2) { x_right = 0; rb = true; }
   if (dy == b1) { y_up = 0; tb = true; }
   if (dy == b3) { y_down = 0; bb = true; }
-  const sgm_accum_t* av = accum_vec;
+  const sgm_accum_t* av = in_global ? accum_vec : tot_vec;
   double ddx, ddy;
   if (mode == 1) {                                                      // SUBPIXEL_PARABOLA (:1566-1576)
     double z[9];
@@ -789,14 +814,16 @@ int sgm_run(const SgmArgs& a, Arena& /*callers_arena*/, cudaStream_t st) {
   } else {
     VWB_TRY(sgm_paths_launch(meta, cost, parts, naccum, g, maxes[0], maxes[1], maxes[2], ar, st));
   }
-  if (naccum == 4) {
+  const bool fused_wta = naccum == 4 && maxes[0] <= 32 && !getenv("VWB200_SGM_WTA_UNFUSED");   // every pixel has <= 32 entries
+  if (naccum == 4 && !fused_wta) {
     const size_t nvec = ((size_t)total + 7) / 8;              // the volumes are 16-byte aligned and padded
     sgm_sum4_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<uint4*>(accum), reinterpret_cast<const uint4*>(parts[1]),
                                              reinterpret_cast<const uint4*>(parts[2]), reinterpret_cast<const uint4*>(parts[3]), nvec);
     VWB_LAUNCH_CHECK();
   }
-  sgm_wta_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, nullptr, nullptr, nullptr, scratch, meta, g, a.out, a.opitch,
-                                                                 a.out_sub != nullptr, a.subpixel_mode, a.out_sub, a.sub_pitch);
+  sgm_wta_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(accum, fused_wta ? parts[1] : nullptr, fused_wta ? parts[2] : nullptr,
+                                                                 fused_wta ? parts[3] : nullptr, scratch, meta, g, a.out, a.opitch,
+                                                                 a.out_sub != nullptr, a.subpixel_mode, a.out_sub, a.sub_pitch, fused_wta ? 1 : 0);
   VWB_LAUNCH_CHECK();
   return VWB200_OK;
 }
