@@ -88,3 +88,21 @@ def test_c_abi_plan_and_single_rank_comm():
     buf = (C.c_float * 16)()
     assert api.lib().vwb200_shard_exchange_halos(comm._h, C.byref(cp), buf, 4, 4, buf, 4, 4, None) == 0
     comm.close()
+
+
+def test_view_tile_rows_cover_the_raster_and_margins_reach_far_enough():
+    """config 3 over N GPUs (bench.py cfg3_sharded): tile rows split over the ranks with no collective"""
+    from visionworkbench_b200 import sharding
+    for rows, tile, world in [(8192, 1024, 1), (8192, 1024, 2), (8192, 1024, 8), (8192, 1024, 3), (5000, 1024, 4), (1024, 1024, 4)]:
+        cover = []
+        for r in range(world):
+            y0, y1, top, bot = sharding.view_rows(r, world, rows, tile, levels=5, kernel=15, search_rows=64)
+            assert 0 <= y0 <= y1 <= rows
+            assert y0 % tile == 0 and (y1 % tile == 0 or y1 == rows)
+            # the rows a tile of this rank reads: bbox grown by half_kernel * 2^levels (pyramid padding) and the search rows
+            assert top == min(7 * 32 + 64, y0) and bot == min(7 * 32 + 64, rows - y1)
+            cover.append((y0, y1))
+        assert cover[0][0] == 0 and cover[-1][1] == rows
+        assert all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+        sizes = [(b - a + tile - 1) // tile for a, b in cover]
+        assert max(sizes) - min(sizes) <= 1                   # balanced to one tile row

@@ -127,3 +127,18 @@ def exchange_halos(p, left_band, right_band):
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return (p.recv_left * left_band.shape[1] + p.recv_right * right_band.shape[1]) * left_band.element_size()
+
+
+def view_rows(rank, world, rows, tile, levels, kernel, search_rows):
+    """Tile-row split of a PyramidCorrelationView job (SURVEY 8e, config 3 over N GPUs): the tiles are the units, a rank takes
+    a contiguous run of tile rows and needs NO data from its neighbours at run time if it holds, besides the rows of its tiles,
+    the margin a tile reaches above and below: the kernel padding at the coarsest level, (kernel // 2) * 2^levels rows
+    (CorrelationView.cc:89-97), plus the search rows.  Returns (y0, y1, top, bottom): the output rows [y0, y1) of this rank and
+    the margins clipped to the raster."""
+    ntr = (rows + tile - 1) // tile                       # tile rows of the job
+    per, extra = divmod(ntr, world)
+    t0 = rank * per + min(rank, extra)
+    t1 = t0 + per + (1 if rank < extra else 0)
+    y0, y1 = min(t0 * tile, rows), min(t1 * tile, rows)
+    reach = (kernel // 2) * (1 << levels) + search_rows
+    return y0, y1, min(reach, y0), min(reach, rows - y1)
